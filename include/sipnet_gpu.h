@@ -1,0 +1,351 @@
+/*
+ * sipnet_gpu.h -- C ABI of the B200 (sm_100a) batched SIPNET integrator.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the body of the
+ * run loop in runModelOutput() (reference src/sipnet/sipnet.c:1963-1982), i.e.
+ *
+ *     setupModel(); setupEvents();
+ *     while (climate != NULL) { updateState(); outputState(...); ... }
+ *
+ * batched over many (site x parameter-ensemble member) runs.  Everything else
+ * of the reference (CLI, sipnet.in, readers, text writers) stays host C and
+ * talks to the device only through the entry points below.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no CUDA or torch types in signatures
+ *  - every entry point returns 0 on success or one of the reference's own exit
+ *    codes (reference src/common/exitCodes.h:16-27); the library never calls
+ *    exit()
+ *  - the caller owns every host array passed in; init copies what it needs
+ *  - the handle owns all device memory
+ *  - there is NO CPU fallback: if no CUDA device is usable init fails with
+ *    SIPNET_GPU_ERR_NO_DEVICE
+ */
+#ifndef SIPNET_GPU_H
+#define SIPNET_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIPNET_GPU_ABI_VERSION 1
+
+/* ---- return codes: reference src/common/exitCodes.h:16-27 ---------------- */
+#define SIPNET_GPU_OK 0
+#define SIPNET_GPU_ERR_FAILURE 1
+#define SIPNET_GPU_ERR_BAD_PARAMETER_VALUE 3 /* e.g. non-positive step length, events.c:460 */
+#define SIPNET_GPU_ERR_UNKNOWN_EVENT 4 /* unknown type / irrigation method, events.c:498,736 */
+#define SIPNET_GPU_ERR_INPUT_FILE 5 /* event without climate record, events.c:476-481 */
+#define SIPNET_GPU_ERR_FILE_OPEN 6
+#define SIPNET_GPU_ERR_INTERNAL 7 /* mean-NPP ring overflow, sipnet.c:1562-1569 */
+#define SIPNET_GPU_ERR_BAD_CLI 8
+#define SIPNET_GPU_ERR_BAD_RESTART 9
+/* library specific (outside the reference's range) */
+#define SIPNET_GPU_ERR_NO_DEVICE 100 /* no usable CUDA device / CUDA runtime error */
+#define SIPNET_GPU_ERR_BAD_ARGUMENT 101 /* NULL pointer, size mismatch, bad step range */
+
+/* ---- model flags: struct Context, reference src/common/context.h:45-56 --- */
+#define SIPNET_GPU_NFLAGS 12
+typedef struct sipnet_gpu_flags {
+  int32_t events;
+  int32_t gdd;
+  int32_t growthResp;
+  int32_t leafWater;
+  int32_t litterPool;
+  int32_t snow; /* no arithmetic effect in the reference either (SURVEY 8a trap 6) */
+  int32_t soilPhenol;
+  int32_t waterHResp;
+  int32_t nitrogenCycle;
+  int32_t anaerobic;
+  int32_t flooding;
+  int32_t carbonSaturation;
+} sipnet_gpu_flags;
+
+/* ---- parameters: struct Parameters, reference src/sipnet/state.h:66-408 ---
+ * Same order as the struct, so a maintainer can pass `(double *)&params`.
+ * Values are the ones left in `params` by readParamData() (sipnet.c:290-427,
+ * i.e. after the TINY floors) and BEFORE setupModel(); the library applies
+ * setupModel()'s unit changes / derived values itself (sipnet.c:1858-1951).
+ * psnTMax and coarseRootAllocation are derived (input value ignored).
+ */
+#define SIPNET_GPU_PARAM_LIST(X)                                               \
+  X(plantWoodInit) X(laiInit) X(soilInit) X(soilWFracInit) X(aMax)             \
+  X(aMaxFrac) X(baseFolRespFrac) X(psnTMin) X(psnTOpt) X(psnTMax)              \
+  X(dVpdSlope) X(dVpdExp) X(halfSatPar) X(attenuation) X(leafOnDay)            \
+  X(leafOffDay) X(gddLeafOn) X(baseVegResp) X(vegRespQ10) X(baseSoilResp)      \
+  X(soilRespQ10) X(waterRemoveFrac) X(wueConst) X(soilWHC) X(leafCSpWt)        \
+  X(cFracLeaf) X(woodTurnoverRate) X(waterDrainFrac) X(litterInit)             \
+  X(snowInit) X(frozenSoilEff) X(immedEvapFrac) X(fastFlowFrac) X(snowMelt)    \
+  X(rdConst) X(rSoilConst1) X(rSoilConst2) X(leafAllocation)                   \
+  X(leafTurnoverRate) X(frozenSoilFolREff) X(frozenSoilThreshold)              \
+  X(litterBreakdownRate) X(fracLitterRespired) X(fineRootFrac)                 \
+  X(coarseRootFrac) X(woodAllocation) X(fineRootAllocation)                    \
+  X(coarseRootAllocation) X(fineRootTurnoverRate) X(coarseRootTurnoverRate)    \
+  X(baseFineRootResp) X(baseCoarseRootResp) X(fineRootQ10) X(coarseRootQ10)    \
+  X(soilTempLeafOn) X(leafGrowth) X(fracLeafFall) X(growthRespFrac)            \
+  X(soilRespMoistEffect) X(leafPoolDepth) X(minNInit) X(soilOrgNInit)          \
+  X(litterOrgNInit) X(plantStorageNInit) X(nVolatilizationFrac)                \
+  X(nLeachingFrac) X(leafCN) X(woodCN) X(fineRootCN) X(kCN)                    \
+  X(nFixationFracMax) X(halfNFixationMax) X(leafOnReallocFrac)                 \
+  X(leafNResorptionFrac) X(fAnoxia) X(anaerobicDecompRate)                     \
+  X(anaerobicTransExp) X(soilMethaneRate) X(litterMethaneRate)                 \
+  X(soilCSaturation)
+
+enum sipnet_gpu_param {
+#define SIPNET_GPU_X(name) SIPNET_P_##name,
+  SIPNET_GPU_PARAM_LIST(SIPNET_GPU_X)
+#undef SIPNET_GPU_X
+      SIPNET_GPU_NPARAMS /* = 80 = sizeof(Params)/sizeof(double), state.h:410 */
+};
+
+/* ---- events: reference src/sipnet/events.h:13-83 -------------------------- */
+enum sipnet_gpu_event_type { /* same numeric values as event_type_t, events.h:13-23 */
+  SIPNET_EV_FERTILIZATION = 0, /* p = orgN, orgC, minN */
+  SIPNET_EV_HARVEST = 1,       /* p = fracRemovedAbove, fracRemovedBelow, fracTransferredAbove, fracTransferredBelow */
+  SIPNET_EV_IRRIGATION = 2,    /* p = amountAdded; method 0 canopy, 1 soil */
+  SIPNET_EV_PLANTING = 3,      /* p = leafC, woodC, fineRootC, coarseRootC */
+  SIPNET_EV_TILLAGE = 4,       /* p = tillageEffect */
+  SIPNET_EV_LEAFON = 5,
+  SIPNET_EV_LEAFOFF = 6,
+  SIPNET_EV_PLANTDEATH = 7     /* computed only; never an input */
+};
+
+typedef struct sipnet_gpu_event {
+  int32_t year;
+  int32_t day;
+  int32_t type;   /* enum sipnet_gpu_event_type */
+  int32_t method; /* irrigation only */
+  double p[4];
+} sipnet_gpu_event;
+
+/* ---- one site's forcing + event schedule ----------------------------------
+ * Climate arrays hold what readClimData() leaves in the ClimateNode list
+ * (reference sipnet.c:205-238, state.h:12-49): par already per day, precip in
+ * cm, vpd/vpdSoil/vPress in kPa with the TINY floors, gdd per step.
+ * Events are in events.in file order (ascending year, day), as returned by
+ * readEventData() (events.h:109).
+ */
+typedef struct sipnet_gpu_site {
+  int64_t nsteps;
+  const int32_t *year;
+  const int32_t *day;
+  const double *time;
+  const double *length;
+  const double *tair;
+  const double *tsoil;
+  const double *par;
+  const double *precip;
+  const double *vpd;
+  const double *vpdSoil;
+  const double *vPress;
+  const double *wspd;
+  const double *gdd;
+  int64_t nevents;
+  const sipnet_gpu_event *events;
+  /* optional NEE observations for the log-likelihood output (per step, NaN =
+   * no observation); may be NULL */
+  const double *nee_obs;
+} sipnet_gpu_site;
+
+/* ---- per-step output vector: the columns of outputState(), sipnet.c:453-473 */
+enum sipnet_gpu_out_col {
+  SIPNET_O_plantWoodC = 0, /* getTotalWoodC() = plantWoodC + plantCAccountingDelta */
+  SIPNET_O_plantLeafC,
+  SIPNET_O_woodCreation,
+  SIPNET_O_soilC,
+  SIPNET_O_coarseRootC,
+  SIPNET_O_fineRootC,
+  SIPNET_O_litterC,
+  SIPNET_O_soilWater,
+  SIPNET_O_soilWetnessFrac,
+  SIPNET_O_snow,
+  SIPNET_O_npp,
+  SIPNET_O_nee,
+  SIPNET_O_cumNEE,
+  SIPNET_O_gpp,
+  SIPNET_O_rAboveground,
+  SIPNET_O_rSoil,
+  SIPNET_O_rRoot,
+  SIPNET_O_ra,
+  SIPNET_O_rh,
+  SIPNET_O_rtot,
+  SIPNET_O_evapotranspiration,
+  SIPNET_O_fluxestranspiration,
+  SIPNET_O_minN,
+  SIPNET_O_soilOrgN,
+  SIPNET_O_litterN,
+  SIPNET_O_plantStorageN,
+  SIPNET_O_n2o,
+  SIPNET_O_nLeaching,
+  SIPNET_O_nFixation,
+  SIPNET_O_nUptake,
+  SIPNET_O_ch4,
+  SIPNET_O_nppStorage, /* envi.plantCAccountingDelta */
+  SIPNET_GPU_NOUT      /* = 32 */
+};
+
+/* Debug dump: every field the reference's --debug-log writes, in file order
+ * (debug_log.c:51-170): 13 envi, 56 fluxes, 33 trackers (lastYear as double),
+ * 3 phenology trackers, isAlive. */
+#define SIPNET_GPU_NDEBUG_ENVI 13
+#define SIPNET_GPU_NDEBUG_FLUX 56
+#define SIPNET_GPU_NDEBUG_TRACK 33
+#define SIPNET_GPU_NDEBUG (13 + 56 + 33 + 3 + 1)
+
+/* ---- computed/applied event records (for the host-side events.out writer) --
+ * One record per events.out row (events.c:379-402): the (up to 10) deltas the
+ * reference prints, in print order. */
+#define SIPNET_GPU_EVREC_NVAL 10
+typedef struct sipnet_gpu_event_record {
+  int32_t step;   /* index into the site's climate arrays */
+  int32_t type;   /* enum sipnet_gpu_event_type */
+  int32_t nval;   /* number of valid entries in val[] */
+  int32_t variant; /* leafon: 0 = computed (leafOnCreation), 1 = from events.in (eventLeafOnCreation) */
+  double val[SIPNET_GPU_EVREC_NVAL];
+} sipnet_gpu_event_record;
+
+/* ---- output selection (bit mask) ------------------------------------------ */
+#define SIPNET_GPU_OUT_FULL 0x01u    /* [NOUT][steps][M] doubles per run range */
+#define SIPNET_GPU_OUT_DEBUG 0x02u   /* [NDEBUG][steps][M] doubles (validation) */
+#define SIPNET_GPU_OUT_LOGLIK 0x04u  /* per-member Gaussian NEE log-likelihood */
+#define SIPNET_GPU_OUT_MOMENTS 0x08u /* per site, per step ensemble mean+variance of summary_cols */
+#define SIPNET_GPU_OUT_QUANTILES 0x10u /* per site, per step ensemble quantiles of summary_cols */
+#define SIPNET_GPU_OUT_EVENTS 0x20u  /* per-member event records */
+
+/* ---- arithmetic build selection -------------------------------------------- */
+#define SIPNET_GPU_MATH_VALIDATION 0 /* -fmad=false, IEEE div: mirrors the reference's gcc -O0 x86-64 arithmetic */
+#define SIPNET_GPU_MATH_FAST 1       /* -fmad=true perf build; re-gated at 1e-10 */
+
+typedef struct sipnet_gpu_config {
+  int32_t abi_version; /* SIPNET_GPU_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal */
+  sipnet_gpu_flags flags;
+
+  int64_t nsites;
+  const sipnet_gpu_site *sites;
+
+  int64_t nmembers;
+  const int32_t *member_site; /* [nmembers], non-decreasing; NULL => all members on site 0 */
+  const double *params;       /* SoA [SIPNET_GPU_NPARAMS][params_ld] */
+  int64_t params_ld;          /* leading dimension (>= nmembers) */
+
+  uint32_t outputs;           /* SIPNET_GPU_OUT_* mask */
+  int32_t math;               /* SIPNET_GPU_MATH_* */
+  int64_t out_steps_capacity; /* max steps per run() kept for FULL/DEBUG/summary gathers; 0 => max site nsteps */
+
+  /* summaries */
+  int32_t n_summary_cols;
+  const int32_t *summary_cols; /* enum sipnet_gpu_out_col values */
+  int32_t n_quantiles;
+  const double *quantiles;     /* probabilities in [0,1] */
+  double nee_sigma;            /* log-likelihood observation sigma (> 0) */
+
+  int32_t max_event_records;   /* per member, for SIPNET_GPU_OUT_EVENTS */
+  int32_t block_threads;       /* 0 => library default */
+  void *stream;                /* cudaStream_t to launch on; NULL => library-owned stream */
+} sipnet_gpu_config;
+
+typedef struct sipnet_gpu_handle sipnet_gpu_handle;
+
+/* What gather() can return. */
+enum sipnet_gpu_gather_what {
+  SIPNET_GPU_GATHER_FULL = 1,     /* double [NOUT][n][M], n = steps of the last run() */
+  SIPNET_GPU_GATHER_DEBUG = 2,    /* double [NDEBUG][n][M] */
+  SIPNET_GPU_GATHER_LOGLIK = 3,   /* double [M] */
+  SIPNET_GPU_GATHER_STATUS = 4,   /* uint32 [M] status bits (SIPNET_GPU_ST_*) */
+  SIPNET_GPU_GATHER_STATE = 5,    /* double [SIPNET_GPU_NSTATE][M] carried state (restart-shaped) */
+  SIPNET_GPU_GATHER_MEAN = 6,     /* double [nsites][n_summary_cols][n] */
+  SIPNET_GPU_GATHER_VARIANCE = 7, /* double [nsites][n_summary_cols][n] (population variance) */
+  SIPNET_GPU_GATHER_QUANTILES = 8, /* double [nsites][n_summary_cols][n_quantiles][n] */
+  SIPNET_GPU_GATHER_EVENT_COUNTS = 9, /* int32 [M] */
+  SIPNET_GPU_GATHER_EVENT_RECORDS = 10, /* sipnet_gpu_event_record [M][max_event_records] */
+  SIPNET_GPU_GATHER_LOGLIK_N = 11 /* double [M]: number of observations that entered the likelihood */
+};
+
+/* per-member status bits (instead of the reference's exit()) */
+#define SIPNET_GPU_ST_BAD_ALLOCATION 0x1u /* ensureAllocation() failed, sipnet.c:1117-1122 (exit 3) */
+#define SIPNET_GPU_ST_RING_OVERFLOW 0x2u  /* mean-NPP tracker out of space, sipnet.c:1562 (exit 7) */
+#define SIPNET_GPU_ST_CLAMPED 0x4u        /* a stock went below -EPS and was clamped (warning, sipnet.c:1349) */
+#define SIPNET_GPU_ST_DIED 0x8u           /* plant mortality happened at least once (sipnet.c:1702) */
+#define SIPNET_GPU_ST_EVREC_OVERFLOW 0x10u /* more event records than max_event_records */
+#define SIPNET_GPU_ST_NONFINITE 0x20u     /* a pool became NaN/Inf */
+
+/* carried state rows for SIPNET_GPU_GATHER_STATE (restart.c:148-308 field list) */
+enum sipnet_gpu_state_row {
+  SIPNET_S_plantWoodC = 0, SIPNET_S_plantLeafC, SIPNET_S_soilC, SIPNET_S_soilWater,
+  SIPNET_S_litterC, SIPNET_S_snow, SIPNET_S_coarseRootC, SIPNET_S_fineRootC,
+  SIPNET_S_minN, SIPNET_S_soilOrgN, SIPNET_S_litterN, SIPNET_S_plantStorageN,
+  SIPNET_S_plantCAccountingDelta,
+  SIPNET_S_gdd, SIPNET_S_soilWetnessFrac, SIPNET_S_yearlyGpp, SIPNET_S_yearlyRtot, SIPNET_S_yearlyRa,
+  SIPNET_S_yearlyRh, SIPNET_S_yearlyNpp, SIPNET_S_yearlyNee, SIPNET_S_yearlyLitter,
+  SIPNET_S_totGpp, SIPNET_S_totRtot, SIPNET_S_totRa, SIPNET_S_totRh, SIPNET_S_totNpp, SIPNET_S_totNee,
+  SIPNET_S_trackersLastYear, SIPNET_S_didLeafGrowth, SIPNET_S_didLeafFall, SIPNET_S_phenLastYear,
+  SIPNET_S_dTillMod, SIPNET_S_meanSum, SIPNET_S_meanStart, SIPNET_S_meanLast,
+  SIPNET_GPU_NSTATE
+};
+
+/*
+ * sipnet_gpu_init -- replaces initModel()+initEvents() hand-off and
+ * setupModel()/setupEvents() (reference sipnet.h:26,35; events.h:173,178;
+ * sipnet.c:1858-1951; events.c:435).  Validates the configuration (event
+ * ordering / climate correspondence as processEvents() would, events.c:471-481,
+ * step lengths events.c:460), binds every event to its step, uploads forcing,
+ * parameters and schedules, and runs setupModel() for every member on the
+ * device.
+ */
+int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle **out);
+
+/*
+ * sipnet_gpu_run -- replaces the `while (climate != NULL) { updateState(); ...}`
+ * loop (reference sipnet.c:1969-1982) for steps [step_begin, step_end) of
+ * every member.  step_begin must equal the number of steps already run
+ * (contiguous segments, like the reference's restart segments,
+ * restart.c / testRestartMVP.c:253-297).  Asynchronous: returns after the
+ * launch; gather() (or sync()) waits.
+ */
+int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end);
+
+/*
+ * sipnet_gpu_gather -- replaces the per-step side outputs of the loop
+ * (outputState sipnet.c:453, writeEventOut events.c:404, outputDebugState
+ * debug_log.c:277) by copying device results into a caller buffer.
+ * `bytes` must be exactly the size documented at enum sipnet_gpu_gather_what.
+ */
+int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size_t bytes);
+
+/* Size in bytes gather(what) will write for the last run range. */
+size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what);
+
+/* Block until all queued device work of this handle has finished. */
+int sipnet_gpu_sync(sipnet_gpu_handle *h);
+
+/* Reset every member to its post-setupModel() state (step counter back to 0). */
+int sipnet_gpu_reset(sipnet_gpu_handle *h);
+
+/* Replaces cleanupModel() (sipnet.c:2012-2023) for device-side resources. */
+void sipnet_gpu_destroy(sipnet_gpu_handle *h);
+
+/* ---- introspection / measurement helpers ----------------------------------- */
+/* Device time (ms, CUDA events on the launching stream) of the step kernel(s)
+ * of the most recent run(); waits for completion. */
+int sipnet_gpu_last_run_ms(sipnet_gpu_handle *h, float *ms);
+/* Number of kernels this library launched since init (all kinds). */
+int64_t sipnet_gpu_launch_count(const sipnet_gpu_handle *h);
+/* Device pointer of a gatherable buffer (for zero-copy collectives); NULL if absent. */
+void *sipnet_gpu_device_ptr(sipnet_gpu_handle *h, int what);
+/* Pinned host allocation helpers so gathers run at full PCIe rate. */
+void *sipnet_gpu_host_alloc(size_t bytes);
+void sipnet_gpu_host_free(void *p);
+const char *sipnet_gpu_last_error(void);
+int sipnet_gpu_abi_version(void);
+/* FP64 FMA issue-rate probe: runs a register-resident DFMA chain on every SM and
+ * returns achieved TFLOP/s (the FP64 roofline denominator; SURVEY 7 hard part 7). */
+int sipnet_gpu_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIPNET_GPU_H */

@@ -1,0 +1,321 @@
+"""Host-side Python view of the C ABI (include/sipnet_gpu.h).
+
+Python is plumbing here: it builds `sipnet_gpu_config` from numpy arrays, calls
+`sipnet_gpu_init / run / gather` through ctypes and hands numpy arrays back.
+All compute happens in the CUDA library; there is no CPU fallback -- if
+libsipnet_gpu.so is missing or no device is usable, these calls raise.
+
+The names mirror the reference interface this path replaces
+(`setupModel`/`updateState`/`outputState`, reference src/sipnet/sipnet.h:26-54).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libsipnet_gpu.so")
+
+
+class SipnetGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sipnet_gpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load libsipnet_gpu.so (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib.sipnet_gpu_init.restype = C.c_int
+    lib.sipnet_gpu_init.argtypes = [C.POINTER(A.Config), C.POINTER(C.c_void_p)]
+    lib.sipnet_gpu_run.restype = C.c_int
+    lib.sipnet_gpu_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.sipnet_gpu_gather.restype = C.c_int
+    lib.sipnet_gpu_gather.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.sipnet_gpu_gather_bytes.restype = C.c_size_t
+    lib.sipnet_gpu_gather_bytes.argtypes = [C.c_void_p, C.c_int]
+    lib.sipnet_gpu_sync.restype = C.c_int
+    lib.sipnet_gpu_sync.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_reset.restype = C.c_int
+    lib.sipnet_gpu_reset.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_destroy.restype = None
+    lib.sipnet_gpu_destroy.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_last_run_ms.restype = C.c_int
+    lib.sipnet_gpu_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.sipnet_gpu_launch_count.restype = C.c_int64
+    lib.sipnet_gpu_launch_count.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_device_ptr.restype = C.c_void_p
+    lib.sipnet_gpu_device_ptr.argtypes = [C.c_void_p, C.c_int]
+    lib.sipnet_gpu_host_alloc.restype = C.c_void_p
+    lib.sipnet_gpu_host_alloc.argtypes = [C.c_size_t]
+    lib.sipnet_gpu_host_free.restype = None
+    lib.sipnet_gpu_host_free.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_last_error.restype = C.c_char_p
+    lib.sipnet_gpu_last_error.argtypes = []
+    lib.sipnet_gpu_abi_version.restype = C.c_int
+    lib.sipnet_gpu_abi_version.argtypes = []
+    lib.sipnet_gpu_measure_fp64_peak.restype = C.c_int
+    lib.sipnet_gpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+@dataclass
+class SiteData:
+    """One site's forcing (post-readClimData units, reference sipnet.c:205-238)
+    and its events.in schedule (file order)."""
+    year: np.ndarray
+    day: np.ndarray
+    clim: dict                      # name -> float64[T] for A.CLIM_COLS
+    events: list = field(default_factory=list)  # (year, day, type, method, p0..p3)
+    nee_obs: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.year = np.ascontiguousarray(self.year, dtype=np.int32)
+        self.day = np.ascontiguousarray(self.day, dtype=np.int32)
+        self.clim = {k: np.ascontiguousarray(self.clim[k], dtype=np.float64)
+                     for k in A.CLIM_COLS}
+        if self.nee_obs is not None:
+            self.nee_obs = np.ascontiguousarray(self.nee_obs, dtype=np.float64)
+
+    @property
+    def nsteps(self) -> int:
+        return int(self.year.shape[0])
+
+    def event_array(self):
+        n = len(self.events)
+        arr = (A.Event * max(n, 1))()
+        for i, ev in enumerate(self.events):
+            y, d, typ, method, *p = ev
+            arr[i].year, arr[i].day, arr[i].type, arr[i].method = int(y), int(d), int(typ), int(method)
+            for k in range(4):
+                arr[i].p[k] = float(p[k]) if k < len(p) else 0.0
+        return arr, n
+
+    def to_struct(self, keep: list) -> A.Site:
+        s = A.Site()
+        s.nsteps = self.nsteps
+        s.year = _ip(self.year)
+        s.day = _ip(self.day)
+        for k in A.CLIM_COLS:
+            setattr(s, k, _dp(self.clim[k]))
+        arr, n = self.event_array()
+        keep.append(arr)
+        s.nevents = n
+        s.events = C.cast(arr, C.POINTER(A.Event))
+        if self.nee_obs is not None:
+            s.nee_obs = _dp(self.nee_obs)
+        return s
+
+
+def flags_struct(flags: dict) -> A.Flags:
+    f = A.Flags()
+    merged = dict(A.DEFAULT_FLAGS)
+    merged.update(flags or {})
+    for n in A.FLAG_NAMES:
+        setattr(f, n, int(merged[n]))
+    return f
+
+
+def flags_array(flags: dict) -> np.ndarray:
+    merged = dict(A.DEFAULT_FLAGS)
+    merged.update(flags or {})
+    return np.array([int(merged[n]) for n in A.FLAG_NAMES], dtype=np.int32)
+
+
+class Ensemble:
+    """A batched SIPNET run on one GPU (wraps a sipnet_gpu_handle)."""
+
+    def __init__(self, sites: Sequence[SiteData], params: np.ndarray,
+                 member_site: Optional[np.ndarray] = None, flags: Optional[dict] = None,
+                 outputs: int = A.OUT_FULL, math: int = A.MATH_VALIDATION,
+                 device: int = 0, out_steps_capacity: int = 0,
+                 summary_cols: Sequence[int] = (), quantiles: Sequence[float] = (),
+                 nee_sigma: float = 1.0, max_event_records: int = 0,
+                 block_threads: int = 0, stream: int = 0, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 2 or params.shape[0] != A.NPARAMS:
+            raise ValueError("params must be float64 [80][M] (struct Parameters order)")
+        self.nmembers = int(params.shape[1])
+        self.sites = list(sites)
+        self.nsites = len(self.sites)
+        self._keep = [params]
+        site_structs = (A.Site * self.nsites)()
+        for i, s in enumerate(self.sites):
+            site_structs[i] = s.to_struct(self._keep)
+        self._keep.append(site_structs)
+        cfg = A.Config()
+        cfg.abi_version = A.ABI_VERSION
+        cfg.device = device
+        cfg.flags = flags_struct(flags)
+        cfg.nsites = self.nsites
+        cfg.sites = C.cast(site_structs, C.POINTER(A.Site))
+        cfg.nmembers = self.nmembers
+        if member_site is not None:
+            ms = np.ascontiguousarray(member_site, dtype=np.int32)
+            self._keep.append(ms)
+            cfg.member_site = _ip(ms)
+            self.member_site = ms
+        else:
+            self.member_site = np.zeros(self.nmembers, dtype=np.int32)
+        cfg.params = _dp(params)
+        cfg.params_ld = self.nmembers
+        cfg.outputs = outputs
+        cfg.math = math
+        cfg.out_steps_capacity = out_steps_capacity
+        sc = np.ascontiguousarray(summary_cols, dtype=np.int32)
+        q = np.ascontiguousarray(quantiles, dtype=np.float64)
+        self._keep += [sc, q]
+        cfg.n_summary_cols = sc.size
+        cfg.summary_cols = _ip(sc) if sc.size else None
+        cfg.n_quantiles = q.size
+        cfg.quantiles = _dp(q) if q.size else None
+        cfg.nee_sigma = nee_sigma
+        cfg.max_event_records = max_event_records
+        cfg.block_threads = block_threads
+        cfg.stream = stream or None
+        self.n_summary_cols = int(sc.size)
+        self.n_quantiles = int(q.size)
+        self.max_event_records = max_event_records
+        self.max_steps = max(s.nsteps for s in self.sites)
+        self.handle = C.c_void_p()
+        rc = self.lib.sipnet_gpu_init(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            self.handle = None
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (0, 0)
+
+    # -- reference: the while(climate) loop, sipnet.c:1969-1982
+    def run(self, step_begin: int = 0, step_end: Optional[int] = None) -> None:
+        if step_end is None:
+            step_end = self.max_steps
+        rc = self.lib.sipnet_gpu_run(self.handle, step_begin, step_end)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (step_begin, step_end)
+
+    def _gather(self, what: int, dtype, shape) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        self.gather_into(what, out)
+        return out
+
+    def gather_into(self, what: int, out: np.ndarray) -> None:
+        rc = self.lib.sipnet_gpu_gather(self.handle, what, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+
+    def gather_raw(self, what: int, ptr: int, nbytes: int) -> None:
+        rc = self.lib.sipnet_gpu_gather(self.handle, what, C.c_void_p(ptr), nbytes)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+
+    @property
+    def nrun(self) -> int:
+        return self.last_range[1] - self.last_range[0]
+
+    def output(self) -> np.ndarray:
+        """[32][n][M] -- outputState() columns for the last run range."""
+        return self._gather(A.GATHER_FULL, np.float64, (A.NOUT, self.nrun, self.nmembers))
+
+    def debug(self) -> np.ndarray:
+        return self._gather(A.GATHER_DEBUG, np.float64, (A.NDEBUG, self.nrun, self.nmembers))
+
+    def loglik(self) -> np.ndarray:
+        return self._gather(A.GATHER_LOGLIK, np.float64, (self.nmembers,))
+
+    def loglik_n(self) -> np.ndarray:
+        return self._gather(A.GATHER_LOGLIK_N, np.float64, (self.nmembers,))
+
+    def status(self) -> np.ndarray:
+        return self._gather(A.GATHER_STATUS, np.uint32, (self.nmembers,))
+
+    def state(self) -> np.ndarray:
+        return self._gather(A.GATHER_STATE, np.float64, (A.NSTATE, self.nmembers))
+
+    def mean(self) -> np.ndarray:
+        return self._gather(A.GATHER_MEAN, np.float64, (self.nsites, self.n_summary_cols, self.nrun))
+
+    def variance(self) -> np.ndarray:
+        return self._gather(A.GATHER_VARIANCE, np.float64, (self.nsites, self.n_summary_cols, self.nrun))
+
+    def quantiles(self) -> np.ndarray:
+        return self._gather(A.GATHER_QUANTILES, np.float64,
+                            (self.nsites, self.n_summary_cols, self.n_quantiles, self.nrun))
+
+    def event_counts(self) -> np.ndarray:
+        return self._gather(A.GATHER_EVENT_COUNTS, np.int32, (self.nmembers,))
+
+    def event_records(self):
+        n = self.nmembers * self.max_event_records
+        buf = (A.EventRecord * n)()
+        rc = self.lib.sipnet_gpu_gather(self.handle, A.GATHER_EVENT_RECORDS, C.cast(buf, C.c_void_p),
+                                        C.sizeof(buf))
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        counts = self.event_counts()
+        return [[buf[m * self.max_event_records + i] for i in range(min(int(counts[m]), self.max_event_records))]
+                for m in range(self.nmembers)]
+
+    def sync(self) -> None:
+        self.lib.sipnet_gpu_sync(self.handle)
+
+    def reset(self) -> None:
+        rc = self.lib.sipnet_gpu_reset(self.handle)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (0, 0)
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        self.lib.sipnet_gpu_last_run_ms(self.handle, C.byref(ms))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.sipnet_gpu_launch_count(self.handle))
+
+    def device_ptr(self, what: int) -> int:
+        return int(self.lib.sipnet_gpu_device_ptr(self.handle, what) or 0)
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.sipnet_gpu_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
