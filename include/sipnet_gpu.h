@@ -325,6 +325,15 @@ int sipnet_gpu_sync(sipnet_gpu_handle *h);
 /* Reset every member to its post-setupModel() state (step counter back to 0). */
 int sipnet_gpu_reset(sipnet_gpu_handle *h);
 
+/*
+ * sipnet_gpu_set_params -- load a new parameter ensemble into an existing
+ * handle (same sites, same member->site map): host->device copy of
+ * params[80][ld], setupModel() derivation, state reset.  This is the per-batch
+ * entry point of an ensemble / MCMC driver that would otherwise re-run
+ * readParamData()+setupModel() per member (sipnet.c:290, 1858).
+ */
+int sipnet_gpu_set_params(sipnet_gpu_handle *h, const double *params, int64_t params_ld);
+
 /* Replaces cleanupModel() (sipnet.c:2012-2023) for device-side resources. */
 void sipnet_gpu_destroy(sipnet_gpu_handle *h);
 
@@ -332,6 +341,11 @@ void sipnet_gpu_destroy(sipnet_gpu_handle *h);
 /* Device time (ms, CUDA events on the launching stream) of the step kernel(s)
  * of the most recent run(); waits for completion. */
 int sipnet_gpu_last_run_ms(sipnet_gpu_handle *h, float *ms);
+/* CUDA-event stopwatch on the handle's stream: start() records an event, stop_ms()
+ * records a second one, waits for it and returns the device time between them
+ * (covers every copy and kernel this handle queued in between). */
+int sipnet_gpu_timer_start(sipnet_gpu_handle *h);
+int sipnet_gpu_timer_stop_ms(sipnet_gpu_handle *h, float *ms);
 /* Number of kernels this library launched since init (all kinds). */
 int64_t sipnet_gpu_launch_count(const sipnet_gpu_handle *h);
 /* Device pointer of a gatherable buffer (for zero-copy collectives); NULL if absent. */

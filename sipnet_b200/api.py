@@ -55,6 +55,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_sync.argtypes = [C.c_void_p]
     lib.sipnet_gpu_reset.restype = C.c_int
     lib.sipnet_gpu_reset.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_set_params.restype = C.c_int
+    lib.sipnet_gpu_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.sipnet_gpu_timer_start.restype = C.c_int
+    lib.sipnet_gpu_timer_start.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_timer_stop_ms.restype = C.c_int
+    lib.sipnet_gpu_timer_stop_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.sipnet_gpu_destroy.restype = None
     lib.sipnet_gpu_destroy.argtypes = [C.c_void_p]
     lib.sipnet_gpu_last_run_ms.restype = C.c_int
@@ -291,6 +297,28 @@ class Ensemble:
         if rc != 0:
             raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
         self.last_range = (0, 0)
+
+    def set_params(self, params, ld: Optional[int] = None) -> None:
+        """Upload a new [80][M] ensemble (numpy array or raw host pointer) and reset."""
+        if isinstance(params, np.ndarray):
+            params = np.ascontiguousarray(params, dtype=np.float64)
+            ptr, ld = params.ctypes.data, params.shape[1]
+        else:
+            ptr = int(params)
+        rc = self.lib.sipnet_gpu_set_params(self.handle, C.c_void_p(ptr), ld)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (0, 0)
+
+    def timer_start(self) -> None:
+        self.lib.sipnet_gpu_timer_start(self.handle)
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        rc = self.lib.sipnet_gpu_timer_stop_ms(self.handle, C.byref(ms))
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        return float(ms.value)
 
     def last_run_ms(self) -> float:
         ms = C.c_float()

@@ -1,0 +1,415 @@
+// sip_kernels.cu -- the fused step kernel (K1) and the setup kernel.
+//
+// Compiled twice by the Makefile into two namespaces of the same library:
+//   -DSIP_NS=val  -fmad=false            (validation arithmetic)
+//   -DSIP_NS=fast -fmad=true -DSIP_FAST_MATH
+//
+// K1 layout: one thread = one ensemble member; a block holds members of ONE
+// site, so forcing and the event schedule are block-uniform.  Per block:
+//   * the members' parameter rows are copied once into a shared-memory tile
+//     [kNParamDev][BLOCK] (conflict-free column access),
+//   * the site's ClimRec stream is staged chunk by chunk into a 2-deep shared
+//     memory ring with cp.async.bulk (TMA 1-D) completing on an mbarrier, so the
+//     copy of chunk i+1 overlaps the arithmetic of chunk i,
+//   * pools / trackers stay in registers for the whole run range and go back to
+//     the SoA state rows once at the end,
+//   * every requested output column is written with one coalesced streaming
+//     store per step (consecutive lanes = consecutive members = 256 B per warp).
+#include <cuda_runtime.h>
+
+#include "sip_step.cuh"
+
+#ifndef SIP_NS
+#define SIP_NS val
+#endif
+
+namespace sip {
+namespace SIP_NS {
+
+constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 112 B = 3584 B
+
+// ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- per-step output sink -----------------------------------------------------------
+struct Emitter {
+  const RunArgs *a;
+  double *outp;  // a->out + m (null => no column output)
+  double *dbgp;  // a->dbg + m
+  int64_t tLocal;
+  const double *obs;  // site's observations or null
+  int64_t tSite;
+  double ll, lln;
+  __device__ __forceinline__ void out(int col, double v) const {
+    if (outp != nullptr) {
+      const int s = a->colSlot[col];
+      if (s >= 0) __stcs(outp + ((int64_t)s * a->outSteps + tLocal) * a->ld, v);
+    }
+  }
+  __device__ __forceinline__ void dbg(int k, double v) const {
+    if (dbgp != nullptr) __stcs(dbgp + ((int64_t)k * a->outSteps + tLocal) * a->ld, v);
+  }
+  __device__ __forceinline__ void nee(double v) {
+    if (obs != nullptr) {
+      const double o = __ldg(obs + tSite);
+      if (o == o) {  // NaN = no observation
+        const double d = (v - o) * a->invSigma;
+        ll += -0.5 * d * d + a->logNorm;
+        lln += 1.0;
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void load_member(const RunArgs &a, int64_t m, Member &mb, MemberExt &ext, bool debug) {
+  const double *s = a.state + m;
+  const int64_t ld = a.ld;
+  mb.wood = s[SIPNET_S_plantWoodC * ld];
+  mb.leaf = s[SIPNET_S_plantLeafC * ld];
+  mb.soil = s[SIPNET_S_soilC * ld];
+  mb.water = s[SIPNET_S_soilWater * ld];
+  mb.litter = s[SIPNET_S_litterC * ld];
+  mb.snow = s[SIPNET_S_snow * ld];
+  mb.coarse = s[SIPNET_S_coarseRootC * ld];
+  mb.fine = s[SIPNET_S_fineRootC * ld];
+  mb.minN = s[SIPNET_S_minN * ld];
+  mb.orgN = s[SIPNET_S_soilOrgN * ld];
+  mb.litN = s[SIPNET_S_litterN * ld];
+  mb.storN = s[SIPNET_S_plantStorageN * ld];
+  mb.delta = s[SIPNET_S_plantCAccountingDelta * ld];
+  mb.gdd = s[SIPNET_S_gdd * ld];
+  mb.wetFrac = s[SIPNET_S_soilWetnessFrac * ld];
+  mb.totNee = s[SIPNET_S_totNee * ld];
+  mb.dTill = s[SIPNET_S_dTillMod * ld];
+  mb.ringSum = s[SIPNET_S_meanSum * ld];
+  mb.ringStart = (int)s[SIPNET_S_meanStart * ld];
+  mb.ringLast = (int)s[SIPNET_S_meanLast * ld];
+  mb.trkLastYear = (int)s[SIPNET_S_trackersLastYear * ld];
+  mb.phenLastYear = (int)s[SIPNET_S_phenLastYear * ld];
+  mb.didGrowth = (int)s[SIPNET_S_didLeafGrowth * ld];
+  mb.didFall = (int)s[SIPNET_S_didLeafFall * ld];
+  mb.status = a.status[m];
+  if (debug) {
+    ext.yGpp = s[SIPNET_S_yearlyGpp * ld];
+    ext.yRtot = s[SIPNET_S_yearlyRtot * ld];
+    ext.yRa = s[SIPNET_S_yearlyRa * ld];
+    ext.yRh = s[SIPNET_S_yearlyRh * ld];
+    ext.yNpp = s[SIPNET_S_yearlyNpp * ld];
+    ext.yNee = s[SIPNET_S_yearlyNee * ld];
+    ext.yLitter = s[SIPNET_S_yearlyLitter * ld];
+    ext.tGpp = s[SIPNET_S_totGpp * ld];
+    ext.tRtot = s[SIPNET_S_totRtot * ld];
+    ext.tRa = s[SIPNET_S_totRa * ld];
+    ext.tRh = s[SIPNET_S_totRh * ld];
+    ext.tNpp = s[SIPNET_S_totNpp * ld];
+  }
+}
+
+__device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const Member &mb, const MemberExt &ext,
+                                             bool debug) {
+  double *s = a.state + m;
+  const int64_t ld = a.ld;
+  s[SIPNET_S_plantWoodC * ld] = mb.wood;
+  s[SIPNET_S_plantLeafC * ld] = mb.leaf;
+  s[SIPNET_S_soilC * ld] = mb.soil;
+  s[SIPNET_S_soilWater * ld] = mb.water;
+  s[SIPNET_S_litterC * ld] = mb.litter;
+  s[SIPNET_S_snow * ld] = mb.snow;
+  s[SIPNET_S_coarseRootC * ld] = mb.coarse;
+  s[SIPNET_S_fineRootC * ld] = mb.fine;
+  s[SIPNET_S_minN * ld] = mb.minN;
+  s[SIPNET_S_soilOrgN * ld] = mb.orgN;
+  s[SIPNET_S_litterN * ld] = mb.litN;
+  s[SIPNET_S_plantStorageN * ld] = mb.storN;
+  s[SIPNET_S_plantCAccountingDelta * ld] = mb.delta;
+  s[SIPNET_S_gdd * ld] = mb.gdd;
+  s[SIPNET_S_soilWetnessFrac * ld] = mb.wetFrac;
+  s[SIPNET_S_totNee * ld] = mb.totNee;
+  s[SIPNET_S_dTillMod * ld] = mb.dTill;
+  s[SIPNET_S_meanSum * ld] = mb.ringSum;
+  s[SIPNET_S_meanStart * ld] = (double)mb.ringStart;
+  s[SIPNET_S_meanLast * ld] = (double)mb.ringLast;
+  s[SIPNET_S_trackersLastYear * ld] = (double)mb.trkLastYear;
+  s[SIPNET_S_phenLastYear * ld] = (double)mb.phenLastYear;
+  s[SIPNET_S_didLeafGrowth * ld] = (double)mb.didGrowth;
+  s[SIPNET_S_didLeafFall * ld] = (double)mb.didFall;
+  uint32_t st = mb.status;
+  if (!(isfinite(mb.wood) && isfinite(mb.leaf) && isfinite(mb.soil) && isfinite(mb.water) && isfinite(mb.litter) &&
+        isfinite(mb.snow) && isfinite(mb.coarse) && isfinite(mb.fine) && isfinite(mb.minN) && isfinite(mb.orgN) &&
+        isfinite(mb.litN) && isfinite(mb.storN) && isfinite(mb.delta))) {
+    st |= SIPNET_GPU_ST_NONFINITE;
+  }
+  a.status[m] = st;
+  if (debug) {
+    s[SIPNET_S_yearlyGpp * ld] = ext.yGpp;
+    s[SIPNET_S_yearlyRtot * ld] = ext.yRtot;
+    s[SIPNET_S_yearlyRa * ld] = ext.yRa;
+    s[SIPNET_S_yearlyRh * ld] = ext.yRh;
+    s[SIPNET_S_yearlyNpp * ld] = ext.yNpp;
+    s[SIPNET_S_yearlyNee * ld] = ext.yNee;
+    s[SIPNET_S_yearlyLitter * ld] = ext.yLitter;
+    s[SIPNET_S_totGpp * ld] = ext.tGpp;
+    s[SIPNET_S_totRtot * ld] = ext.tRtot;
+    s[SIPNET_S_totRa * ld] = ext.tRa;
+    s[SIPNET_S_totRh * ld] = ext.tRh;
+    s[SIPNET_S_totNpp * ld] = ext.tNpp;
+  }
+}
+
+// ---- K1: fused [events -> fluxes -> pools -> trackers -> mean tracker] over a step range ----
+template <class FL, bool DEBUG, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNParamDev][BLOCK]
+  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNParamDev * BLOCK);  // [2][kChunkSteps]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);              // [2]
+
+  const BlockDesc bd = a.blocks[blockIdx.x];
+  const SiteDev site = a.sites[bd.site];
+  const int tid = threadIdx.x;
+  const int64_t m = (int64_t)bd.member0 + tid;
+  bool active = tid < bd.count;
+  const FL fl(a.flags);
+
+  const int64_t t0 = a.stepBegin;
+  const int64_t t1 = a.stepEnd < site.nsteps ? a.stepEnd : site.nsteps;
+  const int64_t nChunks = t1 > t0 ? (t1 - t0 + kChunkSteps - 1) / kChunkSteps : 0;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // parameter tile: coalesced global reads, column-per-thread shared layout
+  for (int k = 0; k < kNParamDev; ++k) tile[k * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+  __syncthreads();
+
+  auto issue = [&](int64_t chunk) {
+    const int64_t cs = t0 + chunk * kChunkSteps;
+    const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
+    const uint32_t bytes = (uint32_t)(n * sizeof(ClimRec));
+    uint64_t *bar = &bars[chunk & 1];
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(climBuf + (chunk & 1) * kChunkSteps, site.clim + cs, bytes, bar);
+  };
+  if (tid == 0 && nChunks > 0) issue(0);
+
+  Member mb;
+  MemberExt ext = {};
+  if (active) {
+    load_member(a, m, mb, ext, DEBUG);
+    if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) active = false;  // reference would have exited (sipnet.c:1117-1122)
+  }
+  const ParamTile prm{tile + tid, BLOCK};
+  const RingRef rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
+  RecSink rec{nullptr, nullptr, a.maxRecs, 0};
+  if (a.recCount != nullptr && active) {
+    rec.count = a.recCount + m;
+    rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
+  }
+  Emitter emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
+               site.neeObs, 0, 0.0, 0.0};
+
+  for (int64_t chunk = 0; chunk < nChunks; ++chunk) {
+    if (tid == 0 && chunk + 1 < nChunks) issue(chunk + 1);  // buffer (chunk+1)&1 was released by the barrier below
+    mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
+    const ClimRec *cbuf = climBuf + (chunk & 1) * kChunkSteps;
+    const int64_t cs = t0 + chunk * kChunkSteps;
+    const int n = (int)((t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps);
+    if (active) {
+      for (int i = 0; i < n; ++i) {
+        const int64_t t = cs + i;
+        emit.tLocal = t - t0;
+        emit.tSite = t;
+        rec.step = (int32_t)t;
+        step<FL, DEBUG>(fl, prm, cbuf[i], site.events, mb, ext, rg, rec, emit);
+      }
+    }
+    __syncthreads();  // everyone is done reading this buffer before it is refilled
+  }
+
+  if (active) {
+    store_member(a, m, mb, ext, DEBUG);
+    if (a.loglik != nullptr && site.neeObs != nullptr) {
+      a.loglik[m] += emit.ll;
+      a.loglikN[m] += emit.lln;
+    }
+  }
+}
+
+// ---- setup kernels: setupModel(), sipnet.c:1858-1951 ----------------------------------------
+// (1) parameter derivation, in place on the uploaded raw rows
+__global__ void derive_params_kernel(double *params, int64_t ld, int64_t nmembers, uint32_t *status) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmembers) return;
+  auto P = [&](int k) -> double & { return params[(int64_t)k * ld + m]; };
+  uint32_t st = 0;
+  // ensureAllocation, sipnet.c:1111-1123
+  P(SIPNET_P_coarseRootAllocation) =
+      1 - P(SIPNET_P_leafAllocation) - P(SIPNET_P_woodAllocation) - P(SIPNET_P_fineRootAllocation);
+  if ((P(SIPNET_P_leafAllocation) >= 1.0) || (P(SIPNET_P_woodAllocation) >= 1.0) ||
+      (P(SIPNET_P_fineRootAllocation) >= 1.0) || (P(SIPNET_P_coarseRootAllocation) < 0)) {
+    st |= SIPNET_GPU_ST_BAD_ALLOCATION;
+  }
+  P(SIPNET_P_baseVegResp) /= 365.0;  // :1873-1877
+  P(SIPNET_P_litterBreakdownRate) /= 365.0;
+  P(SIPNET_P_baseSoilResp) /= 365.0;
+  P(SIPNET_P_woodTurnoverRate) /= 365.0;
+  P(SIPNET_P_leafTurnoverRate) /= 365.0;
+  P(SIPNET_P_psnTMax) = P(SIPNET_P_psnTOpt) + (P(SIPNET_P_psnTOpt) - P(SIPNET_P_psnTMin));  // :1880-1881
+  P(SIPNET_P_fineRootTurnoverRate) /= 365.0;  // :1898-1902
+  P(SIPNET_P_coarseRootTurnoverRate) /= 365.0;
+  P(SIPNET_P_baseCoarseRootResp) /= 365.0;
+  P(SIPNET_P_baseFineRootResp) /= 365.0;
+  if (P(SIPNET_P_fAnoxia) <= 0.0) {  // :1905-1909
+    P(SIPNET_P_fAnoxia) = kTiny;
+  } else if (P(SIPNET_P_fAnoxia) >= 1.0) {
+    P(SIPNET_P_fAnoxia) = 1.0 - kTiny;
+  }
+  if (P(SIPNET_P_anaerobicDecompRate) <= 0.0) {  // :1912-1916
+    P(SIPNET_P_anaerobicDecompRate) = kTiny;
+  } else if (P(SIPNET_P_anaerobicDecompRate) > 1.0) {
+    P(SIPNET_P_anaerobicDecompRate) = 1.0;
+  }
+  // member constant of potPsn(): pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
+  P(kPsnTRangeSqSlot) = sip_pow((P(SIPNET_P_psnTMax) - P(SIPNET_P_psnTMin)) / 2.0, 2.0);
+  status[m] = st;
+}
+
+// (2) initial pools / trackers (also used by reset())
+__global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
+                                  const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
+                                  uint32_t *status, double *loglik, double *loglikN, int32_t *recCount) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmembers) return;
+  auto P = [&](int k) -> double { return params[(int64_t)k * ld + m]; };
+  auto S = [&](int k) -> double & { return state[(int64_t)k * ld + m]; };
+  const RuntimeFlags fl(flags);
+  for (int k = 0; k < SIPNET_GPU_NSTATE; ++k) S(k) = 0.0;
+  S(SIPNET_S_plantWoodC) = (1 - P(SIPNET_P_coarseRootFrac) - P(SIPNET_P_fineRootFrac)) * P(SIPNET_P_plantWoodInit);
+  S(SIPNET_S_plantCAccountingDelta) = 0.0;
+  S(SIPNET_S_plantLeafC) = P(SIPNET_P_laiInit) * P(SIPNET_P_leafCSpWt);
+  S(SIPNET_S_litterC) = fl.on(F_LITTER_POOL) ? P(SIPNET_P_litterInit) : 0.0;
+  S(SIPNET_S_soilC) = P(SIPNET_P_soilInit);
+  S(SIPNET_S_coarseRootC) = P(SIPNET_P_coarseRootFrac) * P(SIPNET_P_plantWoodInit);
+  S(SIPNET_S_fineRootC) = P(SIPNET_P_fineRootFrac) * P(SIPNET_P_plantWoodInit);
+  double water = P(SIPNET_P_soilWFracInit) * P(SIPNET_P_soilWHC);
+  if (water < 0) water = 0;
+  S(SIPNET_S_soilWater) = water;
+  S(SIPNET_S_snow) = P(SIPNET_P_snowInit);
+  if (fl.on(F_NITROGEN)) {
+    S(SIPNET_S_minN) = P(SIPNET_P_minNInit);
+    S(SIPNET_S_soilOrgN) = P(SIPNET_P_soilOrgNInit);
+    S(SIPNET_S_litterN) = P(SIPNET_P_litterOrgNInit);
+    S(SIPNET_S_plantStorageN) = P(SIPNET_P_plantStorageNInit);
+  }
+  // initTrackers, :1406-1413
+  S(SIPNET_S_soilWetnessFrac) = water / P(SIPNET_P_soilWHC);
+  S(SIPNET_S_trackersLastYear) = -1.0;
+  // initPhenologyTrackers, :1501-1527, against the site's FIRST climate record
+  const SiteDev site = sites[memberSite[m]];
+  int didGrowth = 0, didFall = 0, year0 = 0;
+  if (site.nsteps > 0) {
+    const ClimRec c = site.clim[0];
+    year0 = c.year;
+    if (fl.on(F_GDD)) {
+      didGrowth = c.gdd >= P(SIPNET_P_gddLeafOn);  // trackers.lastYear == -1, so no carry-over term
+    } else if (fl.on(F_SOIL_PHENOL)) {
+      didGrowth = c.tsoil >= P(SIPNET_P_soilTempLeafOn);
+    } else if (P(SIPNET_P_leafOnDay) > 0) {
+      didGrowth = ((double)c.day + c.time / 24.0) >= P(SIPNET_P_leafOnDay);
+    }
+    if (P(SIPNET_P_leafOffDay) > 0) didFall = (c.day + c.time / 24.0) >= P(SIPNET_P_leafOffDay);
+    if (didFall && !didGrowth) didGrowth = 1;
+  }
+  S(SIPNET_S_didLeafGrowth) = didGrowth;
+  S(SIPNET_S_didLeafFall) = didFall;
+  S(SIPNET_S_phenLastYear) = year0;
+  // resetMeanTracker(meanNPP, 0), :1948
+  ringV[m] = 0.0;
+  ringW[m] = kMeanNppDays;
+  S(SIPNET_S_meanSum) = 0.0 * kMeanNppDays;
+  status[m] &= SIPNET_GPU_ST_BAD_ALLOCATION;  // keep the static verdict, clear run-time bits
+  if (loglik != nullptr) loglik[m] = 0.0;
+  if (loglikN != nullptr) loglikN[m] = 0.0;
+  if (recCount != nullptr) recCount[m] = 0;
+}
+
+// ---- host-side launchers (C++ linkage inside the library) -------------------------------------
+constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
+constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
+
+template <class FL, bool DEBUG, int BLOCK>
+static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
+  const size_t smem = sizeof(double) * kNParamDev * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) + 2 * sizeof(uint64_t);
+  auto kern = run_kernel<FL, DEBUG, BLOCK>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<nblocks, BLOCK, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int BLOCK>
+static cudaError_t launch_block(const RunArgs &a, int nblocks, bool debug, cudaStream_t stream) {
+  const uint32_t arith = a.flags & ~(uint32_t)F_SNOW;  // ctx.snow has no arithmetic effect (SURVEY 8a trap 6)
+  if (debug) return launch_one<RuntimeFlags, true, BLOCK>(a, nblocks, stream);
+  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW)) return launch_one<StaticFlags<kMaskDefault>, false, BLOCK>(a, nblocks, stream);
+  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW)) return launch_one<StaticFlags<kMaskCropN>, false, BLOCK>(a, nblocks, stream);
+  return launch_one<RuntimeFlags, false, BLOCK>(a, nblocks, stream);
+}
+
+cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, cudaStream_t stream) {
+  switch (blockThreads) {
+    case 32: return launch_block<32>(a, nblocks, debug, stream);
+    case 64: return launch_block<64>(a, nblocks, debug, stream);
+    case 128: return launch_block<128>(a, nblocks, debug, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream) {
+  const int threads = 128;
+  const int blocks = (int)((nmembers + threads - 1) / threads);
+  derive_params_kernel<<<blocks, threads, 0, stream>>>(params, ld, nmembers, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
+                              const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
+                              uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
+                              cudaStream_t stream) {
+  const int threads = 128;
+  const int blocks = (int)((nmembers + threads - 1) / threads);
+  init_state_kernel<<<blocks, threads, 0, stream>>>(params, ld, nmembers, memberSite, sites, flags, state, ringV,
+                                                    ringW, status, loglik, loglikN, recCount);
+  return cudaGetLastError();
+}
+
+}  // namespace SIP_NS
+}  // namespace sip

@@ -1,0 +1,238 @@
+// sip_reduce.cu -- on-device ensemble summaries (K3) and the FP64 roofline probe.
+//
+// Summaries work on the column buffer K1 wrote for the current run range:
+//   cols[t * ld + m]   (one output column, n steps, ld-padded member rows)
+// and reduce every (site, step) row over that site's members.  The reference
+// has no ensemble code at all (SURVEY 8c "unpinned"): the definitions here are
+//   mean      = sum(x) / N                      (finite members only)
+//   variance  = sum((x - mean)^2) / N           (population variance, two pass)
+//   quantile  = numpy's default "linear" rule:  pos = p (N-1), x[lo] + (x[hi]-x[lo]) (pos-lo)
+// and tests/ check them against a trivially-written numpy loop over the
+// oracle's per-step output.  All reductions use a fixed order (strided
+// per-thread partials, then a fixed shared-memory tree), so results are
+// bit-reproducible run to run.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "sip_types.cuh"
+
+namespace sip {
+
+constexpr int kRedThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = kRedThreads / 2; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] += sh[tid + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// grid = (nsteps, nsites); block = kRedThreads
+__global__ void __launch_bounds__(kRedThreads) moments_kernel(const double *cols, int64_t ld, int64_t nsteps,
+                                                              const SiteDev *sites, double *mean, double *var) {
+  __shared__ double sh[kRedThreads];
+  const int64_t t = blockIdx.x;
+  const int site = blockIdx.y;
+  const SiteDev sd = sites[site];
+  const double *row = cols + t * ld + sd.member0;
+  double s = 0.0, cnt = 0.0;
+  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
+    const double x = row[i];
+    if (isfinite(x)) {
+      s += x;
+      cnt += 1.0;
+    }
+  }
+  const double total = block_sum(s, sh);
+  const double n = block_sum(cnt, sh);
+  const double mu = n > 0 ? total / n : nan("");
+  double q = 0.0;
+  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
+    const double x = row[i];
+    if (isfinite(x)) {
+      const double d = x - mu;
+      q += d * d;
+    }
+  }
+  const double ss = block_sum(q, sh);
+  if (threadIdx.x == 0) {
+    mean[(int64_t)site * nsteps + t] = mu;
+    var[(int64_t)site * nsteps + t] = n > 0 ? ss / n : nan("");
+  }
+}
+
+// order-preserving map double -> uint64 (ascending)
+__device__ __forceinline__ uint64_t key_of(double x) {
+  const uint64_t b = (uint64_t)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double val_of(uint64_t k) {
+  const uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (0-based) finite element of row[0..count) by MSB radix select, 8 bits per pass.
+__device__ uint64_t radix_select(const double *row, int count, unsigned long long k, unsigned int *hist) {
+  uint64_t prefix = 0, mask = 0;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += kRedThreads) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < count; i += kRedThreads) {
+      const double x = row[i];
+      if (isfinite(x)) {
+        const uint64_t key = key_of(x);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+      }
+    }
+    __syncthreads();
+    // every thread scans the 256 bins identically (cheap, avoids another barrier pattern)
+    unsigned long long acc = 0;
+    int bin = 0;
+    for (; bin < 256; ++bin) {
+      const unsigned long long c = hist[bin];
+      if (acc + c > k) break;
+      acc += c;
+    }
+    k -= acc;
+    prefix |= (uint64_t)bin << shift;
+    mask |= (uint64_t)0xFF << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// grid = (nsteps, nsites); block = kRedThreads.  out[(site * nq + q) * nsteps + t]
+__global__ void __launch_bounds__(kRedThreads) quantiles_kernel(const double *cols, int64_t ld, int64_t nsteps,
+                                                                const SiteDev *sites, const double *probs, int nq,
+                                                                double *out) {
+  __shared__ unsigned int hist[256];
+  __shared__ double sh[kRedThreads];
+  const int64_t t = blockIdx.x;
+  const int site = blockIdx.y;
+  const SiteDev sd = sites[site];
+  const double *row = cols + t * ld + sd.member0;
+  double cnt = 0.0;
+  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads)
+    if (isfinite(row[i])) cnt += 1.0;
+  const double nfin = block_sum(cnt, sh);
+  for (int q = 0; q < nq; ++q) {
+    double result = nan("");
+    if (nfin > 0) {
+      const double pos = probs[q] * (nfin - 1.0);
+      const double lo = floor(pos);
+      const double frac = pos - lo;
+      const uint64_t klo = radix_select(row, sd.memberCount, (unsigned long long)lo, hist);
+      const double xlo = val_of(klo);
+      double xhi = xlo;
+      if (frac > 0.0) {
+        // x[lo+1]: equals x[lo] if enough duplicates, else the smallest element above it
+        double le = 0.0, above = __longlong_as_double(0x7FF0000000000000ll);
+        for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
+          const double x = row[i];
+          if (isfinite(x)) {
+            if (x <= xlo) le += 1.0; else above = fmin(above, x);
+          }
+        }
+        const double nle = block_sum(le, sh);
+        sh[threadIdx.x] = above;
+        __syncthreads();
+        for (int s = kRedThreads / 2; s > 0; s >>= 1) {
+          if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+          __syncthreads();
+        }
+        const double minAbove = sh[0];
+        __syncthreads();
+        xhi = (nle >= lo + 2.0) ? xlo : minAbove;
+      }
+      result = xlo + (xhi - xlo) * frac;
+    }
+    if (threadIdx.x == 0) out[((int64_t)site * nq + q) * nsteps + t] = result;
+  }
+}
+
+cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int /*ncols*/, const SiteDev *sites,
+                           int64_t nsites, double *mean, double *var, cudaStream_t stream) {
+  // gridDim.y is limited to 65535: tile sites
+  for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
+    const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
+    dim3 grid((unsigned)nsteps, (unsigned)ns);
+    moments_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, mean + s0 * nsteps,
+                                                     var + s0 * nsteps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int /*ncols*/, const SiteDev *sites,
+                             int64_t nsites, const double *probs, int nq, double * /*scratch*/, double *out,
+                             cudaStream_t stream) {
+  for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
+    const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
+    dim3 grid((unsigned)nsteps, (unsigned)ns);
+    quantiles_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, probs, nq,
+                                                       out + s0 * nq * nsteps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// ---- FP64 issue-rate probe -------------------------------------------------------------------
+// Eight independent register-resident DFMA chains per thread; 2 flops per DFMA.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *sink, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.6789) sink[0] = s;  // never true; keeps the chains alive
+}
+
+cudaError_t measure_fp64_peak(int device, double *tflops) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return e;
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+  double *sink = nullptr;
+  if ((e = cudaMalloc(&sink, 8)) != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sm * 8, threads = 256, iters = 1 << 16;
+  fp64_probe_kernel<<<blocks, threads>>>(sink, 1 << 12, 0.999999, 1e-9);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    fp64_probe_kernel<<<blocks, threads>>>(sink, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = best;
+  return e;
+}
+
+}  // namespace sip

@@ -1,0 +1,979 @@
+// sip_step.cuh -- one SIPNET timestep for one ensemble member, as device code.
+//
+// This is the device restatement of updateState() (reference
+// src/sipnet/sipnet.c:1818-1855) and everything below it:
+//   processEvents            events.c:449-742
+//   calculateFluxes          sipnet.c:1256-1336 (+ depeffects.c, nitrogen.c, limitations.c)
+//   updatePoolsAndBalance    sipnet.c:1769-1806 (+ events.c:744-790, nitrogen.c:210-239)
+//   updateTrackers           sipnet.c:1420-1496
+//   updateMeanTrackers       sipnet.c:1546-1570 (+ runmean.c:61-121)
+//   updateEventTrackers      events.c:811-822
+// One thread owns one member; pools and carried trackers live in registers
+// (struct Member) across a chunk of steps; parameters are read from a
+// per-block shared-memory tile; forcing comes from the block's staged ClimRec.
+//
+// Design differences from the reference (results identical):
+//   * no global state; flags are a compile-time or kernel-uniform policy
+//   * the mass-balance tracker (balance.c) is diagnostic only -- nothing in it
+//     feeds back into state -- and is not evaluated
+//   * pure functions evaluated several times with identical arguments in the
+//     reference (calcTempEffect x4, calcRespMoistEffect x2, calcAnaerobicIndex
+//     x4, getMeanTrackerMean x3) are evaluated once
+//   * exit() paths become per-member status bits
+// Expression shapes (association, `x / 365.0`, `-1.0 *`, constant chains) are
+// kept literally: the validation build must do the same IEEE operations as the
+// reference's gcc -O0 binary.
+#pragma once
+#include "sip_math.cuh"
+#include "sip_types.cuh"
+
+namespace sip {
+
+// ---- flag policies -----------------------------------------------------------
+template <uint32_t MASK>
+struct StaticFlags {
+  __device__ __forceinline__ explicit StaticFlags(uint32_t) {}
+  __device__ __forceinline__ bool on(uint32_t bit) const { return (MASK & bit) != 0; }
+};
+struct RuntimeFlags {
+  uint32_t mask;
+  __device__ __forceinline__ explicit RuntimeFlags(uint32_t m) : mask(m) {}
+  __device__ __forceinline__ bool on(uint32_t bit) const { return (mask & bit) != 0; }
+};
+
+// ---- parameter tile in shared memory: element k of this thread at tile[k * stride] ----
+struct ParamTile {
+  const double *base;  // already offset by threadIdx.x
+  int stride;
+  __device__ __forceinline__ double operator()(int k) const { return base[k * stride]; }
+};
+#define SIP_P(name) prm(SIPNET_P_##name)
+
+// ---- per-member register state -------------------------------------------------
+struct Member {
+  // Envi, state.h:416-463
+  double wood, leaf, soil, water, litter, snow, coarse, fine, minN, orgN, litN, storN, delta;
+  // carried trackers (state.h:650-726): only what feeds back or is output
+  double gdd, totNee, wetFrac;
+  double dTill;    // eventTrackers.d_till_mod, events.h:213-221
+  double ringSum;  // MeanTracker.sum, runmean.h
+  int ringStart, ringLast;
+  int trkLastYear;   // trackers.lastYear
+  int phenLastYear;  // phenologyTrackers.lastYear
+  int didGrowth, didFall;
+  uint32_t status;
+};
+
+// extended trackers, only carried by the DEBUG instantiation (restart/debug-log rows)
+struct MemberExt {
+  double yGpp, yRtot, yRa, yRh, yNpp, yNee, yLitter, tGpp, tRtot, tRa, tRh, tNpp;
+};
+
+// ---- mean-NPP ring in HBM: slot s of member m at v[s * ld + m] -----------------
+struct RingRef {
+  double *v;
+  double *w;
+  int64_t ld;
+  int cap;
+  __device__ __forceinline__ double &val(int s) const { return v[(int64_t)s * ld]; }
+  __device__ __forceinline__ double &wgt(int s) const { return w[(int64_t)s * ld]; }
+};
+
+__device__ __forceinline__ void ring_reset(Member &mb, const RingRef &rg, double v) {  // runmean.c:44-51
+  mb.ringStart = mb.ringLast = 0;
+  rg.val(0) = v;
+  rg.wgt(0) = kMeanNppDays;
+  mb.ringSum = v * kMeanNppDays;
+}
+
+__device__ __forceinline__ void ring_push(Member &mb, const RingRef &rg, double value, double weight) {
+  // addValueToMeanTracker, runmean.c:61-115 (weight <= 0 is rejected at init: events.c:460)
+  if (weight >= kMeanNppDays) {
+    ring_reset(mb, rg, value);
+    return;
+  }
+  double left = weight;
+  int i = mb.ringStart;
+  double sum = mb.ringSum;
+  while (left > 0) {
+    const double wi = rg.wgt(i);
+    const double vi = rg.val(i);
+    if (wi > left) {
+      rg.wgt(i) = wi - left;
+      sum -= left * vi;
+      left = 0;
+    } else {
+      sum -= wi * vi;
+      left -= wi;
+      i = (i + 1 == rg.cap) ? 0 : i + 1;
+    }
+  }
+  mb.ringStart = i;
+  i = (mb.ringLast + 1 == rg.cap) ? 0 : mb.ringLast + 1;
+  if (i == mb.ringStart) {  // out of space: reference restores and exits 7 (sipnet.c:1562-1569)
+    rg.wgt(i) = rg.wgt(i) + weight;
+    sum += weight * rg.val(i);
+    mb.ringSum = sum;
+    mb.status |= SIPNET_GPU_ST_RING_OVERFLOW;
+    return;
+  }
+  mb.ringLast = i;
+  rg.val(i) = value;
+  rg.wgt(i) = weight;
+  sum += value * weight;
+  mb.ringSum = sum;
+}
+
+// ---- small helpers ---------------------------------------------------------------
+__device__ __forceinline__ bool has_biomass(const Member &mb) {  // hasSufficientBiomass, sipnet.c:1530-1536
+  const double totWood = mb.wood + mb.delta;
+  const double totRoot = mb.fine + mb.coarse;
+  return mb.wood > kTiny && totWood > kTiny && totRoot > kTiny;
+}
+
+__device__ __forceinline__ void clamp_stock(double &v, double floorv, uint32_t &status) {
+  // ensureNonNegative, sipnet.c:1346-1356
+  if (v < floorv) {
+    if (fabs(v) > kEps) status |= SIPNET_GPU_ST_CLAMPED;
+    v = 0.;
+  }
+}
+
+// record sink for events.out rows (events.c:379-402)
+struct RecSink {
+  sipnet_gpu_event_record *recs;  // this member's slots, or null
+  int32_t *count;                 // this member's counter, or null
+  int32_t maxRecs;
+  int32_t step;
+  __device__ __forceinline__ void add(Member &mb, int type, int variant, int nval, const double *v) const {
+    if (count == nullptr) return;
+    const int n = *count;
+    if (recs != nullptr && n < maxRecs) {
+      sipnet_gpu_event_record &r = recs[n];
+      r.step = step;
+      r.type = type;
+      r.nval = nval;
+      r.variant = variant;
+      for (int k = 0; k < SIPNET_GPU_EVREC_NVAL; ++k) r.val[k] = (k < nval) ? v[k] : 0.0;
+    } else if (recs != nullptr) {
+      mb.status |= SIPNET_GPU_ST_EVREC_OVERFLOW;
+    }
+    *count = n + 1;
+  }
+};
+
+// all 56 per-day rates of struct FluxVars (state.h:469-645); the non-debug
+// instantiations only keep the ones that are live
+struct Rates {
+  double photosynthesis, leafLitter, woodLitter, rVeg, rSoil, rain, transpiration, drainage, litterToSoil,
+      rLitter, snowFall, snowMelt, sublimation, immedEvap, fastFlow, evaporation, fineRootLoss, coarseRootLoss,
+      fineRootCreation, coarseRootCreation, rCoarseRoot, rFineRoot, leafCreation, woodCreation, leafOnCreation,
+      leafOnCreationFromWood, nVolatilization, nLeaching, nOrgSoil, nOrgLitter, nMin, nFixation, nUptake,
+      leafOffNResorption, reductionNResorption, eventLeafC, eventWoodC, eventFineRootC, eventCoarseRootC,
+      eventEvap, eventSoilWater, eventSoilC, eventLitterC, eventMinN, eventSoilOrgN, eventLitterN, eventInputC,
+      eventOutputC, eventInputN, eventOutputN, eventLeafOnCreation, eventLeafOnCreationFromWood,
+      eventLeafOffLitter, eventLeafOffNResorption, soilMethane, litterMethane;
+};
+
+// per-step tracker values that are outputs only (not carried)
+struct StepTrack {
+  double gpp, rtot, ra, rh, rRoot, rSoil, rAboveground, npp, nee, woodCreation, evapotranspiration, methane, n2o,
+      nLeaching, nFixation, nUptake, meanNPP;
+};
+
+// ---- nitrogen helpers, nitrogen.c ----------------------------------------------------
+template <class PT>
+__device__ __forceinline__ double n_leafon_from_c(const PT &prm, double c) {  // nitrogen.c:86-88
+  return fmax(0.0, c / SIP_P(leafCN) - c / SIP_P(woodCN));
+}
+template <class FL, class PT>
+__device__ __forceinline__ double n_demand(const FL &fl, const PT &prm, const Rates &r) {  // nitrogen.c:91-106
+  if (!fl.on(F_NITROGEN)) return 0.0;
+  const double d = r.woodCreation / SIP_P(woodCN) + r.leafCreation / SIP_P(leafCN) +
+                   r.fineRootCreation / SIP_P(fineRootCN) + r.coarseRootCreation / SIP_P(woodCN);
+  return fmax(0.0, d);
+}
+__device__ __forceinline__ double n_non_uptake(const Rates &r) {  // nitrogen.c:124-126
+  return r.nMin - r.nVolatilization - r.nLeaching;
+}
+template <class PT>
+__device__ __forceinline__ double n_unclaimed_storage(const PT &prm, const Member &mb, const Rates &r,
+                                                      double len) {  // nitrogen.c:129-136
+  const double cflux = r.leafOnCreation + r.eventLeafOnCreation;
+  const double nflux = n_leafon_from_c(prm, cflux);
+  return fmax(0.0, mb.storN - nflux * len);
+}
+template <class PT>
+__device__ __forceinline__ double n_fix_frac(const PT &prm, const Member &mb) {  // nitrogen.c:139-153
+  double inhib;
+  const double denom = SIP_P(halfNFixationMax) + mb.minN;
+  if (denom < kTiny) {
+    inhib = 1;
+  } else {
+    inhib = SIP_P(halfNFixationMax) / denom;
+  }
+  return SIP_P(nFixationFracMax) * inhib;
+}
+template <class FL, class PT>
+__device__ __forceinline__ void n_fix_and_uptake(const FL &fl, const PT &prm, const Member &mb, Rates &r,
+                                                 double len) {  // nitrogen.c:156-168
+  const double demand = n_demand(fl, prm, r);
+  const double storage = n_unclaimed_storage(prm, mb, r, len) / len;
+  const double rem = fmax(0.0, demand - storage);
+  const double ff = n_fix_frac(prm, mb);
+  r.nFixation = ff * rem;
+  r.nUptake = (1 - ff) * rem;
+}
+
+// checkLeafOnLimitation, limitations.c:13-64
+template <class FL, class PT>
+__device__ __forceinline__ void limit_leaf_on(const FL &fl, const PT &prm, const Member &mb, double len,
+                                              double &flux) {
+  const double demandC = flux * len;
+  if (demandC < kTiny) return;
+  const double availC = (mb.wood + mb.coarse) * SIP_P(leafOnReallocFrac);
+  const double cLim = availC / demandC;
+  double nLim = 1.0;
+  if (fl.on(F_NITROGEN)) {
+    const double demandN = n_leafon_from_c(prm, demandC);
+    if (demandN > kTiny) nLim = mb.storN / demandN;
+  }
+  const double lim = clip01(fmin(cLim, nLim));
+  if (lim < 1) flux *= lim;
+}
+
+// ---- the step ----------------------------------------------------------------------
+// Emit is a functor: emit.out(col, value) for outputState() columns and, in the
+// DEBUG instantiation, emit.dbg(index, value) for the debug-log fields.
+template <class FL, bool DEBUG, class PT, class Emit>
+__device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec &c, const EventDev *events,
+                                     Member &mb, MemberExt &ext, const RingRef &rg, const RecSink &rec,
+                                     Emit &emit) {
+  const double len = c.length;
+  const double oldSoilWater = mb.water;  // sipnet.c:1821
+  Rates r = {};                          // resetFluxes, sipnet.c:1222
+  bool alive = has_biomass(mb);          // initPlantSurvivalTracker, sipnet.c:1538
+  double harvRemoved = 0, harvTransferred = 0;  // events.c:468-469
+
+  // ---------------- processEvents, events.c:471-741 (events pre-bound to this step) ----
+  for (int e = c.evBegin; e < c.evEnd; ++e) {
+    const EventDev ev = events[e];
+    switch (ev.type) {
+      case SIPNET_EV_IRRIGATION: {  // :484-506
+        const double amount = ev.p[0];
+        double soilAmt, evapAmt;
+        if (ev.method == 0) {
+          evapAmt = SIP_P(immedEvapFrac) * amount;
+          soilAmt = amount - evapAmt;
+        } else {
+          evapAmt = 0.0;
+          soilAmt = amount;
+        }
+        r.eventEvap += evapAmt / len;
+        r.eventSoilWater += soilAmt / len;
+        const double v[2] = {soilAmt, evapAmt};
+        rec.add(mb, ev.type, 0, 2, v);
+      } break;
+      case SIPNET_EV_PLANTING: {  // :507-542
+        const double leafC = ev.p[0], woodC = ev.p[1], fineC = ev.p[2], coarseC = ev.p[3];
+        r.eventLeafC += leafC / len;
+        r.eventWoodC += woodC / len;
+        r.eventFineRootC += fineC / len;
+        r.eventCoarseRootC += coarseC / len;
+        const double inC = leafC + woodC + fineC + coarseC;
+        double inN = 0.0;
+        r.eventInputC += inC / len;
+        if (fl.on(F_NITROGEN)) {
+          inN = leafC / SIP_P(leafCN) + woodC / SIP_P(woodCN) + fineC / SIP_P(fineRootCN) +
+                coarseC / SIP_P(woodCN);
+          r.eventInputN += inN / len;
+        }
+        const double v[6] = {leafC, woodC, fineC, coarseC, inC, inN};
+        rec.add(mb, ev.type, 0, 6, v);
+      } break;
+      case SIPNET_EV_HARVEST: {  // :543-635
+        const double fRA = ev.p[0], fRB = ev.p[1], fTA = ev.p[2], fTB = ev.p[3];
+        const double woodC = mb.wood + mb.delta;
+        const double above = woodC + mb.leaf;
+        const double below = mb.fine + mb.coarse;
+        const double total = above + below;
+        if (total > kTiny) {
+          const double removed = fRA * above + fRB * below;
+          const double moved = fTA * above + fTB * below;
+          harvRemoved += removed / total;
+          harvTransferred += moved / total;
+        }
+        double litterAdd = fTA * (mb.leaf + woodC);
+        double soilAdd = fTB * (mb.fine + mb.coarse);
+        const double dLeaf = -mb.leaf * (fRA + fTA);
+        const double dWood = -woodC * (fRA + fTA);
+        const double dFine = -mb.fine * (fRB + fTB);
+        const double dCoarse = -mb.coarse * (fRB + fTB);
+        if (!fl.on(F_LITTER_POOL)) {
+          soilAdd += litterAdd;
+          litterAdd = 0.0;
+        }
+        r.eventLitterC += litterAdd / len;
+        r.eventSoilC += soilAdd / len;
+        r.eventLeafC += dLeaf / len;
+        r.eventWoodC += dWood / len;
+        r.eventFineRootC += dFine / len;
+        r.eventCoarseRootC += dCoarse / len;
+        double litterNAdd = 0.0, soilNAdd = 0.0;
+        if (fl.on(F_NITROGEN)) {
+          const double nAbove = (mb.leaf / SIP_P(leafCN)) + (mb.wood / SIP_P(woodCN));
+          const double nBelow = (mb.fine / SIP_P(fineRootCN)) + (mb.coarse / SIP_P(woodCN));
+          litterNAdd = fTA * nAbove;
+          soilNAdd = fTB * nBelow;
+          r.eventSoilOrgN += soilNAdd / len;
+          r.eventLitterN += litterNAdd / len;
+        }
+        const double outC = ((woodC + mb.leaf) * fRA + (mb.fine + mb.coarse) * fRB);
+        double outN = 0.0;
+        r.eventOutputC += outC / len;
+        if (fl.on(F_NITROGEN)) {
+          outN = (mb.wood / SIP_P(woodCN) + mb.leaf / SIP_P(leafCN)) * fRA +
+                 (mb.fine / SIP_P(fineRootCN) + mb.coarse / SIP_P(woodCN)) * fRB;
+          r.eventOutputN += outN / len;
+        }
+        const double v[10] = {soilAdd, litterAdd, dLeaf, dWood, dFine, dCoarse, soilNAdd, litterNAdd, outC, outN};
+        rec.add(mb, ev.type, 0, 10, v);
+      } break;
+      case SIPNET_EV_TILLAGE: {  // :636-646
+        mb.dTill += ev.p[0];
+        const double v[1] = {ev.p[0]};
+        rec.add(mb, ev.type, 0, 1, v);
+      } break;
+      case SIPNET_EV_FERTILIZATION: {  // :647-685
+        const double orgC = ev.p[1];
+        double orgN = 0.0, minN = 0.0;
+        if (fl.on(F_NITROGEN)) {
+          orgN = ev.p[0];
+          minN = ev.p[2];
+        }
+        if (fl.on(F_LITTER_POOL)) {
+          r.eventLitterC += orgC / len;
+        } else {
+          r.eventSoilC += orgC / len;
+        }
+        if (fl.on(F_NITROGEN)) {
+          r.eventLitterN += orgN / len;
+          r.eventMinN += minN / len;
+        }
+        r.eventInputC += orgC / len;
+        if (fl.on(F_NITROGEN)) r.eventInputN += (orgN + minN) / len;
+        const double v[6] = {fl.on(F_LITTER_POOL) ? orgC : 0.0, fl.on(F_LITTER_POOL) ? 0.0 : orgC, minN, orgN, orgC,
+                             (orgN + minN)};
+        rec.add(mb, ev.type, 0, 6, v);
+      } break;
+      case SIPNET_EV_LEAFON: {  // :686-705
+        double flux = SIP_P(leafGrowth) / len;
+        limit_leaf_on(fl, prm, mb, len, flux);
+        r.eventLeafOnCreation += flux;
+        const double src = mb.wood + mb.coarse;
+        if (src > kTiny) r.eventLeafOnCreationFromWood += flux * mb.wood / src;
+      } break;
+      case SIPNET_EV_LEAFOFF: {  // :706-728
+        const double leafOff = mb.leaf * SIP_P(fracLeafFall);
+        r.eventLeafOffLitter += leafOff / len;
+        double litterNAdd = 0.0, resorb = 0.0;
+        if (fl.on(F_NITROGEN)) {
+          const double leafN = leafOff / SIP_P(leafCN);
+          resorb = leafN * SIP_P(leafNResorptionFrac);
+          litterNAdd = leafN - resorb;
+          r.eventLeafOffNResorption += resorb / len;
+          r.eventLitterN += litterNAdd / len;
+        }
+        const double v[3] = {leafOff, resorb, litterNAdd};
+        rec.add(mb, ev.type, 1, 3, v);
+      } break;
+      default:
+        break;  // PLANTDEATH is ignored (events.c:729-734); unknown types are rejected at init
+    }
+  }
+
+  // ---------------- calculateFluxes, sipnet.c:1256-1336 -------------------------------
+  const double whc = SIP_P(soilWHC);
+  const double lai = mb.leaf / SIP_P(leafCSpWt);  // :1274
+  const double meanNpp = mb.ringSum / kMeanNppDays;  // getMeanTrackerMean, runmean.c:118
+  const double woodTot = mb.wood + mb.delta;         // getTotalWoodC
+
+  // potPsn, :590-641
+  const double respPerGram = SIP_P(baseFolRespFrac) * SIP_P(aMax);
+  const double grossAMax = SIP_P(aMax) * SIP_P(aMaxFrac) + respPerGram;
+  // psnTRangeSq holds pow((psnTMax - psnTMin) / 2.0, 2) evaluated once per member by the setup kernel
+  double dTemp = (SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)) / prm(kPsnTRangeSqSlot);
+  dTemp = fmax(dTemp, 0.0);
+  double dVpd = 1.0 - SIP_P(dVpdSlope) * sip_pow(c.vpd, SIP_P(dVpdExp));
+  dVpd = fmax(dVpd, 0.0);
+  double dLight;
+  if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
+    double cum = 0.0, cur = 0.0;
+    const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar);
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) {
+      const double cumLai = lai * ((double)layer / 6);
+      const double inten = c.par * sip_exp(-1.0 * att * cumLai);
+      cur = (1 - sip_pow2(-1.0 * inten / hsp));
+      const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
+      cum += coeff * cur;
+    }
+    cum -= cur;
+    dLight = cum / (3.0 * 6);
+  } else {
+    dLight = 0;
+  }
+  const double conv = 12.0 * (1.0 / 1000000000.0) * (SIP_P(leafCSpWt) / SIP_P(cFracLeaf)) * lai * 86400.0;
+  const double potPsn = grossAMax * dTemp * dVpd * dLight * conv;
+  const double baseFolResp = respPerGram * conv;
+
+  // moisture, :656-699
+  double dWater;
+  if (potPsn < kTiny) {
+    r.transpiration = 0.0;
+    dWater = 1;
+  } else {
+    const double wue = SIP_P(wueConst) / c.vpd;
+    const double potTrans = potPsn / wue * 1000.0 * (44.0 / 12.0) * (1.0 / 10000.0);
+    double removable = fmin(mb.water, whc) * SIP_P(waterRemoveFrac);
+    if (c.tsoil < SIP_P(frozenSoilThreshold)) removable *= SIP_P(frozenSoilEff);
+    r.transpiration = fmin(removable, potTrans);
+    dWater = r.transpiration / potTrans;
+  }
+
+  // calcPrecip, :848-882
+  if (c.tair <= 0) {
+    r.snowFall = c.precip / len;
+    r.rain = 0;
+  } else {
+    r.snowFall = 0;
+    r.rain = c.precip / len;
+  }
+  r.immedEvap = r.rain * SIP_P(immedEvapFrac);
+  if (fl.on(F_LEAF_WATER)) {
+    const double maxPool = lai * SIP_P(leafPoolDepth);
+    if (r.immedEvap > maxPool) r.immedEvap = maxPool;
+  }
+  const double netRain = r.rain - r.immedEvap;  // :1281
+
+  // snowPack, :888-946
+  {
+    const double k = (1.3 * 1005.) / 66. * (1. / 2835000.) * 1000. * 1000. * (1. / 10000) * 86400.0;
+    if (mb.snow <= 0) {
+      r.snowMelt = 0;
+      r.sublimation = 0;
+    } else {
+      const double rd = SIP_P(rdConst) / c.wspd;
+      r.sublimation = k * (0.6 - c.vPress) / rd;
+      double left = mb.snow + (r.snowFall * len);
+      if (r.sublimation < 0) r.sublimation = 0;
+      if (left - (r.sublimation * len) < 0) {
+        r.sublimation = left / len;
+        left = 0;
+      } else {
+        left -= (r.sublimation * len);
+      }
+      if (c.tair <= 0) {
+        r.snowMelt = 0;
+      } else {
+        r.snowMelt = SIP_P(snowMelt) * c.tair;
+        if (left - (r.snowMelt * len) < 0) r.snowMelt = left / len;
+      }
+    }
+  }
+
+  // calcSoilWaterFluxes, :963-1031
+  const double waterFrac = clip01(mb.water / whc);  // getClippedWaterFrac, depeffects.c:11
+  {
+    const double k = (1.3 * 1005.) / 66. * (1. / 2501000.) * 1000. * 1000. * (1. / 10000) * 86400.0;
+    double netIn = netRain + r.snowMelt;
+    r.fastFlow = netIn * SIP_P(fastFlowFrac);
+    netIn -= r.fastFlow;
+    double left = mb.water + netIn * len - r.transpiration * len;
+    if (mb.snow > 0) {
+      r.evaporation = 0;
+    } else {
+      const double rd = SIP_P(rdConst) / c.wspd;
+      const double rsoil = sip_exp(SIP_P(rSoilConst1) - SIP_P(rSoilConst2) * waterFrac);
+      r.evaporation = k * c.vpdSoil / (rd + rsoil);
+      if (r.evaporation < 0) r.evaporation = 0;
+      if (left - (r.evaporation * len) < kTiny) {
+        r.evaporation = (left - kTiny) / len;
+        left = 0;
+      } else {
+        left -= (r.evaporation * len);
+      }
+    }
+    if (left > whc) {
+      const double excess = left - whc;
+      if (fl.on(F_FLOODING)) {
+        r.drainage = fmin(excess * SIP_P(waterDrainFrac), excess / len);
+      } else {
+        r.drainage = excess / len;
+      }
+    } else {
+      r.drainage = 0;
+    }
+  }
+
+  r.photosynthesis = potPsn * dWater;  // getGpp, :1034
+
+  // vegResp / vegResp2, :1051-1103
+  {
+    double fol = baseFolResp * sip_pow(SIP_P(vegRespQ10), (c.tair - SIP_P(psnTOpt)) / 10.0);
+    if (c.tsoil < SIP_P(frozenSoilThreshold)) fol *= SIP_P(frozenSoilFolREff);
+    const double woodR = SIP_P(baseVegResp) * woodTot * sip_pow(SIP_P(vegRespQ10), c.tair / 10.0);
+    if (fl.on(F_GROWTH_RESP)) {
+      double growth = SIP_P(growthRespFrac) * meanNpp;
+      if (growth < 0) growth = 0;
+      r.rVeg = fol + woodR + growth;
+    } else {
+      r.rVeg = fol + woodR;
+    }
+  }
+
+  // calcWoodAndLeafFluxes, :756-782
+  r.woodLitter += woodTot * SIP_P(woodTurnoverRate);
+  r.leafLitter += mb.leaf * SIP_P(leafTurnoverRate);
+  r.leafCreation += meanNpp * SIP_P(leafAllocation);
+  r.woodCreation += meanNpp * SIP_P(woodAllocation);
+
+  // calcLeafOnOffFluxes, :800-842
+  {
+    if (c.year > mb.phenLastYear) {
+      mb.didGrowth = 0;
+      mb.didFall = 0;
+      mb.phenLastYear = c.year;
+    }
+    if (!mb.didGrowth) {
+      bool past;  // pastLeafGrowth, :705-729
+      if (fl.on(F_GDD)) {
+        double g = c.gdd;
+        if (c.year == mb.trkLastYear) g += mb.gdd;
+        past = g >= SIP_P(gddLeafOn);
+      } else if (fl.on(F_SOIL_PHENOL)) {
+        past = c.tsoil >= SIP_P(soilTempLeafOn);
+      } else if (SIP_P(leafOnDay) > 0) {
+        const double now = (double)c.day + c.time / 24.0;
+        past = now >= SIP_P(leafOnDay);
+      } else {
+        past = false;
+      }
+      if (past) {
+        double on = SIP_P(leafGrowth) / len;
+        limit_leaf_on(fl, prm, mb, len, on);
+        r.leafOnCreation += on;
+        const double src = mb.wood + mb.coarse;
+        if (src > kTiny) r.leafOnCreationFromWood += on * mb.wood / src;
+        mb.didGrowth = 1;
+      }
+    }
+    if (!mb.didFall) {
+      bool past = false;  // pastLeafFall, :733-742
+      if (SIP_P(leafOffDay) > 0) past = (c.day + c.time / 24.0) >= SIP_P(leafOffDay);
+      if (past) {
+        const double off = (mb.leaf * SIP_P(fracLeafFall)) / len;
+        r.leafLitter += off;
+        mb.didFall = 1;
+        if (off > kTiny && fl.on(F_EVENTS)) {
+          const double v[1] = {off * len};
+          rec.add(mb, SIPNET_EV_LEAFOFF, 0, 1, v);
+        }
+      }
+    }
+  }
+
+  // shared dependency terms (depeffects.c); each is a pure function of (tsoil, soilWater, params)
+  const double tempEffect = sip_pow(SIP_P(soilRespQ10), c.tsoil / 10);  // calcTempEffect :72-75
+  double anaerobicIdx = 0.0;                                              // calcAnaerobicIndex :15-22
+  if (fl.on(F_ANAEROBIC) || fl.on(F_NITROGEN)) {
+    const double fa = SIP_P(fAnoxia);
+    anaerobicIdx = clip01((waterFrac - fa) / (1 - fa));
+  }
+  double moistEffect;  // calcRespMoistEffect :24-63
+  if (!fl.on(F_WATER_HRESP) || c.tsoil < 0) {
+    moistEffect = 1.0;
+  } else if (!fl.on(F_ANAEROBIC)) {
+    moistEffect = sip_pow(waterFrac, SIP_P(soilRespMoistEffect));
+  } else {
+    const double dAer = clip01(waterFrac / SIP_P(fAnoxia));
+    moistEffect = (1 - anaerobicIdx) * dAer + SIP_P(anaerobicDecompRate) * anaerobicIdx;
+  }
+  const double tillEffect = 1 + mb.dTill;  // calcTillageEffect :77
+
+  // calcLitterFluxes, :1150-1171
+  if (fl.on(F_LITTER_POOL)) {
+    double cn = 1.0;  // calcCNEffect, depeffects.c:79-88
+    if (fl.on(F_NITROGEN)) cn = SIP_P(kCN) / (SIP_P(kCN) + safe_ratio(mb.litter, mb.litN));
+    const double breakdown = mb.litter * SIP_P(litterBreakdownRate) * tempEffect * moistEffect * tillEffect * cn;
+    r.rLitter = breakdown * SIP_P(fracLitterRespired);
+    r.litterToSoil = breakdown * (1.0 - SIP_P(fracLitterRespired));
+  }
+
+  // calcRootFluxes, :1176-1196
+  r.coarseRootLoss += SIP_P(coarseRootTurnoverRate) * mb.coarse;
+  r.fineRootLoss += SIP_P(fineRootTurnoverRate) * mb.fine;
+  r.coarseRootCreation += SIP_P(coarseRootAllocation) * meanNpp;
+  r.fineRootCreation += SIP_P(fineRootAllocation) * meanNpp;
+  r.rCoarseRoot = SIP_P(baseCoarseRootResp) * mb.coarse * sip_pow(SIP_P(coarseRootQ10), c.tsoil / 10.0);
+  r.rFineRoot = SIP_P(baseFineRootResp) * mb.fine * sip_pow(SIP_P(fineRootQ10), c.tsoil / 10.0);
+
+  // calcSoilRespiration, :1132-1148
+  {
+    double cn = 1.0;
+    if (fl.on(F_NITROGEN)) cn = SIP_P(kCN) / (SIP_P(kCN) + safe_ratio(mb.soil, mb.orgN));
+    r.rSoil = mb.soil * SIP_P(baseSoilResp) * moistEffect * tempEffect * tillEffect * cn;
+  }
+
+  // calcMethaneFlux, :1201-1214
+  if (fl.on(F_ANAEROBIC)) {
+    const double mm = sip_pow(anaerobicIdx, SIP_P(anaerobicTransExp));  // calcMethaneMoistEffect
+    r.soilMethane = SIP_P(soilMethaneRate) * mb.soil * tempEffect * mm;
+    if (fl.on(F_LITTER_POOL)) r.litterMethane = SIP_P(litterMethaneRate) * mb.litter * tempEffect * mm;
+  }
+
+  // checkNegativeCreation, limitations.c:146-182
+  {
+    const double turnover = mb.leaf * SIP_P(leafTurnoverRate);
+    const double leafDef = mb.leaf / len + r.leafCreation - turnover;
+    if (leafDef < 0) {
+      r.woodCreation += leafDef;
+      r.leafCreation -= leafDef;
+    }
+    const double fineDef = mb.fine / len + r.fineRootCreation - r.fineRootLoss;
+    const double coarseDef = mb.coarse / len + r.coarseRootCreation - r.coarseRootLoss;
+    if ((fineDef < 0.0) != (coarseDef < 0.0)) {
+      if (fineDef < 0.0) {
+        r.coarseRootCreation += fineDef;
+        r.fineRootCreation -= fineDef;
+      }
+      if (coarseDef < 0.0) {
+        r.fineRootCreation += coarseDef;
+        r.coarseRootCreation -= coarseDef;
+      }
+    }
+  }
+
+  if (fl.on(F_NITROGEN)) {
+    // calcNResorptionFluxes, nitrogen.c:170-196
+    if (r.woodCreation + r.leafCreation + r.fineRootCreation + r.coarseRootCreation < 0.0) {
+      r.reductionNResorption -= (r.leafCreation / SIP_P(leafCN) + r.woodCreation / SIP_P(woodCN) +
+                                 r.coarseRootCreation / SIP_P(woodCN) + r.fineRootCreation / SIP_P(fineRootCN));
+    }
+    r.leafOffNResorption += SIP_P(leafNResorptionFrac) * r.leafLitter / SIP_P(leafCN);
+    // calcNVolatilizationFlux, nitrogen.c:15-25 (+ calcVolatilizationMoistEffect, depeffects.c:90-96)
+    {
+      const double dw = 0.05 + 3.8 * anaerobicIdx * (1 - anaerobicIdx);
+      r.nVolatilization = SIP_P(nVolatilizationFrac) * mb.minN * tempEffect * dw;
+    }
+    // calcNLeachingFlux, nitrogen.c:30-40
+    {
+      double phi;
+      if ((r.drainage / whc) < 1) {
+        phi = r.drainage / whc;
+      } else {
+        phi = 1;
+      }
+      r.nLeaching = mb.minN * phi * SIP_P(nLeachingFrac);
+    }
+    // calcNPoolFluxes, nitrogen.c:45-83
+    {
+      const double litterCN = safe_ratio(mb.litter, mb.litN);
+      const double soilCN = safe_ratio(mb.soil, mb.orgN);
+      const double litterMin = r.rLitter / litterCN;
+      const double soilMin = r.rSoil / soilCN;
+      const double inputs =
+          r.litterToSoil / litterCN + r.fineRootLoss / SIP_P(fineRootCN) + r.coarseRootLoss / SIP_P(woodCN);
+      const double sat = fl.on(F_CSAT) ? clip01(mb.soil / SIP_P(soilCSaturation)) : 0.0;
+      r.nOrgLitter = r.leafLitter / SIP_P(leafCN) - r.leafOffNResorption + r.woodLitter / SIP_P(woodCN) -
+                     litterMin - r.litterToSoil / litterCN + (inputs * sat);
+      r.nOrgSoil = inputs * (1 - sat) - soilMin;
+      r.nMin = litterMin + soilMin;
+    }
+    n_fix_and_uptake(fl, prm, mb, r, len);  // nitrogen.c:156-168
+
+    // checkMineralNLimitation, limitations.c:119-130
+    {
+      const double pool = mb.minN + (r.nMin + r.eventMinN) * len;
+      const double loss = (r.nLeaching + r.nVolatilization) * len;
+      if (loss > kTiny && loss > pool) {
+        const double red = pool / loss;
+        r.nLeaching *= red;
+        r.nVolatilization *= red;
+      }
+    }
+    // checkNitrogenLimitation, limitations.c:69-114
+    {
+      const double uptakeDemand = r.nUptake * len;
+      const double nonUptake = n_non_uptake(r) * len;
+      const double avail = mb.minN + nonUptake;
+      if (uptakeDemand > kTiny && uptakeDemand > avail) {
+        const double unclaimed = n_unclaimed_storage(prm, mb, r, len);
+        const double demand = n_demand(fl, prm, r) * len;
+        const double uptakeFrac = 1 - n_fix_frac(prm, mb);
+        const double red = (avail / uptakeFrac + unclaimed) / demand;
+        r.woodCreation *= red;
+        r.leafCreation *= red;
+        r.fineRootCreation *= red;
+        r.coarseRootCreation *= red;
+        n_fix_and_uptake(fl, prm, mb, r, len);
+      }
+    }
+  }
+
+  // writeLeafOnEventIfNeeded, sipnet.c:1230-1247
+  if (fl.on(F_EVENTS)) {
+    if (r.leafOnCreation > kTiny) {
+      const double v[2] = {r.leafOnCreation * len, r.leafOnCreationFromWood * len};
+      rec.add(mb, SIPNET_EV_LEAFON, 0, 2, v);
+    }
+    if (r.eventLeafOnCreation > kTiny) {
+      const double v[2] = {r.eventLeafOnCreation * len, r.eventLeafOnCreationFromWood * len};
+      rec.add(mb, SIPNET_EV_LEAFON, 1, 2, v);
+    }
+  }
+
+  // ---------------- updatePoolsAndBalance, sipnet.c:1769-1806 ---------------------------
+  // updatePoolsForEvents, events.c:744-790
+  mb.wood += r.eventWoodC * len;
+  mb.leaf += r.eventLeafC * len;
+  mb.soil += r.eventSoilC * len;
+  if (fl.on(F_LITTER_POOL)) mb.litter += r.eventLitterC * len;
+  mb.wood -= r.eventLeafOnCreationFromWood * len;
+  {
+    const double evFromRoot = r.eventLeafOnCreation - r.eventLeafOnCreationFromWood;
+    mb.coarse -= evFromRoot * len;
+  }
+  mb.leaf += (r.eventLeafOnCreation - r.eventLeafOffLitter) * len;
+  if (fl.on(F_LITTER_POOL)) {
+    mb.litter += r.eventLeafOffLitter * len;
+  } else {
+    mb.soil += r.eventLeafOffLitter * len;
+  }
+  mb.coarse += r.eventCoarseRootC * len;
+  mb.fine += r.eventFineRootC * len;
+  mb.water += r.eventSoilWater * len;
+  if (fl.on(F_NITROGEN)) {
+    mb.minN += r.eventMinN * len;
+    mb.orgN += r.eventSoilOrgN * len;
+    mb.litN += r.eventLitterN * len;
+    const double onN = n_leafon_from_c(prm, r.eventLeafOnCreation);
+    mb.storN += (r.eventLeafOffNResorption - onN) * len;
+  }
+
+  // updateMainPools, sipnet.c:1579-1626
+  {
+    const double ra = r.rVeg + r.rFineRoot + r.rCoarseRoot;
+    const double alloc = r.leafCreation + r.woodCreation + r.fineRootCreation + r.coarseRootCreation;
+    mb.delta += ((r.photosynthesis - ra) - alloc) * len;
+    mb.wood += (r.woodCreation - r.woodLitter - r.leafOnCreationFromWood) * len;
+    mb.leaf += (r.leafCreation + r.leafOnCreation - r.leafLitter) * len;
+    mb.water += (r.rain + r.snowMelt - r.immedEvap - r.fastFlow - r.evaporation - r.transpiration - r.drainage) * len;
+    mb.snow += (r.snowFall - r.snowMelt - r.sublimation) * len;
+  }
+
+  // updatePoolsForSoil, sipnet.c:1634-1680
+  if (fl.on(F_LITTER_POOL)) {
+    const double inputs = r.coarseRootLoss + r.fineRootLoss + r.litterToSoil;
+    const double sat = fl.on(F_CSAT) ? clip01(mb.soil / SIP_P(soilCSaturation)) : 0.0;
+    mb.litter +=
+        (r.woodLitter + r.leafLitter + (inputs * sat) - r.litterToSoil - r.rLitter - r.litterMethane) * len;
+    mb.soil += (inputs * (1 - sat) - r.rSoil - r.soilMethane) * len;
+  } else {
+    mb.soil += (r.coarseRootLoss + r.fineRootLoss + r.woodLitter + r.leafLitter - r.rSoil - r.soilMethane) * len;
+  }
+  {
+    const double fromRoot = r.leafOnCreation - r.leafOnCreationFromWood;
+    mb.coarse += (r.coarseRootCreation - r.coarseRootLoss - fromRoot) * len;
+    mb.fine += (r.fineRootCreation - r.fineRootLoss) * len;
+  }
+
+  // updateNitrogenPools, nitrogen.c:210-239
+  if (fl.on(F_NITROGEN)) {
+    const double demand = n_demand(fl, prm, r);
+    const double fromStorage = demand - r.nUptake - r.nFixation;
+    const double onN = n_leafon_from_c(prm, r.leafOnCreation);
+    mb.storN += (r.leafOffNResorption + r.reductionNResorption - fromStorage - onN) * len;
+    const double nonUptake = n_non_uptake(r);
+    mb.minN += (nonUptake - r.nUptake) * len;
+    mb.orgN += r.nOrgSoil * len;
+    mb.litN += r.nOrgLitter * len;
+  }
+
+  // checkForMortality, sipnet.c:1688-1767
+  if (!alive) {
+    if (has_biomass(mb)) alive = true;
+  } else if (!has_biomass(mb)) {
+    alive = false;
+    mb.status |= SIPNET_GPU_ST_DIED;
+    const double totWood = mb.wood + mb.delta;
+    const double totRoot = mb.fine + mb.coarse;
+    mb.soil += totRoot;
+    if (fl.on(F_LITTER_POOL)) {
+      mb.litter += mb.wood + mb.leaf + mb.delta;
+    } else {
+      mb.soil += mb.wood + mb.leaf + mb.delta;
+    }
+    if (fl.on(F_NITROGEN)) {
+      mb.orgN += mb.fine / SIP_P(fineRootCN) + mb.coarse / SIP_P(woodCN);
+      mb.litN += mb.wood / SIP_P(woodCN) + mb.leaf / SIP_P(leafCN) + mb.storN;
+    }
+    mb.wood = 0.0;
+    mb.leaf = 0.0;
+    mb.coarse = 0.0;
+    mb.fine = 0.0;
+    mb.delta = 0.0;
+    if (fl.on(F_NITROGEN)) mb.storN = 0.0;
+    ring_reset(mb, rg, 0.0);
+    if (fl.on(F_EVENTS)) {
+      const double v[4] = {harvRemoved, harvTransferred, totWood, totRoot};
+      rec.add(mb, SIPNET_EV_PLANTDEATH, 0, 4, v);
+    }
+  }
+
+  // ensureNonNegativeStocks, sipnet.c:1368-1397
+  clamp_stock(mb.wood, 0, mb.status);
+  clamp_stock(mb.leaf, 0, mb.status);
+  if (fl.on(F_LITTER_POOL)) clamp_stock(mb.litter, 0, mb.status);
+  clamp_stock(mb.soil, 0, mb.status);
+  clamp_stock(mb.coarse, 0, mb.status);
+  clamp_stock(mb.fine, 0, mb.status);
+  clamp_stock(mb.water, 0, mb.status);
+  clamp_stock(mb.snow, kTiny, mb.status);
+  clamp_stock(mb.minN, 0, mb.status);
+  clamp_stock(mb.orgN, 0, mb.status);
+  clamp_stock(mb.litN, 0, mb.status);
+  clamp_stock(mb.storN, 0, mb.status);
+
+  // ---------------- updateTrackers, sipnet.c:1420-1496 ------------------------------------
+  StepTrack t;
+  if (c.year != mb.trkLastYear) {
+    if (DEBUG) ext.yGpp = ext.yRtot = ext.yRa = ext.yRh = ext.yNpp = ext.yNee = 0.0;
+    mb.gdd = 0.0;
+    mb.trkLastYear = c.year;
+  }
+  t.gpp = r.photosynthesis * len;
+  t.rh = (r.rLitter + r.rSoil) * len;
+  t.rAboveground = (r.rVeg) * len;
+  t.rRoot = (r.rCoarseRoot + r.rFineRoot) * len;
+  t.rSoil = t.rRoot + t.rh;
+  t.ra = t.rRoot + t.rAboveground;
+  t.rtot = t.ra + t.rh;
+  t.npp = t.gpp - t.ra;
+  t.nee = -1.0 * (t.npp - t.rh);
+  if (DEBUG) {
+    ext.yGpp += t.gpp;
+    ext.yRa += t.ra;
+    ext.yRh += t.rh;
+    ext.yRtot += t.rtot;
+    ext.yNpp += t.npp;
+    ext.yNee += t.nee;
+    ext.tGpp += t.gpp;
+    ext.tRa += t.ra;
+    ext.tRh += t.rh;
+    ext.tRtot += t.rtot;
+    ext.tNpp += t.npp;
+  }
+  mb.totNee += t.nee;
+  t.woodCreation = r.woodCreation * len;
+  t.methane = (r.soilMethane + r.litterMethane) * len;
+  t.evapotranspiration = (r.transpiration + r.immedEvap + r.evaporation + r.sublimation + r.eventEvap) * len;
+  mb.wetFrac = (oldSoilWater + mb.water) / (2.0 * whc);
+  if (DEBUG) ext.yLitter += r.leafLitter + r.eventLeafOffLitter;
+  if (fl.on(F_GDD)) {
+    mb.gdd += c.gdd;
+  } else {
+    mb.gdd = 0.0;
+  }
+  t.meanNPP = mb.ringSum / kMeanNppDays;  // read before this step's insert (sipnet.c:1486 precedes :1852)
+  if (fl.on(F_NITROGEN)) {
+    t.n2o = r.nVolatilization * len;
+    t.nLeaching = r.nLeaching * len;
+    t.nFixation = r.nFixation * len;
+    t.nUptake = r.nUptake * len;
+  } else {
+    t.n2o = t.nLeaching = t.nFixation = t.nUptake = 0.0;
+  }
+
+  // ---------------- outputs (outputState, sipnet.c:455-472) ---------------------------------
+  emit.out(SIPNET_O_plantWoodC, mb.wood + mb.delta);
+  emit.out(SIPNET_O_plantLeafC, mb.leaf);
+  emit.out(SIPNET_O_woodCreation, t.woodCreation);
+  emit.out(SIPNET_O_soilC, mb.soil);
+  emit.out(SIPNET_O_coarseRootC, mb.coarse);
+  emit.out(SIPNET_O_fineRootC, mb.fine);
+  emit.out(SIPNET_O_litterC, mb.litter);
+  emit.out(SIPNET_O_soilWater, mb.water);
+  emit.out(SIPNET_O_soilWetnessFrac, mb.wetFrac);
+  emit.out(SIPNET_O_snow, mb.snow);
+  emit.out(SIPNET_O_npp, t.npp);
+  emit.out(SIPNET_O_nee, t.nee);
+  emit.out(SIPNET_O_cumNEE, mb.totNee);
+  emit.out(SIPNET_O_gpp, t.gpp);
+  emit.out(SIPNET_O_rAboveground, t.rAboveground);
+  emit.out(SIPNET_O_rSoil, t.rSoil);
+  emit.out(SIPNET_O_rRoot, t.rRoot);
+  emit.out(SIPNET_O_ra, t.ra);
+  emit.out(SIPNET_O_rh, t.rh);
+  emit.out(SIPNET_O_rtot, t.rtot);
+  emit.out(SIPNET_O_evapotranspiration, t.evapotranspiration);
+  emit.out(SIPNET_O_fluxestranspiration, r.transpiration);
+  emit.out(SIPNET_O_minN, mb.minN);
+  emit.out(SIPNET_O_soilOrgN, mb.orgN);
+  emit.out(SIPNET_O_litterN, mb.litN);
+  emit.out(SIPNET_O_plantStorageN, mb.storN);
+  emit.out(SIPNET_O_n2o, t.n2o);
+  emit.out(SIPNET_O_nLeaching, t.nLeaching);
+  emit.out(SIPNET_O_nFixation, t.nFixation);
+  emit.out(SIPNET_O_nUptake, t.nUptake);
+  emit.out(SIPNET_O_ch4, t.methane);
+  emit.out(SIPNET_O_nppStorage, mb.delta);
+  emit.nee(t.nee);
+
+  // ---------------- updateMeanTrackers, sipnet.c:1546-1570 -----------------------------------
+  if (alive) {
+    const double npp = r.photosynthesis - r.rVeg - r.rCoarseRoot - r.rFineRoot;
+    ring_push(mb, rg, npp, len);
+  }
+
+  if (DEBUG) {  // debug-log field order, debug_log.c:51-170
+    int k = 0;
+    const double ev[13] = {mb.wood, mb.leaf, mb.soil, mb.water, mb.litter, mb.snow, mb.coarse,
+                           mb.fine, mb.minN, mb.orgN, mb.litN,  mb.storN,  mb.delta};
+#pragma unroll
+    for (int i = 0; i < 13; ++i) emit.dbg(k++, ev[i]);
+    const double rv[56] = {r.photosynthesis, r.leafLitter, r.woodLitter, r.rVeg, r.rSoil, r.rain, r.transpiration,
+                           r.drainage, r.litterToSoil, r.rLitter, r.snowFall, r.snowMelt, r.sublimation,
+                           r.immedEvap, r.fastFlow, r.evaporation, r.fineRootLoss, r.coarseRootLoss,
+                           r.fineRootCreation, r.coarseRootCreation, r.rCoarseRoot, r.rFineRoot, r.leafCreation,
+                           r.woodCreation, r.leafOnCreation, r.leafOnCreationFromWood, r.nVolatilization,
+                           r.nLeaching, r.nOrgSoil, r.nOrgLitter, r.nMin, r.nFixation, r.nUptake,
+                           r.leafOffNResorption, r.reductionNResorption, r.eventLeafC, r.eventWoodC,
+                           r.eventFineRootC, r.eventCoarseRootC, r.eventEvap, r.eventSoilWater, r.eventSoilC,
+                           r.eventLitterC, r.eventMinN, r.eventSoilOrgN, r.eventLitterN, r.eventInputC,
+                           r.eventOutputC, r.eventInputN, r.eventOutputN, r.eventLeafOnCreation,
+                           r.eventLeafOnCreationFromWood, r.eventLeafOffLitter, r.eventLeafOffNResorption,
+                           r.soilMethane, r.litterMethane};
+#pragma unroll
+    for (int i = 0; i < 56; ++i) emit.dbg(k++, rv[i]);
+    const double tv[33] = {t.gpp, t.rtot, t.ra, t.rh, t.rRoot, t.rSoil, t.rAboveground, t.npp, t.nee,
+                           t.woodCreation, mb.gdd, t.evapotranspiration, mb.wetFrac, ext.yGpp, ext.yRtot,
+                           ext.yRa, ext.yRh, ext.yNpp, ext.yNee, ext.yLitter, ext.tGpp, ext.tRtot, ext.tRa,
+                           ext.tRh, ext.tNpp, mb.totNee, (double)mb.trkLastYear, t.methane, t.n2o, t.nLeaching,
+                           t.nFixation, t.nUptake, t.meanNPP};
+#pragma unroll
+    for (int i = 0; i < 33; ++i) emit.dbg(k++, tv[i]);
+    emit.dbg(k++, (double)mb.didGrowth);
+    emit.dbg(k++, (double)mb.didFall);
+    emit.dbg(k++, (double)mb.phenLastYear);
+    emit.dbg(k++, alive ? 1.0 : 0.0);
+  }
+
+  // ---------------- updateEventTrackers, events.c:811-822 -------------------------------------
+  if (mb.dTill > 0) {
+    mb.dTill *= c.tillDecay;
+    if (mb.dTill < 0.01) mb.dTill = 0.0;
+  }
+}
+
+}  // namespace sip

@@ -1,0 +1,103 @@
+// sip_types.cuh -- device-side data layout of the batched SIPNET integrator.
+//
+// HBM layout (all FP64, structure-of-arrays, indexed by ensemble member m):
+//   params  [80][ld]      derived parameters (post setupModel(), reference sipnet.c:1858-1916)
+//   state   [NSTATE][ld]  carried state between run() segments (restart.c:148-308 field list)
+//   ring_v  [cap][ld]     5-day mean-NPP ring values   (runmean.c)
+//   ring_w  [cap][ld]     5-day mean-NPP ring weights
+//   out     [ncols][n][ld] per-step output columns of the current run range (outputState order)
+// Per site (shared by all its members, staged to shared memory per step chunk):
+//   ClimRec [T_s]         one 112-byte record per climate step (ClimateVars, state.h:12-49,
+//                         plus the pre-bound event range of that step)
+//   EventDev[nev]         events.in rows in file order
+#pragma once
+#include <cstdint>
+
+#include "../../include/sipnet_gpu.h"
+
+namespace sip {
+
+constexpr double kTiny = 0.000001;  // reference common/util.h:14
+constexpr double kEps = 1e-8;       // reference balance.h:6
+constexpr double kMeanNppDays = 5.0;  // MEAN_NPP_DAYS, sipnet.c:39
+constexpr int kRingMax = 250;         // MEAN_NPP_MAX_ENTRIES, sipnet.c:40
+
+// Device parameter rows: the 80 of struct Parameters plus derived per-member constants.
+constexpr int kPsnTRangeSqSlot = SIPNET_GPU_NPARAMS;  // pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
+constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 1;
+
+// flag bits (runtime mask / compile-time specialisation)
+enum : uint32_t {
+  F_EVENTS = 1u << 0,
+  F_GDD = 1u << 1,
+  F_GROWTH_RESP = 1u << 2,
+  F_LEAF_WATER = 1u << 3,
+  F_LITTER_POOL = 1u << 4,
+  F_SNOW = 1u << 5,
+  F_SOIL_PHENOL = 1u << 6,
+  F_WATER_HRESP = 1u << 7,
+  F_NITROGEN = 1u << 8,
+  F_ANAEROBIC = 1u << 9,
+  F_FLOODING = 1u << 10,
+  F_CSAT = 1u << 11,
+};
+
+// One climate step as staged to shared memory: 14 x 8 bytes = 112 bytes
+// (multiple of 16 so a chunk is a legal cp.async.bulk size).
+struct alignas(16) ClimRec {
+  double time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
+  // exp(-length * (1 / 30.0)) evaluated on the host with the host libm: the
+  // tillage decay factor of updateEventTrackers() (events.c:816) depends on the
+  // step length only, so it is hoisted out of the member loop.
+  double tillDecay;
+  int32_t year, day;
+  int32_t evBegin, evEnd;  // events of this step: [evBegin, evEnd) in the site's EventDev array
+};
+static_assert(sizeof(ClimRec) == 112, "ClimRec must be 112 bytes");
+
+struct alignas(16) EventDev {
+  double p[4];
+  int32_t type, method, pad0, pad1;
+};
+static_assert(sizeof(EventDev) == 48, "EventDev must be 48 bytes");
+
+struct SiteDev {
+  const ClimRec *clim;
+  const EventDev *events;
+  const double *neeObs;  // may be null
+  int64_t nsteps;
+  int32_t member0, memberCount;
+};
+
+struct BlockDesc {
+  int32_t site, member0, count, pad;
+};
+
+struct RunArgs {
+  int64_t ld;
+  int64_t nmembers;
+  const double *params;
+  double *state;
+  double *ringV;
+  double *ringW;
+  uint32_t *status;
+  const BlockDesc *blocks;
+  const SiteDev *sites;
+  int64_t stepBegin, stepEnd;
+  // outputs (null => not requested)
+  double *out;       // [ncols][outSteps][ld]
+  int64_t outSteps;  // steps in this run range
+  double *dbg;       // [NDEBUG][outSteps][ld]
+  double *loglik;    // [ld] accumulators
+  double *loglikN;   // [ld]
+  sipnet_gpu_event_record *recs;  // [nmembers][maxRecs]
+  int32_t *recCount;              // [nmembers]
+  int32_t maxRecs;
+  int32_t ringCap;
+  uint32_t flags;          // runtime flag mask (generic kernel)
+  double invSigma;         // 1 / nee_sigma
+  double logNorm;          // -log(sigma) - 0.5*log(2*pi)
+  int8_t colSlot[SIPNET_GPU_NOUT];  // output column -> slot in `out`, or -1
+};
+
+}  // namespace sip

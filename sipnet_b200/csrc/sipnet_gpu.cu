@@ -1,0 +1,718 @@
+// sipnet_gpu.cu -- implementation of the C ABI in include/sipnet_gpu.h.
+//
+// Host-side responsibilities (everything that is state-independent is decided
+// here, once, so the device loop carries no control plane):
+//   * validate the configuration the way the reference would fail at run time
+//     (processEvents(): non-positive step length -> 3, event without climate
+//     record -> 5, unknown irrigation method / event type -> 4; frontend.c:217:
+//     first event before first climate record -> 5)
+//   * bind every events.in row to the climate step on which the reference's
+//     gEvent pointer walk (events.c:471-481) would fire it
+//   * size the mean-NPP ring from the site's step lengths
+//   * build the block -> (site, member range) table
+//   * own all device memory, the stream and the timing events
+// There is no CPU compute path: without a CUDA device init() fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sip_types.cuh"
+
+namespace sip {
+#define SIP_DECLARE_NS(ns)                                                                                          \
+  namespace ns {                                                                                                    \
+  cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, cudaStream_t stream);         \
+  cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);   \
+  cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,      \
+                                const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,  \
+                                uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,               \
+                                cudaStream_t stream);                                                               \
+  }
+SIP_DECLARE_NS(val)
+SIP_DECLARE_NS(fast)
+cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
+                           int64_t nsites, double *mean, double *var, cudaStream_t stream);
+cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
+                             int64_t nsites, const double *probs, int nq, double *scratch, double *out,
+                             cudaStream_t stream);
+cudaError_t measure_fp64_peak(int device, double *tflops);
+}  // namespace sip
+
+using namespace sip;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(SIPNET_GPU_ERR_NO_DEVICE, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+  } while (0)
+
+struct sipnet_gpu_handle {
+  int device = 0;
+  uint32_t flags = 0;
+  uint32_t outputs = 0;
+  int math = 0;
+  int64_t nmembers = 0, ld = 0, nsites = 0, maxSteps = 0;
+  int64_t outCap = 0;      // steps of output kept per run
+  int64_t stepsDone = 0;   // next step to run
+  int64_t lastBegin = 0, lastEnd = 0;
+  int blockThreads = 128, nblocks = 0, ringCap = 0;
+  int ncols = 0;  // column slots in `out`
+  int8_t colSlot[SIPNET_GPU_NOUT];
+  std::vector<int32_t> summaryCols;
+  std::vector<double> quantiles;
+  int maxRecs = 0;
+  double sigma = 1.0;
+  bool sitesDiffer = false;
+  bool anyObs = false;
+
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  cudaEvent_t evStart = nullptr, evStop = nullptr, evT0 = nullptr, evT1 = nullptr;
+  int64_t launches = 0;
+
+  // device memory
+  double *params = nullptr, *state = nullptr, *ringV = nullptr, *ringW = nullptr;
+  uint32_t *status = nullptr;
+  int32_t *memberSite = nullptr;
+  BlockDesc *blocks = nullptr;
+  SiteDev *sites = nullptr;
+  std::vector<void *> siteAllocs;
+  double *out = nullptr, *dbg = nullptr, *loglik = nullptr, *loglikN = nullptr;
+  sipnet_gpu_event_record *recs = nullptr;
+  int32_t *recCount = nullptr;
+  double *mean = nullptr, *var = nullptr, *quant = nullptr, *qprobs = nullptr, *qscratch = nullptr;
+  bool summariesValid = false;
+  std::vector<SiteDev> hostSites;
+};
+
+static uint32_t flag_mask(const sipnet_gpu_flags &f) {
+  uint32_t m = 0;
+  if (f.events) m |= F_EVENTS;
+  if (f.gdd) m |= F_GDD;
+  if (f.growthResp) m |= F_GROWTH_RESP;
+  if (f.leafWater) m |= F_LEAF_WATER;
+  if (f.litterPool) m |= F_LITTER_POOL;
+  if (f.snow) m |= F_SNOW;
+  if (f.soilPhenol) m |= F_SOIL_PHENOL;
+  if (f.waterHResp) m |= F_WATER_HRESP;
+  if (f.nitrogenCycle) m |= F_NITROGEN;
+  if (f.anaerobic) m |= F_ANAEROBIC;
+  if (f.flooding) m |= F_FLOODING;
+  if (f.carbonSaturation) m |= F_CSAT;
+  return m;
+}
+
+// Build one site's ClimRec stream with events bound to steps.  Returns 0 or a reference exit code.
+static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimRec> &recs, std::vector<EventDev> &evs,
+                      double &minLen, int64_t siteIndex) {
+  if (s.nsteps <= 0) return fail(SIPNET_GPU_ERR_INPUT_FILE, "site %lld: no climate data", (long long)siteIndex);
+  const void *need[] = {s.year, s.day, s.time, s.length, s.tair, s.tsoil, s.par, s.precip,
+                        s.vpd,  s.vpdSoil, s.vPress, s.wspd, s.gdd};
+  for (const void *p : need)
+    if (p == nullptr) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "site %lld: NULL climate array", (long long)siteIndex);
+  const int64_t nev = (eventsOn && s.events != nullptr) ? s.nevents : 0;  // initEvents(), events.c:427-433
+  if (nev > 0) {  // frontend.c:217-222 / isFirstEventBefore(), events.c:437-447
+    const sipnet_gpu_event &e0 = s.events[0];
+    const bool before = (e0.year != s.year[0]) ? (e0.year < s.year[0]) : (e0.day < s.day[0]);
+    if (before)
+      return fail(SIPNET_GPU_ERR_INPUT_FILE, "site %lld: first event occurs before the start of the climate file",
+                  (long long)siteIndex);
+  }
+  recs.resize((size_t)s.nsteps);
+  evs.clear();
+  evs.reserve((size_t)nev);
+  int64_t e = 0;
+  for (int64_t t = 0; t < s.nsteps; ++t) {
+    ClimRec &c = recs[(size_t)t];
+    c.time = s.time[t];
+    c.length = s.length[t];
+    c.tair = s.tair[t];
+    c.tsoil = s.tsoil[t];
+    c.par = s.par[t];
+    c.precip = s.precip[t];
+    c.vpd = s.vpd[t];
+    c.vpdSoil = s.vpdSoil[t];
+    c.vPress = s.vPress[t];
+    c.wspd = s.wspd[t];
+    c.gdd = s.gdd[t];
+    c.year = s.year[t];
+    c.day = s.day[t];
+    if (!(c.length > 0))  // events.c:460-465
+      return fail(SIPNET_GPU_ERR_BAD_PARAMETER_VALUE, "site %lld: climate length (%f) on year %d day %d is non-positive",
+                  (long long)siteIndex, c.length, c.year, c.day);
+    minLen = std::min(minLen, c.length);
+    c.tillDecay = std::exp(-c.length * (1 / 30.0));  // events.c:816, events.h:58
+    c.evBegin = (int32_t)e;
+    while (e < nev && s.events[e].year <= c.year && s.events[e].day <= c.day) {  // events.c:471
+      const sipnet_gpu_event &ev = s.events[e];
+      if (ev.year < c.year || ev.day < c.day)  // events.c:476-481
+        return fail(SIPNET_GPU_ERR_INPUT_FILE,
+                    "site %lld: agronomic event for year %d day %d has no corresponding climate record",
+                    (long long)siteIndex, ev.year, ev.day);
+      if (ev.type < SIPNET_EV_FERTILIZATION || ev.type > SIPNET_EV_PLANTDEATH)  // events.c:735-737
+        return fail(SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown event type %d", (long long)siteIndex, ev.type);
+      if (ev.type == SIPNET_EV_IRRIGATION && ev.method != 0 && ev.method != 1)  // events.c:498-501
+        return fail(SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown irrigation method type: %d",
+                    (long long)siteIndex, ev.method);
+      EventDev d;
+      for (int k = 0; k < 4; ++k) d.p[k] = ev.p[k];
+      d.type = ev.type;
+      d.method = ev.method;
+      d.pad0 = d.pad1 = 0;
+      evs.push_back(d);
+      ++e;
+    }
+    c.evEnd = (int32_t)e;
+  }
+  return 0;
+}
+
+static void free_handle(sipnet_gpu_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
+                  h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant, h->qprobs,
+                  h->qscratch};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (void *p : h->siteAllocs)
+    if (p) cudaFree(p);
+  if (h->evStart) cudaEventDestroy(h->evStart);
+  if (h->evStop) cudaEventDestroy(h->evStop);
+  if (h->evT0) cudaEventDestroy(h->evT0);
+  if (h->evT1) cudaEventDestroy(h->evT1);
+  if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+template <class T>
+static cudaError_t dalloc(T **p, size_t count) {
+  return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+static int run_init_state(sipnet_gpu_handle *h) {
+  cudaError_t e;
+  if (h->math == SIPNET_GPU_MATH_FAST)
+    e = fast::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state, h->ringV,
+                                h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
+  else
+    e = val::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state, h->ringV,
+                               h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "init_state launch failed: %s", cudaGetErrorString(e));
+  h->stepsDone = 0;
+  h->lastBegin = h->lastEnd = 0;
+  h->summariesValid = false;
+  return 0;
+}
+
+static int derive_params(sipnet_gpu_handle *h);
+
+extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle **out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL config or handle pointer");
+  if (cfg->abi_version != SIPNET_GPU_ABI_VERSION)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "ABI version mismatch: caller %d, library %d", cfg->abi_version,
+                SIPNET_GPU_ABI_VERSION);
+  if (cfg->nsites <= 0 || !cfg->sites) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no sites");
+  if (cfg->nmembers <= 0 || !cfg->params) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no members / params");
+  if (cfg->params_ld < cfg->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "params_ld < nmembers");
+  if (cfg->math != SIPNET_GPU_MATH_VALIDATION && cfg->math != SIPNET_GPU_MATH_FAST)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "unknown math mode %d", cfg->math);
+  if (cfg->block_threads != 0 && cfg->block_threads != 32 && cfg->block_threads != 64 && cfg->block_threads != 128)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "block_threads must be 0, 32, 64 or 128");
+  if ((cfg->outputs & SIPNET_GPU_OUT_LOGLIK) && !(cfg->nee_sigma > 0))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "nee_sigma must be > 0");
+  if ((cfg->outputs & (SIPNET_GPU_OUT_MOMENTS | SIPNET_GPU_OUT_QUANTILES)) &&
+      (cfg->n_summary_cols <= 0 || !cfg->summary_cols))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "summary outputs need summary_cols");
+  if ((cfg->outputs & SIPNET_GPU_OUT_QUANTILES) && (cfg->n_quantiles <= 0 || !cfg->quantiles))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "quantile output needs quantiles");
+  for (int i = 0; i < cfg->n_summary_cols; ++i)
+    if (cfg->summary_cols[i] < 0 || cfg->summary_cols[i] >= SIPNET_GPU_NOUT)
+      return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "summary column %d out of range", cfg->summary_cols[i]);
+  for (int i = 0; i < cfg->n_quantiles; ++i)
+    if (!(cfg->quantiles[i] >= 0.0 && cfg->quantiles[i] <= 1.0))
+      return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "quantile probability out of [0,1]");
+
+  // member -> site map: non-decreasing
+  std::vector<int32_t> memberSite((size_t)cfg->nmembers, 0);
+  if (cfg->member_site) {
+    for (int64_t m = 0; m < cfg->nmembers; ++m) {
+      const int32_t s = cfg->member_site[m];
+      if (s < 0 || s >= cfg->nsites) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "member_site[%lld] out of range", (long long)m);
+      if (m > 0 && s < cfg->member_site[m - 1])
+        return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "member_site must be non-decreasing");
+      memberSite[(size_t)m] = s;
+    }
+  }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(SIPNET_GPU_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", cfg->device);
+  CUDA_OK(cudaSetDevice(cfg->device));
+
+  sipnet_gpu_handle *h = new sipnet_gpu_handle();
+  h->device = cfg->device;
+  h->flags = flag_mask(cfg->flags);
+  h->outputs = cfg->outputs;
+  h->math = cfg->math;
+  h->nmembers = cfg->nmembers;
+  h->ld = (cfg->nmembers + 15) / 16 * 16;
+  h->nsites = cfg->nsites;
+  h->sigma = cfg->nee_sigma > 0 ? cfg->nee_sigma : 1.0;
+  h->maxRecs = (cfg->outputs & SIPNET_GPU_OUT_EVENTS) ? std::max(cfg->max_event_records, 0) : 0;
+  h->summaryCols.assign(cfg->summary_cols, cfg->summary_cols + std::max(cfg->n_summary_cols, 0));
+  h->quantiles.assign(cfg->quantiles, cfg->quantiles + std::max(cfg->n_quantiles, 0));
+
+#define INIT_CUDA(expr)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      int rc__ = fail(SIPNET_GPU_ERR_NO_DEVICE, "%s failed: %s", #expr, cudaGetErrorString(e__));        \
+      free_handle(h);                                                                                    \
+      return rc__;                                                                                       \
+    }                                                                                                    \
+  } while (0)
+
+  if (cfg->stream) {
+    h->stream = (cudaStream_t)cfg->stream;
+  } else {
+    INIT_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->ownStream = true;
+  }
+  INIT_CUDA(cudaEventCreate(&h->evStart));
+  INIT_CUDA(cudaEventCreate(&h->evStop));
+  INIT_CUDA(cudaEventCreate(&h->evT0));
+  INIT_CUDA(cudaEventCreate(&h->evT1));
+
+  // ---- sites ----
+  h->hostSites.resize((size_t)cfg->nsites);
+  double minLen = 1e300;
+  std::vector<ClimRec> recs;
+  std::vector<EventDev> evs;
+  int64_t firstLen = cfg->sites[0].nsteps;
+  for (int64_t s = 0; s < cfg->nsites; ++s) {
+    int rc = build_site(cfg->sites[s], cfg->flags.events != 0, recs, evs, minLen, s);
+    if (rc) {
+      free_handle(h);
+      return rc;
+    }
+    SiteDev &sd = h->hostSites[(size_t)s];
+    sd.nsteps = cfg->sites[s].nsteps;
+    sd.member0 = 0;
+    sd.memberCount = 0;
+    h->maxSteps = std::max(h->maxSteps, sd.nsteps);
+    if (sd.nsteps != firstLen) h->sitesDiffer = true;
+    ClimRec *dClim = nullptr;
+    INIT_CUDA(dalloc(&dClim, recs.size()));
+    h->siteAllocs.push_back(dClim);
+    INIT_CUDA(cudaMemcpyAsync(dClim, recs.data(), recs.size() * sizeof(ClimRec), cudaMemcpyHostToDevice, h->stream));
+    INIT_CUDA(cudaStreamSynchronize(h->stream));  // recs is reused for the next site
+    sd.clim = dClim;
+    EventDev *dEv = nullptr;
+    INIT_CUDA(dalloc(&dEv, evs.size()));
+    h->siteAllocs.push_back(dEv);
+    if (!evs.empty()) INIT_CUDA(cudaMemcpy(dEv, evs.data(), evs.size() * sizeof(EventDev), cudaMemcpyHostToDevice));
+    sd.events = dEv;
+    sd.neeObs = nullptr;
+    if ((cfg->outputs & SIPNET_GPU_OUT_LOGLIK) && cfg->sites[s].nee_obs) {
+      double *dObs = nullptr;
+      INIT_CUDA(dalloc(&dObs, (size_t)sd.nsteps));
+      h->siteAllocs.push_back(dObs);
+      INIT_CUDA(cudaMemcpy(dObs, cfg->sites[s].nee_obs, (size_t)sd.nsteps * sizeof(double), cudaMemcpyHostToDevice));
+      sd.neeObs = dObs;
+      h->anyObs = true;
+    }
+  }
+  // ring capacity: occupancy <= 1 partially evicted entry + floor(5/minLen) whole entries (+ slack), capped like
+  // the reference (MEAN_NPP_MAX_ENTRIES, sipnet.c:40) so the overflow condition is the reference's.
+  {
+    double bound = std::floor(kMeanNppDays / minLen) + 3.0;
+    h->ringCap = (int)std::min<double>(kRingMax, std::max(2.0, bound));
+  }
+
+  // ---- members, blocks ----
+  {
+    int64_t m = 0;
+    while (m < cfg->nmembers) {
+      const int32_t s = memberSite[(size_t)m];
+      int64_t m1 = m;
+      while (m1 < cfg->nmembers && memberSite[(size_t)m1] == s) ++m1;
+      h->hostSites[(size_t)s].member0 = (int32_t)m;
+      h->hostSites[(size_t)s].memberCount = (int32_t)(m1 - m);
+      m = m1;
+    }
+  }
+  auto count_blocks = [&](int bt) {
+    int64_t n = 0;
+    for (const SiteDev &sd : h->hostSites) n += (sd.memberCount + bt - 1) / bt;
+    return n;
+  };
+  if (cfg->block_threads) {
+    h->blockThreads = cfg->block_threads;
+  } else {
+    int smCount = 148;
+    cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, cfg->device);
+    h->blockThreads = 32;
+    for (int bt : {128, 64}) {  // largest block that still gives every SM >= 2 blocks
+      if (count_blocks(bt) >= 2 * (int64_t)smCount) {
+        h->blockThreads = bt;
+        break;
+      }
+    }
+  }
+  std::vector<BlockDesc> blocks;
+  for (int64_t s = 0; s < cfg->nsites; ++s) {
+    const SiteDev &sd = h->hostSites[(size_t)s];
+    for (int32_t off = 0; off < sd.memberCount; off += h->blockThreads)
+      blocks.push_back(BlockDesc{(int32_t)s, sd.member0 + off, std::min(h->blockThreads, sd.memberCount - off), 0});
+  }
+  h->nblocks = (int)blocks.size();
+
+  INIT_CUDA(dalloc(&h->sites, h->hostSites.size()));
+  INIT_CUDA(cudaMemcpy(h->sites, h->hostSites.data(), h->hostSites.size() * sizeof(SiteDev), cudaMemcpyHostToDevice));
+  INIT_CUDA(dalloc(&h->blocks, blocks.size()));
+  INIT_CUDA(cudaMemcpy(h->blocks, blocks.data(), blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice));
+  INIT_CUDA(dalloc(&h->memberSite, memberSite.size()));
+  INIT_CUDA(cudaMemcpy(h->memberSite, memberSite.data(), memberSite.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+  // ---- parameters: upload raw rows, derive in place ----
+  INIT_CUDA(dalloc(&h->params, (size_t)kNParamDev * h->ld));
+  INIT_CUDA(cudaMemsetAsync(h->params, 0, (size_t)kNParamDev * h->ld * sizeof(double), h->stream));
+  INIT_CUDA(cudaMemcpy2DAsync(h->params, h->ld * sizeof(double), cfg->params, cfg->params_ld * sizeof(double),
+                              cfg->nmembers * sizeof(double), SIPNET_GPU_NPARAMS, cudaMemcpyHostToDevice, h->stream));
+  INIT_CUDA(dalloc(&h->status, (size_t)h->ld));
+  INIT_CUDA(cudaMemsetAsync(h->status, 0, (size_t)h->ld * sizeof(uint32_t), h->stream));
+  INIT_CUDA(dalloc(&h->state, (size_t)SIPNET_GPU_NSTATE * h->ld));
+  INIT_CUDA(cudaMemsetAsync(h->state, 0, (size_t)SIPNET_GPU_NSTATE * h->ld * sizeof(double), h->stream));
+  INIT_CUDA(dalloc(&h->ringV, (size_t)h->ringCap * h->ld));
+  INIT_CUDA(dalloc(&h->ringW, (size_t)h->ringCap * h->ld));
+  INIT_CUDA(cudaMemsetAsync(h->ringV, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
+  INIT_CUDA(cudaMemsetAsync(h->ringW, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
+
+  // ---- outputs ----
+  h->outCap = cfg->out_steps_capacity > 0 ? std::min(cfg->out_steps_capacity, h->maxSteps) : h->maxSteps;
+  for (int c = 0; c < SIPNET_GPU_NOUT; ++c) h->colSlot[c] = -1;
+  if (cfg->outputs & SIPNET_GPU_OUT_FULL) {
+    for (int c = 0; c < SIPNET_GPU_NOUT; ++c) h->colSlot[c] = (int8_t)c;
+    h->ncols = SIPNET_GPU_NOUT;
+  } else if (cfg->outputs & (SIPNET_GPU_OUT_MOMENTS | SIPNET_GPU_OUT_QUANTILES)) {
+    for (int32_t c : h->summaryCols)
+      if (h->colSlot[c] < 0) h->colSlot[c] = (int8_t)h->ncols++;
+  }
+  if (h->ncols > 0) INIT_CUDA(dalloc(&h->out, (size_t)h->ncols * h->outCap * h->ld));
+  if (cfg->outputs & SIPNET_GPU_OUT_DEBUG) INIT_CUDA(dalloc(&h->dbg, (size_t)SIPNET_GPU_NDEBUG * h->outCap * h->ld));
+  if (cfg->outputs & SIPNET_GPU_OUT_LOGLIK) {
+    INIT_CUDA(dalloc(&h->loglik, (size_t)h->ld));
+    INIT_CUDA(dalloc(&h->loglikN, (size_t)h->ld));
+  }
+  if (cfg->outputs & SIPNET_GPU_OUT_EVENTS) {
+    INIT_CUDA(dalloc(&h->recCount, (size_t)h->ld));
+    if (h->maxRecs > 0) INIT_CUDA(dalloc(&h->recs, (size_t)h->nmembers * h->maxRecs));
+  }
+  const size_t nsum = (size_t)h->nsites * h->summaryCols.size() * h->outCap;
+  if (cfg->outputs & SIPNET_GPU_OUT_MOMENTS) {
+    INIT_CUDA(dalloc(&h->mean, nsum));
+    INIT_CUDA(dalloc(&h->var, nsum));
+  }
+  if (cfg->outputs & SIPNET_GPU_OUT_QUANTILES) {
+    INIT_CUDA(dalloc(&h->quant, nsum * h->quantiles.size()));
+    INIT_CUDA(dalloc(&h->qprobs, h->quantiles.size()));
+    INIT_CUDA(cudaMemcpy(h->qprobs, h->quantiles.data(), h->quantiles.size() * sizeof(double), cudaMemcpyHostToDevice));
+    INIT_CUDA(dalloc(&h->qscratch, (size_t)h->ld * 2));
+  }
+
+  // ---- setupModel() on the device ----
+  {
+    int rc = derive_params(h);
+    if (rc) {
+      free_handle(h);
+      return rc;
+    }
+  }
+  {
+    int rc = run_init_state(h);
+    if (rc) {
+      free_handle(h);
+      return rc;
+    }
+  }
+  INIT_CUDA(cudaStreamSynchronize(h->stream));
+#undef INIT_CUDA
+  *out = h;
+  return SIPNET_GPU_OK;
+}
+
+static int derive_params(sipnet_gpu_handle *h) {
+  cudaError_t e = (h->math == SIPNET_GPU_MATH_FAST)
+                      ? fast::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream)
+                      : val::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "derive launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int sipnet_gpu_set_params(sipnet_gpu_handle *h, const double *params, int64_t params_ld) {
+  if (!h || !params) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle or params");
+  if (params_ld < h->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "params_ld < nmembers");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemcpy2DAsync(h->params, h->ld * sizeof(double), params, params_ld * sizeof(double),
+                            h->nmembers * sizeof(double), SIPNET_GPU_NPARAMS, cudaMemcpyHostToDevice, h->stream));
+  int rc = derive_params(h);
+  if (rc) return rc;
+  return run_init_state(h);
+}
+
+extern "C" int sipnet_gpu_timer_start(sipnet_gpu_handle *h) {
+  if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaEventRecord(h->evT0, h->stream));
+  return 0;
+}
+
+extern "C" int sipnet_gpu_timer_stop_ms(sipnet_gpu_handle *h, float *ms) {
+  if (!h || !ms) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaEventRecord(h->evT1, h->stream));
+  CUDA_OK(cudaEventSynchronize(h->evT1));
+  CUDA_OK(cudaEventElapsedTime(ms, h->evT0, h->evT1));
+  return 0;
+}
+
+extern "C" int sipnet_gpu_reset(sipnet_gpu_handle *h) {
+  if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  return run_init_state(h);
+}
+
+extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end) {
+  if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
+  if (step_begin != h->stepsDone)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "step_begin %lld is not the next step (%lld): segments must be contiguous",
+                (long long)step_begin, (long long)h->stepsDone);
+  if (step_end < step_begin || step_end > h->maxSteps)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "bad step range [%lld, %lld) for %lld steps", (long long)step_begin,
+                (long long)step_end, (long long)h->maxSteps);
+  const bool keeps = (h->out != nullptr) || (h->dbg != nullptr);
+  if (keeps && step_end - step_begin > h->outCap)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "run range of %lld steps exceeds out_steps_capacity %lld",
+                (long long)(step_end - step_begin), (long long)h->outCap);
+  CUDA_OK(cudaSetDevice(h->device));
+  h->lastBegin = step_begin;
+  h->lastEnd = step_end;
+  h->summariesValid = false;
+  if (step_end == step_begin) return SIPNET_GPU_OK;
+
+  RunArgs a;
+  memset(&a, 0, sizeof a);
+  a.ld = h->ld;
+  a.nmembers = h->nmembers;
+  a.params = h->params;
+  a.state = h->state;
+  a.ringV = h->ringV;
+  a.ringW = h->ringW;
+  a.status = h->status;
+  a.blocks = h->blocks;
+  a.sites = h->sites;
+  a.stepBegin = step_begin;
+  a.stepEnd = step_end;
+  a.out = h->out;
+  a.outSteps = step_end - step_begin;
+  a.dbg = h->dbg;
+  a.loglik = h->loglik;
+  a.loglikN = h->loglikN;
+  a.recs = h->recs;
+  a.recCount = h->recCount;
+  a.maxRecs = h->maxRecs;
+  a.ringCap = h->ringCap;
+  a.flags = h->flags;
+  a.invSigma = 1.0 / h->sigma;
+  a.logNorm = -std::log(h->sigma) - 0.5 * std::log(2.0 * M_PI);
+  memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);
+
+  if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
+    if (h->out) CUDA_OK(cudaMemsetAsync(h->out, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
+    if (h->dbg)
+      CUDA_OK(cudaMemsetAsync(h->dbg, 0xFF, (size_t)SIPNET_GPU_NDEBUG * a.outSteps * h->ld * sizeof(double), h->stream));
+  }
+  CUDA_OK(cudaEventRecord(h->evStart, h->stream));
+  cudaError_t e = (h->math == SIPNET_GPU_MATH_FAST)
+                      ? fast::launch_run(a, h->nblocks, h->blockThreads, h->dbg != nullptr, h->stream)
+                      : val::launch_run(a, h->nblocks, h->blockThreads, h->dbg != nullptr, h->stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "run launch failed: %s", cudaGetErrorString(e));
+  CUDA_OK(cudaEventRecord(h->evStop, h->stream));
+  h->stepsDone = step_end;
+  return SIPNET_GPU_OK;
+}
+
+static int ensure_summaries(sipnet_gpu_handle *h) {
+  if (h->summariesValid) return 0;
+  const int64_t n = h->lastEnd - h->lastBegin;
+  if (n <= 0) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no run range to summarise");
+  // summary columns occupy `out` slots; with OUT_FULL the slot of column c is c itself
+  const int ns = (int)h->summaryCols.size();
+  for (int i = 0; i < ns; ++i) {
+    const int slot = h->colSlot[h->summaryCols[(size_t)i]];
+    const double *cols = h->out + (size_t)slot * n * h->ld;
+    if (h->mean) {
+      cudaError_t e = launch_moments(cols, h->ld, n, 1, h->sites, h->nsites, h->mean + (size_t)i * h->nsites * n,
+                                     h->var + (size_t)i * h->nsites * n, h->stream);
+      h->launches++;
+      if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "moments launch failed: %s", cudaGetErrorString(e));
+    }
+    if (h->quant) {
+      cudaError_t e = launch_quantiles(cols, h->ld, n, 1, h->sites, h->nsites, h->qprobs, (int)h->quantiles.size(),
+                                       h->qscratch, h->quant + (size_t)i * h->nsites * h->quantiles.size() * n,
+                                       h->stream);
+      h->launches++;
+      if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "quantile launch failed: %s", cudaGetErrorString(e));
+    }
+  }
+  h->summariesValid = true;
+  return 0;
+}
+
+extern "C" size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what) {
+  if (!h) return 0;
+  const size_t n = (size_t)(h->lastEnd - h->lastBegin);
+  const size_t M = (size_t)h->nmembers;
+  const size_t ns = h->summaryCols.size();
+  switch (what) {
+    case SIPNET_GPU_GATHER_FULL: return (h->outputs & SIPNET_GPU_OUT_FULL) ? SIPNET_GPU_NOUT * n * M * 8 : 0;
+    case SIPNET_GPU_GATHER_DEBUG: return h->dbg ? (size_t)SIPNET_GPU_NDEBUG * n * M * 8 : 0;
+    case SIPNET_GPU_GATHER_LOGLIK:
+    case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglik ? M * 8 : 0;
+    case SIPNET_GPU_GATHER_STATUS: return M * 4;
+    case SIPNET_GPU_GATHER_STATE: return (size_t)SIPNET_GPU_NSTATE * M * 8;
+    case SIPNET_GPU_GATHER_MEAN:
+    case SIPNET_GPU_GATHER_VARIANCE: return h->mean ? (size_t)h->nsites * ns * n * 8 : 0;
+    case SIPNET_GPU_GATHER_QUANTILES: return h->quant ? (size_t)h->nsites * ns * h->quantiles.size() * n * 8 : 0;
+    case SIPNET_GPU_GATHER_EVENT_COUNTS: return h->recCount ? M * 4 : 0;
+    case SIPNET_GPU_GATHER_EVENT_RECORDS: return h->recs ? M * (size_t)h->maxRecs * sizeof(sipnet_gpu_event_record) : 0;
+    default: return 0;
+  }
+}
+
+// rows x nmembers doubles out of a [rows][ld] device array
+static int copy_rows(sipnet_gpu_handle *h, void *dst, const void *src, size_t rows, size_t elem) {
+  CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)h->nmembers * elem, src, (size_t)h->ld * elem, (size_t)h->nmembers * elem, rows,
+                            cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size_t bytes) {
+  if (!h || !dst) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle or destination");
+  const size_t need = sipnet_gpu_gather_bytes(h, what);
+  if (need == 0) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "gather(%d): output was not requested at init or nothing has run", what);
+  if (bytes != need)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "gather(%d): buffer is %zu bytes, expected %zu", what, bytes, need);
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t n = (size_t)(h->lastEnd - h->lastBegin);
+  switch (what) {
+    case SIPNET_GPU_GATHER_FULL: return copy_rows(h, dst, h->out, SIPNET_GPU_NOUT * n, 8);
+    case SIPNET_GPU_GATHER_DEBUG: return copy_rows(h, dst, h->dbg, (size_t)SIPNET_GPU_NDEBUG * n, 8);
+    case SIPNET_GPU_GATHER_LOGLIK: return copy_rows(h, dst, h->loglik, 1, 8);
+    case SIPNET_GPU_GATHER_LOGLIK_N: return copy_rows(h, dst, h->loglikN, 1, 8);
+    case SIPNET_GPU_GATHER_STATUS: return copy_rows(h, dst, h->status, 1, 4);
+    case SIPNET_GPU_GATHER_STATE: return copy_rows(h, dst, h->state, SIPNET_GPU_NSTATE, 8);
+    case SIPNET_GPU_GATHER_EVENT_COUNTS: return copy_rows(h, dst, h->recCount, 1, 4);
+    case SIPNET_GPU_GATHER_EVENT_RECORDS:
+      CUDA_OK(cudaMemcpyAsync(dst, h->recs, need, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      return 0;
+    case SIPNET_GPU_GATHER_MEAN:
+    case SIPNET_GPU_GATHER_VARIANCE:
+    case SIPNET_GPU_GATHER_QUANTILES: {
+      int rc = ensure_summaries(h);
+      if (rc) return rc;
+      // device layout is [col][site][...][n]; the ABI promises [site][col][...][n]
+      const size_t ns = h->summaryCols.size();
+      const size_t inner = (what == SIPNET_GPU_GATHER_QUANTILES ? h->quantiles.size() : 1) * n;
+      const double *src = what == SIPNET_GPU_GATHER_MEAN ? h->mean : what == SIPNET_GPU_GATHER_VARIANCE ? h->var : h->quant;
+      for (size_t c = 0; c < ns; ++c)
+        for (size_t s = 0; s < (size_t)h->nsites; ++s)
+          CUDA_OK(cudaMemcpyAsync((double *)dst + (s * ns + c) * inner, src + (c * (size_t)h->nsites + s) * inner,
+                                  inner * 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      return 0;
+    }
+    default: return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "unknown gather selector %d", what);
+  }
+}
+
+extern "C" int sipnet_gpu_sync(sipnet_gpu_handle *h) {
+  if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" void sipnet_gpu_destroy(sipnet_gpu_handle *h) { free_handle(h); }
+
+extern "C" int sipnet_gpu_last_run_ms(sipnet_gpu_handle *h, float *ms) {
+  if (!h || !ms) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaEventSynchronize(h->evStop));
+  CUDA_OK(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+  return 0;
+}
+
+extern "C" int64_t sipnet_gpu_launch_count(const sipnet_gpu_handle *h) { return h ? h->launches : 0; }
+
+extern "C" void *sipnet_gpu_device_ptr(sipnet_gpu_handle *h, int what) {
+  if (!h) return nullptr;
+  switch (what) {
+    case SIPNET_GPU_GATHER_FULL: return h->out;
+    case SIPNET_GPU_GATHER_DEBUG: return h->dbg;
+    case SIPNET_GPU_GATHER_LOGLIK: return h->loglik;
+    case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglikN;
+    case SIPNET_GPU_GATHER_STATUS: return h->status;
+    case SIPNET_GPU_GATHER_STATE: return h->state;
+    case SIPNET_GPU_GATHER_MEAN: return ensure_summaries(h) ? nullptr : h->mean;
+    case SIPNET_GPU_GATHER_VARIANCE: return ensure_summaries(h) ? nullptr : h->var;
+    case SIPNET_GPU_GATHER_QUANTILES: return ensure_summaries(h) ? nullptr : h->quant;
+    default: return nullptr;
+  }
+}
+
+extern "C" void *sipnet_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void sipnet_gpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+extern "C" const char *sipnet_gpu_last_error(void) { return g_err.c_str(); }
+extern "C" int sipnet_gpu_abi_version(void) { return SIPNET_GPU_ABI_VERSION; }
+
+extern "C" int sipnet_gpu_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", device);
+  CUDA_OK(measure_fp64_peak(device, tflops));
+  return 0;
+}

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference and oracle/_ref built by
+`make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+For every case it stores, in tests/golden/<case>.npz:
+  inputs   flags[12], params[80] (as left by the reference's readParamData),
+           year/day/clim[11][T] (as left by the reference's readClimData),
+           events[n][8] (year, day, type, method, p0..p3 from readEventData)
+  outputs  produced by the reference's own setupModel()/updateState() loop via
+           oracle/ref_shim.c, at full double precision:
+           rows      step indices kept (first 48, every 16th, last 8)
+           out32     [len(rows)][32]  outputState() columns
+           dbg       [len(rows)][106] every Envi/Fluxes/Trackers field
+           colsum    [32]  sum over ALL steps of each output column (float64, step order)
+           colabs    [32]  max |value| over all steps
+           nsteps, rc
+  text     the reference's events.out (exact bytes) and an md5 of its sipnet.out
+
+Cases: the reference's four active smoke cases (tests/smoke/{niwot,russell_1..3})
+and synthetic cases that reach the branches the smoke goldens miss
+(planting/harvest/tillage/canopy irrigation/mortality/N limitation).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.pyoracle import RefShim  # noqa: E402
+from sipnet_b200 import _abi as A, synth  # noqa: E402
+from sipnet_b200.api import flags_array  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+SMOKE = {
+    "niwot": {},
+    "russell_1": {},
+    "russell_2": dict(litterPool=1, nitrogenCycle=1, anaerobic=1),
+    "russell_3": dict(growthResp=1, leafWater=1, litterPool=1, waterHResp=0),
+}
+
+
+def keep_rows(T: int) -> np.ndarray:
+    rows = set(range(min(48, T))) | set(range(0, T, 16)) | set(range(max(T - 8, 0), T))
+    return np.array(sorted(rows), dtype=np.int64)
+
+
+def events_matrix(events) -> np.ndarray:
+    return np.array([list(map(float, e)) for e in events], dtype=np.float64).reshape(-1, 8)
+
+
+def run_case(shim: RefShim, name: str, flags: dict, params: np.ndarray, site, print_header=1):
+    with tempfile.TemporaryDirectory() as td:
+        ev_out = os.path.join(td, "events.out")
+        main_out = os.path.join(td, "sipnet.out")
+        rc, done, out, dbg = shim.run(flags, params, site, events_out=ev_out, main_out=main_out,
+                                      print_header=print_header)
+        ev_text = open(ev_out, "rb").read() if os.path.exists(ev_out) else b""
+        main_md5 = hashlib.md5(open(main_out, "rb").read()).hexdigest()
+    rows = keep_rows(done)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        flags=flags_array(flags), params=params, year=site.year, day=site.day,
+        clim=np.stack([site.clim[k] for k in A.CLIM_COLS]), events=events_matrix(site.events),
+        rows=rows, out32=out[rows], dbg=dbg[rows], colsum=out[:done].sum(axis=0),
+        colabs=np.abs(out[:done]).max(axis=0), nsteps=np.int64(done), rc=np.int64(rc),
+        print_header=np.int64(print_header),
+        events_out=np.frombuffer(ev_text, dtype=np.uint8), main_out_md5=np.frombuffer(main_md5.encode(), dtype=np.uint8))
+    print(f"{name}: rc={rc} steps={done} rows={rows.size} events.out={len(ev_text)}B")
+
+
+def main():
+    shim = RefShim()
+    for name, flags in SMOKE.items():
+        d = os.path.join(REF, "tests", "smoke", name)
+        full = dict(A.DEFAULT_FLAGS)
+        full.update(flags)
+        site = shim.read_clim(os.path.join(d, "sipnet.clim"), full["gdd"])
+        site.events = shim.read_events(os.path.join(d, "events.in"))
+        params = shim.read_params(os.path.join(d, "sipnet.param"), full)
+        run_case(shim, "smoke_" + name, full, params, site, print_header=0 if name == "niwot" else 1)
+    # synthetic: C3-style event schedule, two members of the wide prior + the anchor, 3 years
+    for variant in ("half-daily", "unequal"):
+        site = synth.synth_site(3, 3, variant, with_events=True)
+        P = synth.synth_params(8, stream=3)
+        for m in (0, 1, 5):
+            run_case(shim, f"synth_{variant.replace('-', '')}_m{m}", synth.SYNTH_FLAGS, P[:, m], site)
+
+
+if __name__ == "__main__":
+    main()

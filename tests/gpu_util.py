@@ -1,0 +1,45 @@
+"""Shared helpers for the GPU parity tests."""
+import numpy as np
+
+from sipnet_b200 import _abi as A
+
+RTOL = 1e-10  # north_star: "all state pools and fluxes within 1e-10 relative"
+
+# fields that must match EXACTLY (branch / event / clamp decisions)
+EXACT_DEBUG = ("t.lastYear", "pt.didLeafGrowth", "pt.didLeafFall", "pt.lastYear", "s.isAlive")
+
+
+def column_scales(ref: np.ndarray) -> np.ndarray:
+    """Per-column magnitude over the run: max_t |col| (>= tiny).  ref is [T][ncol]."""
+    s = np.nanmax(np.abs(ref), axis=0)
+    return np.where(s > 0, s, 1.0)
+
+
+def debug_scales(ref_dbg: np.ndarray) -> np.ndarray:
+    s = column_scales(ref_dbg)
+    # plantCAccountingDelta is a cancellation accumulator whose terms are ~plantWoodC
+    # (SURVEY 7 hard part 2): scale it by plantWoodC.
+    s[A.D["envi.plantCAccountingDelta"]] = max(s[A.D["envi.plantCAccountingDelta"]], s[A.D["envi.plantWoodC"]])
+    return s
+
+
+def out_scales(ref_out: np.ndarray) -> np.ndarray:
+    s = column_scales(ref_out)
+    s[A.O["nppStorage"]] = max(s[A.O["nppStorage"]], s[A.O["plantWoodC"]])
+    return s
+
+
+def max_rel(a: np.ndarray, b: np.ndarray, scale: np.ndarray) -> np.ndarray:
+    """max over time of |a-b| / max(|a|,|b|,floor) per column, floor = 1e-6 * column magnitude:
+    strict relative error except for values six orders below the column's own scale."""
+    den = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-6 * scale[None, :])
+    err = np.abs(a - b) / den
+    err = np.where(np.isnan(a) & np.isnan(b), 0.0, err)
+    return np.nanmax(err, axis=0)
+
+
+def assert_close(a, b, scale, names, rtol=RTOL, what=""):
+    e = max_rel(a, b, scale)
+    bad = np.argwhere(~(e <= rtol)).ravel()
+    assert bad.size == 0, what + " " + ", ".join(f"{names[i]}={e[i]:.3e}" for i in bad[:8])
+    return float(np.nanmax(e)) if e.size else 0.0

@@ -1,0 +1,208 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle.
+
+Bars (north_star): event day/type application and pool-clamping branches EXACT;
+all state pools and fluxes within 1e-10 relative (FP64, fmad disabled on the
+validation build).  The tolerance is written in gpu_util.RTOL."""
+import numpy as np
+import pytest
+
+from conftest import Golden, golden_names
+from gpu_util import EXACT_DEBUG, RTOL, assert_close, debug_scales, out_scales
+from sipnet_b200 import _abi as A, api, synth
+
+pytestmark = pytest.mark.gpu
+
+ALL = A.OUT_FULL | A.OUT_DEBUG | A.OUT_EVENTS
+
+
+def run_gpu(sites, params, member_site, flags, outputs=ALL, math=A.MATH_VALIDATION, **kw):
+    ens = api.Ensemble(sites, params, member_site, flags, outputs=outputs, math=math, max_event_records=4096
+                       if outputs & A.OUT_EVENTS else 0, **kw)
+    ens.run()
+    res = dict(out=ens.output() if outputs & A.OUT_FULL else None,
+               dbg=ens.debug() if outputs & A.OUT_DEBUG else None,
+               status=ens.status(), state=ens.state(),
+               recs=ens.event_records() if outputs & A.OUT_EVENTS else None)
+    ens.close()
+    return res
+
+
+def check_member(res, m, o_out, o_dbg, o_recs, rtol=RTOL, tag=""):
+    T = o_out.shape[0]
+    g_out = res["out"][:, :T, m].T
+    g_dbg = res["dbg"][:, :T, m].T
+    for name in EXACT_DEBUG:
+        k = A.D[name]
+        assert np.array_equal(g_dbg[:, k], o_dbg[:, k]), f"{tag} {name} differs (branch decision)"
+    e1 = assert_close(g_out, o_out, out_scales(o_out), A.OUT_NAMES, rtol, tag + " out")
+    e2 = assert_close(g_dbg, o_dbg, debug_scales(o_dbg), A.DEBUG_NAMES, rtol, tag + " dbg")
+    # zero / non-zero pattern of every pool is a clamp/branch outcome: exact
+    pools = slice(0, 13)
+    assert np.array_equal(g_dbg[:, pools] == 0, o_dbg[:, pools] == 0), f"{tag} pool clamp pattern differs"
+    if o_recs is not None:
+        g_recs = res["recs"][m]
+        assert [(r.step, r.type, r.variant, r.nval) for r in g_recs] == \
+               [(r.step, r.type, r.variant, r.nval) for r in o_recs], f"{tag} event rows differ"
+        for gr, orr in zip(g_recs, o_recs):
+            for k in range(orr.nval):
+                a, b = gr.val[k], orr.val[k]
+                assert abs(a - b) <= rtol * max(abs(a), abs(b), 1e-6), (tag, orr.type, k, a, b)
+    return max(e1, e2)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_cases(oracle, name):
+    """Reference fixtures (smoke cases + synthetic event cases) through the CUDA path."""
+    g = Golden(name)
+    P = np.repeat(g.params[:, None], 3, axis=1)
+    res = run_gpu([g.site], P, None, g.flags)
+    rc, done, o_out, o_dbg, o_recs = oracle.run(g.flags, g.params, g.site, max_event_records=4096)
+    assert rc == 0 and done == g.nsteps
+    worst = check_member(res, 0, o_out, o_dbg, o_recs, tag=name)
+    # the committed reference rows themselves
+    assert_close(res["out"][:, g.rows, 0].T, g.out32, out_scales(o_out), A.OUT_NAMES, RTOL, name + " golden out")
+    assert_close(res["dbg"][:, g.rows, 0].T, g.dbg, debug_scales(o_dbg), A.DEBUG_NAMES, RTOL, name + " golden dbg")
+    # identical members give identical results
+    assert np.array_equal(res["out"][:, :, 0], res["out"][:, :, 2], equal_nan=True)
+    assert (res["status"] & (A.ST_BAD_ALLOCATION | A.ST_RING_OVERFLOW | A.ST_NONFINITE)).max() == 0
+    print(f"{name}: worst relative error {worst:.3e}")
+
+
+@pytest.mark.parametrize("variant", ["half-daily", "unequal"])
+def test_wide_prior_ensemble_10yr(oracle, variant):
+    """C2-shaped: 1 site x 96 wide-prior members x 10 yr, every field of every step."""
+    site = synth.synth_site(0, 10, variant)
+    P = synth.synth_params(96)
+    res = run_gpu([site], P, None, synth.SYNTH_FLAGS)
+    worst = 0.0
+    for m in range(P.shape[1]):
+        rc, done, o_out, o_dbg, o_recs = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, max_event_records=4096)
+        assert rc == 0
+        worst = max(worst, check_member(res, m, o_out, o_dbg, o_recs, tag=f"{variant} m{m}"))
+    print(f"wide prior {variant}: worst relative error {worst:.3e}")
+
+
+def test_multi_site_events_c3_shape(oracle):
+    """C3-shaped: several sites x members with the agronomic schedule; ragged member counts."""
+    sites, P, ms, flags = synth.config_c3(nsites=5, members_per_site=7, nyears=4)
+    res = run_gpu(sites, P, ms, flags)
+    for m in range(P.shape[1]):
+        rc, done, o_out, o_dbg, o_recs = oracle.run(flags, P[:, m], sites[ms[m]], max_event_records=4096)
+        assert rc == 0
+        check_member(res, m, o_out, o_dbg, o_recs, tag=f"c3 m{m}")
+    assert (res["status"] & A.ST_DIED).any()
+
+
+@pytest.mark.parametrize("flags", [
+    dict(gdd=0, soilPhenol=1), dict(gdd=0), dict(flooding=1), dict(litterPool=1, carbonSaturation=1),
+    dict(litterPool=1, anaerobic=1), dict(events=0), dict(growthResp=1, leafWater=1),
+    dict(litterPool=1, anaerobic=1, nitrogenCycle=1, carbonSaturation=1, flooding=1, growthResp=1, leafWater=1),
+])
+def test_flag_matrix(oracle, flags):
+    full = dict(A.DEFAULT_FLAGS)
+    full.update(flags)
+    site = synth.synth_site(5, 2, "half-daily", with_events=True, gdd_flag=full["gdd"])
+    P = synth.synth_params(4, stream=5)
+    P[A.P["soilCSaturation"], :] = 2700.0
+    P[A.P["waterDrainFrac"], :] = 0.5
+    res = run_gpu([site], P, None, full)
+    for m in range(P.shape[1]):
+        rc, done, o_out, o_dbg, o_recs = oracle.run(full, P[:, m], site, max_event_records=4096)
+        check_member(res, m, o_out, o_dbg, o_recs, tag=f"{flags} m{m}")
+
+
+def test_specialised_kernels_equal_generic(oracle):
+    """The compile-time-flag kernels (no DEBUG) produce the same bits as the
+    runtime-flag DEBUG kernel on the outputState() columns."""
+    for flags in (dict(A.DEFAULT_FLAGS), dict(synth.SYNTH_FLAGS)):
+        site = synth.synth_site(7, 3, "half-daily", with_events=True)
+        P = synth.synth_params(40, stream=7)
+        a = run_gpu([site], P, None, flags, outputs=A.OUT_FULL)
+        b = run_gpu([site], P, None, flags, outputs=A.OUT_FULL | A.OUT_DEBUG)
+        assert np.array_equal(a["out"], b["out"], equal_nan=True)
+
+
+@pytest.mark.parametrize("block", [32, 64, 128])
+def test_block_size_invariance(block):
+    sites, P, ms, flags = synth.config_c3(nsites=3, members_per_site=45, nyears=2)
+    a = run_gpu(sites, P, ms, flags, outputs=A.OUT_FULL, block_threads=block)
+    b = run_gpu(sites, P, ms, flags, outputs=A.OUT_FULL, block_threads=32)
+    assert np.array_equal(a["out"], b["out"], equal_nan=True)
+
+
+def test_segmented_run_equals_continuous():
+    """Chunked sipnet_gpu_run == one run, bit for bit (reference: testRestartMVP.c:253-297)."""
+    site = synth.synth_site(9, 3, "unequal", with_events=True)
+    P = synth.synth_params(33, stream=9)
+    flags = synth.SYNTH_FLAGS
+    whole = run_gpu([site], P, None, flags, outputs=A.OUT_FULL | A.OUT_DEBUG)
+    ens = api.Ensemble([site], P, None, flags, outputs=A.OUT_FULL | A.OUT_DEBUG, out_steps_capacity=500)
+    T = site.nsteps
+    outs, dbgs = [], []
+    for t0 in range(0, T, 500):
+        ens.run(t0, min(T, t0 + 500))
+        outs.append(ens.output())
+        dbgs.append(ens.debug())
+    state = ens.state()
+    ens.close()
+    assert np.array_equal(np.concatenate(outs, axis=1), whole["out"], equal_nan=True)
+    assert np.array_equal(np.concatenate(dbgs, axis=1), whole["dbg"], equal_nan=True)
+    assert np.array_equal(state, whole["state"], equal_nan=True)
+
+
+def test_ragged_site_lengths(oracle):
+    s0 = synth.synth_site(20, 2, "half-daily")
+    s1 = synth.synth_site(21, 1, "half-daily")
+    P = synth.synth_params(10, stream=20)
+    ms = np.array([0] * 6 + [1] * 4, np.int32)
+    res = run_gpu([s0, s1], P, ms, synth.SYNTH_FLAGS, outputs=A.OUT_FULL)
+    for m in range(10):
+        site = (s0, s1)[ms[m]]
+        rc, done, o_out, _, _ = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, want_debug=False)
+        assert_close(res["out"][:, :site.nsteps, m].T, o_out, out_scales(o_out), A.OUT_NAMES, RTOL, f"ragged m{m}")
+        assert np.isnan(res["out"][:, site.nsteps:, m]).all()
+
+
+def test_init_error_codes_match_oracle(oracle):
+    p = synth.base_param_vector()[:, None]
+    fl = synth.SYNTH_FLAGS
+
+    def gpu_rc(site, params=p):
+        try:
+            api.Ensemble([site], params, None, fl).close()
+            return 0
+        except api.SipnetGpuError as e:
+            return e.code
+    s = synth.synth_site(2, 1, "half-daily"); s.events = [(2010, 5, A.EV_TILLAGE, 0, 0.1, 0, 0, 0)]
+    assert gpu_rc(s) == oracle.run(fl, p[:, 0], s)[0] == 5
+    s = synth.synth_site(2, 1, "half-daily"); s.events = [(2011, 50, A.EV_IRRIGATION, 2, 1.0, 0, 0, 0)]
+    assert gpu_rc(s) == oracle.run(fl, p[:, 0], s)[0] == 4
+    s = synth.synth_site(2, 1, "half-daily"); s.clim["length"] = s.clim["length"].copy(); s.clim["length"][10] = 0.0
+    assert gpu_rc(s) == oracle.run(fl, p[:, 0], s)[0] == 3
+    base = synth.synth_site(2, 1, "half-daily")
+    keep = base.day != 100
+    s2 = api.SiteData(base.year[keep], base.day[keep], {k: v[keep] for k, v in base.clim.items()},
+                      [(2011, 100, A.EV_TILLAGE, 0, 0.1, 0, 0, 0)])
+    assert gpu_rc(s2) == oracle.run(fl, p[:, 0], s2)[0] == 5
+    # bad allocation: per-member status bit instead of exit(3)
+    pb = np.repeat(p, 3, axis=1); pb[A.P["leafAllocation"], 1] = 0.7
+    ens = api.Ensemble([base], pb, None, fl)
+    ens.run()
+    st = ens.status()
+    ens.close()
+    assert st[1] & A.ST_BAD_ALLOCATION and not (st[0] & A.ST_BAD_ALLOCATION)
+    assert oracle.run(fl, pb[:, 1], base)[0] == 3
+
+
+@pytest.mark.parametrize("variant", ["half-daily", "unequal"])
+def test_fast_math_build_within_tolerance(oracle, variant):
+    """-fmad=true perf build, re-gated at 1e-10 against the oracle."""
+    site = synth.synth_site(0, 10, variant, with_events=True)
+    P = synth.synth_params(64)
+    res = run_gpu([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL, math=A.MATH_FAST)
+    worst = 0.0
+    for m in range(P.shape[1]):
+        rc, done, o_out, _, _ = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, want_debug=False)
+        worst = max(worst, assert_close(res["out"][:, :, m].T, o_out, out_scales(o_out), A.OUT_NAMES, RTOL,
+                                        f"fast {variant} m{m}"))
+    print(f"fast math {variant}: worst relative error {worst:.3e}")
