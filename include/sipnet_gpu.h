@@ -359,6 +359,11 @@ int sipnet_gpu_abi_version(void);
  * returns achieved TFLOP/s (the FP64 roofline denominator; SURVEY 7 hard part 7). */
 int sipnet_gpu_measure_fp64_peak(int device, double *tflops);
 
+/* Validation hook: evaluate the device exp (op 0: out = exp(x)) or pow (op 1: out = pow(x, y))
+ * on host arrays of n doubles, so the device libm can be compared bit for bit with the
+ * reference's host libm (glibc) -- see sipnet_b200/csrc/sip_libm.cuh. */
+int sipnet_gpu_eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

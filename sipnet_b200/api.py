@@ -79,6 +79,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_abi_version.argtypes = []
     lib.sipnet_gpu_measure_fp64_peak.restype = C.c_int
     lib.sipnet_gpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.sipnet_gpu_eval_libm.restype = C.c_int
+    lib.sipnet_gpu_eval_libm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     if path is None:
         _lib = lib
     return lib
@@ -153,6 +155,21 @@ def flags_array(flags: dict) -> np.ndarray:
     merged = dict(A.DEFAULT_FLAGS)
     merged.update(flags or {})
     return np.array([int(merged[n]) for n in A.FLAG_NAMES], dtype=np.int32)
+
+
+def device_libm(op: str, x: np.ndarray, y: Optional[np.ndarray] = None, device: int = 0) -> np.ndarray:
+    """Evaluate the DEVICE exp/pow (glibc-exact restatement) on arrays (validation hook)."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    yp = None
+    if op == "pow":
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        yp = y.ctypes.data
+    rc = lib.sipnet_gpu_eval_libm(device, 0 if op == "exp" else 1, x.ctypes.data, yp, out.ctypes.data, x.size)
+    if rc != 0:
+        raise SipnetGpuError(rc, (lib.sipnet_gpu_last_error() or b"").decode())
+    return out
 
 
 class Ensemble:

@@ -26,7 +26,7 @@
 namespace sip {
 namespace SIP_NS {
 
-constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 112 B = 3584 B
+constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 128 B = 4096 B
 
 // ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
         emit.tLocal = t - t0;
         emit.tSite = t;
         rec.step = (int32_t)t;
-        step<FL, DEBUG>(fl, prm, cbuf[i], site.events, mb, ext, rg, rec, emit);
+        step<FL, DEBUG>(fl, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, a.log2Hi, a.log2Lo);
       }
     }
     __syncthreads();  // everyone is done reading this buffer before it is refilled
@@ -299,6 +299,14 @@ __global__ void derive_params_kernel(double *params, int64_t ld, int64_t nmember
   }
   // member constant of potPsn(): pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
   P(kPsnTRangeSqSlot) = sip_pow((P(SIPNET_P_psnTMax) - P(SIPNET_P_psnTMin)) / 2.0, 2.0);
+  // log_inline() of the member-constant pow() bases
+  const int bases[4] = {SIPNET_P_vegRespQ10, SIPNET_P_coarseRootQ10, SIPNET_P_fineRootQ10, SIPNET_P_soilRespQ10};
+  const int slots[4] = {kLogVegQ10, kLogCoarseQ10, kLogFineQ10, kLogSoilQ10};
+  for (int i = 0; i < 4; ++i) {
+    const libm::LogHL l = libm::pow_log(P(bases[i]));
+    P(slots[i]) = l.hi;
+    P(slots[i] + 1) = l.lo;
+  }
   status[m] = st;
 }
 

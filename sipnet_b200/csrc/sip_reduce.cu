@@ -15,6 +15,7 @@
 
 #include <cstdint>
 
+#include "sip_libm.cuh"
 #include "sip_types.cuh"
 
 namespace sip {
@@ -232,6 +233,31 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
   cudaEventDestroy(e1);
   cudaFree(sink);
   *tflops = best;
+  return e;
+}
+
+// ---- validation hook: device exp / pow on arrays ------------------------------------------
+__global__ void eval_libm_kernel(int op, const double *x, const double *y, double *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = op == 0 ? libm::exp(x[i]) : libm::pow(x[i], y[i]);
+}
+
+cudaError_t eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return e;
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  const size_t bytes = (size_t)n * sizeof(double);
+  if ((e = cudaMalloc(&dx, bytes)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&dy, bytes)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&dout, bytes)) != cudaSuccess) return e;
+  cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice);
+  if (y != nullptr) cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice);
+  eval_libm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(op, dx, dy, dout, n);
+  e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dy);
+  cudaFree(dout);
   return e;
 }
 

@@ -248,7 +248,7 @@ __device__ __forceinline__ void limit_leaf_on(const FL &fl, const PT &prm, const
 template <class FL, bool DEBUG, class PT, class Emit>
 __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec &c, const EventDev *events,
                                      Member &mb, MemberExt &ext, const RingRef &rg, const RecSink &rec,
-                                     Emit &emit) {
+                                     Emit &emit, const double log2Hi, const double log2Lo) {
   const double len = c.length;
   const double oldSoilWater = mb.water;  // sipnet.c:1821
   Rates r = {};                          // resetFluxes, sipnet.c:1222
@@ -404,7 +404,7 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   // psnTRangeSq holds pow((psnTMax - psnTMin) / 2.0, 2) evaluated once per member by the setup kernel
   double dTemp = (SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)) / prm(kPsnTRangeSqSlot);
   dTemp = fmax(dTemp, 0.0);
-  double dVpd = 1.0 - SIP_P(dVpdSlope) * sip_pow(c.vpd, SIP_P(dVpdExp));
+  double dVpd = 1.0 - SIP_P(dVpdSlope) * sip_pow_cached(c.vpd, c.logVpdHi, c.logVpdLo, SIP_P(dVpdExp));
   dVpd = fmax(dVpd, 0.0);
   double dLight;
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
@@ -414,7 +414,7 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     for (int layer = 0; layer <= 6; ++layer) {
       const double cumLai = lai * ((double)layer / 6);
       const double inten = c.par * sip_exp(-1.0 * att * cumLai);
-      cur = (1 - sip_pow2(-1.0 * inten / hsp));
+      cur = (1 - sip_pow_cached(2.0, log2Hi, log2Lo, -1.0 * inten / hsp));
       const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
       cum += coeff * cur;
     }
@@ -520,9 +520,11 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
 
   // vegResp / vegResp2, :1051-1103
   {
-    double fol = baseFolResp * sip_pow(SIP_P(vegRespQ10), (c.tair - SIP_P(psnTOpt)) / 10.0);
+    double fol = baseFolResp * sip_pow_cached(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
+                                              (c.tair - SIP_P(psnTOpt)) / 10.0);
     if (c.tsoil < SIP_P(frozenSoilThreshold)) fol *= SIP_P(frozenSoilFolREff);
-    const double woodR = SIP_P(baseVegResp) * woodTot * sip_pow(SIP_P(vegRespQ10), c.tair / 10.0);
+    const double woodR = SIP_P(baseVegResp) * woodTot *
+                         sip_pow_cached(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1), c.tair / 10.0);
     if (fl.on(F_GROWTH_RESP)) {
       double growth = SIP_P(growthRespFrac) * meanNpp;
       if (growth < 0) growth = 0;
@@ -584,7 +586,8 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   }
 
   // shared dependency terms (depeffects.c); each is a pure function of (tsoil, soilWater, params)
-  const double tempEffect = sip_pow(SIP_P(soilRespQ10), c.tsoil / 10);  // calcTempEffect :72-75
+  const double tempEffect =
+      sip_pow_cached(SIP_P(soilRespQ10), prm(kLogSoilQ10), prm(kLogSoilQ10 + 1), c.tsoil / 10);  // calcTempEffect :72-75
   double anaerobicIdx = 0.0;                                              // calcAnaerobicIndex :15-22
   if (fl.on(F_ANAEROBIC) || fl.on(F_NITROGEN)) {
     const double fa = SIP_P(fAnoxia);
@@ -615,8 +618,10 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   r.fineRootLoss += SIP_P(fineRootTurnoverRate) * mb.fine;
   r.coarseRootCreation += SIP_P(coarseRootAllocation) * meanNpp;
   r.fineRootCreation += SIP_P(fineRootAllocation) * meanNpp;
-  r.rCoarseRoot = SIP_P(baseCoarseRootResp) * mb.coarse * sip_pow(SIP_P(coarseRootQ10), c.tsoil / 10.0);
-  r.rFineRoot = SIP_P(baseFineRootResp) * mb.fine * sip_pow(SIP_P(fineRootQ10), c.tsoil / 10.0);
+  r.rCoarseRoot = SIP_P(baseCoarseRootResp) * mb.coarse *
+                  sip_pow_cached(SIP_P(coarseRootQ10), prm(kLogCoarseQ10), prm(kLogCoarseQ10 + 1), c.tsoil / 10.0);
+  r.rFineRoot = SIP_P(baseFineRootResp) * mb.fine *
+                sip_pow_cached(SIP_P(fineRootQ10), prm(kLogFineQ10), prm(kLogFineQ10 + 1), c.tsoil / 10.0);
 
   // calcSoilRespiration, :1132-1148
   {

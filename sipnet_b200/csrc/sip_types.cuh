@@ -24,7 +24,13 @@ constexpr int kRingMax = 250;         // MEAN_NPP_MAX_ENTRIES, sipnet.c:40
 
 // Device parameter rows: the 80 of struct Parameters plus derived per-member constants.
 constexpr int kPsnTRangeSqSlot = SIPNET_GPU_NPARAMS;  // pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
-constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 1;
+// log_inline() of the member-constant pow() bases, as hi + lo (sip_libm.cuh pow_log); NaN = base is not
+// "regular" and the full pow() runs instead.  Reusing them is bit-identical to calling pow(base, y).
+constexpr int kLogVegQ10 = SIPNET_GPU_NPARAMS + 1;     // vegRespQ10, sipnet.c:1056,1067
+constexpr int kLogCoarseQ10 = SIPNET_GPU_NPARAMS + 3;  // coarseRootQ10, sipnet.c:1076
+constexpr int kLogFineQ10 = SIPNET_GPU_NPARAMS + 5;    // fineRootQ10, sipnet.c:1076
+constexpr int kLogSoilQ10 = SIPNET_GPU_NPARAMS + 7;    // soilRespQ10, depeffects.c:74
+constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 9;
 
 // flag bits (runtime mask / compile-time specialisation)
 enum : uint32_t {
@@ -42,7 +48,7 @@ enum : uint32_t {
   F_CSAT = 1u << 11,
 };
 
-// One climate step as staged to shared memory: 14 x 8 bytes = 112 bytes
+// One climate step as staged to shared memory: 16 x 8 bytes = 128 bytes
 // (multiple of 16 so a chunk is a legal cp.async.bulk size).
 struct alignas(16) ClimRec {
   double time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
@@ -50,10 +56,12 @@ struct alignas(16) ClimRec {
   // tillage decay factor of updateEventTrackers() (events.c:816) depends on the
   // step length only, so it is hoisted out of the member loop.
   double tillDecay;
+  // log_inline(vpd) as hi + lo (sip_libm.cuh pow_log) for pow(vpd, dVpdExp), sipnet.c:626; NaN = not regular
+  double logVpdHi, logVpdLo;
   int32_t year, day;
   int32_t evBegin, evEnd;  // events of this step: [evBegin, evEnd) in the site's EventDev array
 };
-static_assert(sizeof(ClimRec) == 112, "ClimRec must be 112 bytes");
+static_assert(sizeof(ClimRec) == 128, "ClimRec must be 128 bytes");
 
 struct alignas(16) EventDev {
   double p[4];
@@ -95,6 +103,7 @@ struct RunArgs {
   int32_t maxRecs;
   int32_t ringCap;
   uint32_t flags;          // runtime flag mask (generic kernel)
+  double log2Hi, log2Lo;   // log_inline(2.0) for pow(2, y), sipnet.c:551
   double invSigma;         // 1 / nee_sigma
   double logNorm;          // -log(sigma) - 0.5*log(2*pi)
   int8_t colSlot[SIPNET_GPU_NOUT];  // output column -> slot in `out`, or -1

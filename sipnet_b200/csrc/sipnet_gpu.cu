@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "sip_libm.cuh"
 #include "sip_types.cuh"
 
 namespace sip {
@@ -42,6 +43,7 @@ cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int
                              int64_t nsites, const double *probs, int nq, double *scratch, double *out,
                              cudaStream_t stream);
 cudaError_t measure_fp64_peak(int device, double *tflops);
+cudaError_t eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n);
 }  // namespace sip
 
 using namespace sip;
@@ -159,6 +161,11 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimR
                   (long long)siteIndex, c.length, c.year, c.day);
     minLen = std::min(minLen, c.length);
     c.tillDecay = std::exp(-c.length * (1 / 30.0));  // events.c:816, events.h:58
+    {
+      const libm::LogHL l = libm::pow_log(c.vpd);  // host evaluation of the same operations
+      c.logVpdHi = l.hi;
+      c.logVpdLo = l.lo;
+    }
     c.evBegin = (int32_t)e;
     while (e < nev && s.events[e].year <= c.year && s.events[e].day <= c.day) {  // events.c:471
       const sipnet_gpu_event &ev = s.events[e];
@@ -546,6 +553,11 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
   a.maxRecs = h->maxRecs;
   a.ringCap = h->ringCap;
   a.flags = h->flags;
+  {
+    const libm::LogHL l2 = libm::pow_log(2.0);
+    a.log2Hi = l2.hi;
+    a.log2Lo = l2.lo;
+  }
   a.invSigma = 1.0 / h->sigma;
   a.logNorm = -std::log(h->sigma) - 0.5 * std::log(2.0 * M_PI);
   memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);
@@ -714,5 +726,15 @@ extern "C" int sipnet_gpu_measure_fp64_peak(int device, double *tflops) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
     return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", device);
   CUDA_OK(measure_fp64_peak(device, tflops));
+  return 0;
+}
+
+extern "C" int sipnet_gpu_eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n) {
+  if (!x || !out || n <= 0 || (op != 0 && op != 1) || (op == 1 && !y))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "bad eval_libm arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", device);
+  CUDA_OK(eval_libm(device, op, x, y, out, n));
   return 0;
 }

@@ -15,24 +15,32 @@ def column_scales(ref: np.ndarray) -> np.ndarray:
     return np.where(s > 0, s, 1.0)
 
 
+# Error metric (SURVEY 7 hard part 2): |a-b| <= rtol * max(|a|, |b|, floor), floor per column.
+#  * default floor = 1e-6 x the column's own magnitude over the run, i.e. strict
+#    relative error except for values six orders below the column's scale;
+#  * plantCAccountingDelta (printed as nppStorage) is a CANCELLATION ACCUMULATOR:
+#    |value| ~ 1e-2 while the terms it sums are ~ plantWoodC ~ 1e3, so 1-ulp
+#    differences of pow/exp between CUDA's libm and glibc show up as ~1e-9 of its
+#    own value although they are ~1e-15 of the quantities involved.  The survey
+#    measured the same amplification inside the reference itself (+-1 ulp libm
+#    perturbation => 1.3e-8 relative on this field only, no branch flips) and
+#    prescribes plantWoodC as its floor; the printed column plantWoodC =
+#    plantWoodC + delta (sipnet.c:455-456) is held to the strict default.
 def debug_scales(ref_dbg: np.ndarray) -> np.ndarray:
-    s = column_scales(ref_dbg)
-    # plantCAccountingDelta is a cancellation accumulator whose terms are ~plantWoodC
-    # (SURVEY 7 hard part 2): scale it by plantWoodC.
-    s[A.D["envi.plantCAccountingDelta"]] = max(s[A.D["envi.plantCAccountingDelta"]], s[A.D["envi.plantWoodC"]])
+    s = 1e-6 * column_scales(ref_dbg)
+    s[A.D["envi.plantCAccountingDelta"]] = column_scales(ref_dbg)[A.D["envi.plantWoodC"]]
     return s
 
 
 def out_scales(ref_out: np.ndarray) -> np.ndarray:
-    s = column_scales(ref_out)
-    s[A.O["nppStorage"]] = max(s[A.O["nppStorage"]], s[A.O["plantWoodC"]])
+    s = 1e-6 * column_scales(ref_out)
+    s[A.O["nppStorage"]] = column_scales(ref_out)[A.O["plantWoodC"]]
     return s
 
 
 def max_rel(a: np.ndarray, b: np.ndarray, scale: np.ndarray) -> np.ndarray:
-    """max over time of |a-b| / max(|a|,|b|,floor) per column, floor = 1e-6 * column magnitude:
-    strict relative error except for values six orders below the column's own scale."""
-    den = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-6 * scale[None, :])
+    """max over time of |a-b| / max(|a|,|b|,floor) per column (floor: see above)."""
+    den = np.maximum(np.maximum(np.abs(a), np.abs(b)), scale[None, :])
     err = np.abs(a - b) / den
     err = np.where(np.isnan(a) & np.isnan(b), 0.0, err)
     return np.nanmax(err, axis=0)

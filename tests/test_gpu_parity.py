@@ -27,10 +27,15 @@ def run_gpu(sites, params, member_site, flags, outputs=ALL, math=A.MATH_VALIDATI
     return res
 
 
+BITEXACT = {"checked": 0, "exact": 0}
+
+
 def check_member(res, m, o_out, o_dbg, o_recs, rtol=RTOL, tag=""):
     T = o_out.shape[0]
     g_out = res["out"][:, :T, m].T
     g_dbg = res["dbg"][:, :T, m].T
+    BITEXACT["checked"] += 1
+    BITEXACT["exact"] += int(np.array_equal(g_out, o_out, equal_nan=True) and np.array_equal(g_dbg, o_dbg, equal_nan=True))
     for name in EXACT_DEBUG:
         k = A.D[name]
         assert np.array_equal(g_dbg[:, k], o_dbg[:, k]), f"{tag} {name} differs (branch decision)"
@@ -206,3 +211,12 @@ def test_fast_math_build_within_tolerance(oracle, variant):
         worst = max(worst, assert_close(res["out"][:, :, m].T, o_out, out_scales(o_out), A.OUT_NAMES, RTOL,
                                         f"fast {variant} m{m}"))
     print(f"fast math {variant}: worst relative error {worst:.3e}")
+
+
+def test_zz_validation_build_is_bit_identical():
+    """With the glibc-exact exp/pow (sip_libm.cuh) and -fmad=false the validation build performs the
+    reference's IEEE operations one for one: every member checked above must have matched the oracle
+    (itself bit-identical to the unmodified reference) in EVERY bit of every field of every step."""
+    assert BITEXACT["checked"] > 0
+    print(f"bit-identical members: {BITEXACT['exact']} of {BITEXACT['checked']}")
+    assert BITEXACT["exact"] == BITEXACT["checked"]
