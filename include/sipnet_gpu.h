@@ -272,6 +272,8 @@ enum sipnet_gpu_gather_what {
 #define SIPNET_GPU_ST_DIED 0x8u           /* plant mortality happened at least once (sipnet.c:1702) */
 #define SIPNET_GPU_ST_EVREC_OVERFLOW 0x10u /* more event records than max_event_records */
 #define SIPNET_GPU_ST_NONFINITE 0x20u     /* a pool became NaN/Inf */
+#define SIPNET_GPU_ST_REPLAY 0x40u        /* the optimistic kernel met an input outside its guards and the member
+                                             was re-run by the general kernel (informational; results are exact) */
 
 /* carried state rows for SIPNET_GPU_GATHER_STATE (restart.c:148-308 field list) */
 enum sipnet_gpu_state_row {

@@ -132,7 +132,7 @@ MATH_VALIDATION, MATH_FAST = 0, 1
  GATHER_EVENT_RECORDS, GATHER_LOGLIK_N) = range(1, 12)
 
 ST_BAD_ALLOCATION, ST_RING_OVERFLOW, ST_CLAMPED, ST_DIED, ST_EVREC_OVERFLOW, \
-    ST_NONFINITE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+    ST_NONFINITE, ST_REPLAY = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 
 ERR_NO_DEVICE, ERR_BAD_ARGUMENT = 100, 101
 EVREC_NVAL = 10

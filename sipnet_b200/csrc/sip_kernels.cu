@@ -1,8 +1,11 @@
-// sip_kernels.cu -- the fused step kernel (K1) and the setup kernel.
+// sip_kernels.cu -- the fused step kernel (K1) and the setup kernels.
 //
-// Compiled twice by the Makefile into two namespaces of the same library:
-//   -DSIP_NS=val  -fmad=false            (validation arithmetic)
-//   -DSIP_NS=fast -fmad=true -DSIP_FAST_MATH
+// Compiled with -fmad=false: the model arithmetic keeps the reference's operation
+// order, and exp/pow/division are explicit operation sequences (sip_libm.cuh,
+// sip_num.cuh), so every kernel here is bit-identical to the reference binary.
+// Two numerics policies of the SAME arithmetic:
+//   FastNum  (production)  branch-free main paths + guard flag, ~2.3x fewer instructions
+//   ExactNum (validation / debug dump / replay of members the fast kernel flagged)
 //
 // K1 layout: one thread = one ensemble member; a block holds members of ONE
 // site, so forcing and the event schedule are block-uniform.  Per block:
@@ -19,12 +22,8 @@
 
 #include "sip_step.cuh"
 
-#ifndef SIP_NS
-#define SIP_NS val
-#endif
-
 namespace sip {
-namespace SIP_NS {
+namespace k1 {
 
 constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 128 B = 4096 B
 
@@ -87,8 +86,9 @@ struct Emitter {
   }
 };
 
-__device__ __forceinline__ void load_member(const RunArgs &a, int64_t m, Member &mb, MemberExt &ext, bool debug) {
-  const double *s = a.state + m;
+__device__ __forceinline__ void load_member(const RunArgs &a, const double *state, const uint32_t *status, int64_t m,
+                                            Member &mb, MemberExt &ext, bool debug) {
+  const double *s = state + m;
   const int64_t ld = a.ld;
   mb.wood = s[SIPNET_S_plantWoodC * ld];
   mb.leaf = s[SIPNET_S_plantLeafC * ld];
@@ -114,7 +114,7 @@ __device__ __forceinline__ void load_member(const RunArgs &a, int64_t m, Member 
   mb.phenLastYear = (int)s[SIPNET_S_phenLastYear * ld];
   mb.didGrowth = (int)s[SIPNET_S_didLeafGrowth * ld];
   mb.didFall = (int)s[SIPNET_S_didLeafFall * ld];
-  mb.status = a.status[m];
+  mb.status = status[m];
   if (debug) {
     ext.yGpp = s[SIPNET_S_yearlyGpp * ld];
     ext.yRtot = s[SIPNET_S_yearlyRtot * ld];
@@ -183,7 +183,9 @@ __device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const 
 }
 
 // ---- K1: fused [events -> fluxes -> pools -> trackers -> mean tracker] over a step range ----
-template <class FL, bool DEBUG, int BLOCK>
+// REPLAY = true: only members the optimistic kernel flagged (SIPNET_GPU_ST_REPLAY set during this
+// segment) are integrated, starting again from the segment's start state (RunArgs::*Backup).
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY>
 __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNParamDev][BLOCK]
@@ -196,6 +198,10 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
   const int64_t m = (int64_t)bd.member0 + tid;
   bool active = tid < bd.count;
   const FL fl(a.flags);
+  if (REPLAY) {
+    active = active && ((a.status[m] & SIPNET_GPU_ST_REPLAY) != 0) && ((a.statusBackup[m] & SIPNET_GPU_ST_REPLAY) == 0);
+    if (!__syncthreads_or(active ? 1 : 0)) return;  // nothing to replay in this block (the normal case)
+  }
 
   const int64_t t0 = a.stepBegin;
   const int64_t t1 = a.stepEnd < site.nsteps ? a.stepEnd : site.nsteps;
@@ -223,9 +229,23 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
   Member mb;
   MemberExt ext = {};
   if (active) {
-    load_member(a, m, mb, ext, DEBUG);
+    if (REPLAY) {  // restore the member's segment-start state: ring columns, accumulators, status
+      for (int sl = 0; sl < a.ringCap; ++sl) {
+        a.ringV[(int64_t)sl * a.ld + m] = a.ringVBackup[(int64_t)sl * a.ld + m];
+        a.ringW[(int64_t)sl * a.ld + m] = a.ringWBackup[(int64_t)sl * a.ld + m];
+      }
+      if (a.loglik != nullptr) {
+        a.loglik[m] = a.loglikBackup[m];
+        a.loglikN[m] = a.loglikNBackup[m];
+      }
+      if (a.recCount != nullptr) a.recCount[m] = a.recCountBackup[m];
+    }
+    load_member(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
+    if (REPLAY) mb.status |= SIPNET_GPU_ST_REPLAY;
     if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) active = false;  // reference would have exited (sipnet.c:1117-1122)
   }
+  NM nm;
+  const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
   const ParamTile prm{tile + tid, BLOCK};
   const RingRef rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
   RecSink rec{nullptr, nullptr, a.maxRecs, 0};
@@ -248,13 +268,14 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
         emit.tLocal = t - t0;
         emit.tSite = t;
         rec.step = (int32_t)t;
-        step<FL, DEBUG>(fl, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, a.log2Hi, a.log2Lo);
+        step<FL, DEBUG>(fl, nm, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, kc);
       }
     }
     __syncthreads();  // everyone is done reading this buffer before it is refilled
   }
 
   if (active) {
+    if (NM::kFast && nm.bad) mb.status |= SIPNET_GPU_ST_REPLAY;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
     if (a.loglik != nullptr && site.neeObs != nullptr) {
       a.loglik[m] += emit.ll;
@@ -299,6 +320,27 @@ __global__ void derive_params_kernel(double *params, int64_t ld, int64_t nmember
   }
   // member constant of potPsn(): pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
   P(kPsnTRangeSqSlot) = sip_pow((P(SIPNET_P_psnTMax) - P(SIPNET_P_psnTMin)) / 2.0, 2.0);
+  // division seeds of the member-constant divisors and member-constant sub-expressions (sip_num.cuh)
+  {
+    const FastNum fn;
+    P(kOneMinusFa) = 1 - P(SIPNET_P_fAnoxia);
+    P(kTwoWhc) = 2.0 * P(SIPNET_P_soilWHC);
+    P(kOneMinusFracLitResp) = 1.0 - P(SIPNET_P_fracLitterRespired);
+    P(kRespPerGram) = P(SIPNET_P_baseFolRespFrac) * P(SIPNET_P_aMax);
+    P(kGrossAMax) = P(SIPNET_P_aMax) * P(SIPNET_P_aMaxFrac) + P(kRespPerGram);
+    P(kConvBase) = 12.0 * (1.0 / 1000000000.0) * (P(SIPNET_P_leafCSpWt) / P(SIPNET_P_cFracLeaf));
+    P(kSeedLeafCSpWt) = fn.seed(P(SIPNET_P_leafCSpWt));
+    P(kSeedPsnTRangeSq) = fn.seed(P(kPsnTRangeSqSlot));
+    P(kSeedHalfSatPar) = fn.seed(P(SIPNET_P_halfSatPar));
+    P(kSeedWhc) = fn.seed(P(SIPNET_P_soilWHC));
+    P(kSeedTwoWhc) = fn.seed(P(kTwoWhc));
+    P(kSeedLeafCN) = fn.seed(P(SIPNET_P_leafCN));
+    P(kSeedWoodCN) = fn.seed(P(SIPNET_P_woodCN));
+    P(kSeedFineRootCN) = fn.seed(P(SIPNET_P_fineRootCN));
+    P(kSeedFAnoxia) = fn.seed(P(SIPNET_P_fAnoxia));
+    P(kSeedOneMinusFa) = fn.seed(P(kOneMinusFa));
+    P(kSeedCSat) = fn.seed(P(SIPNET_P_soilCSaturation));
+  }
   // log_inline() of the member-constant pow() bases
   const int bases[4] = {SIPNET_P_vegRespQ10, SIPNET_P_coarseRootQ10, SIPNET_P_fineRootQ10, SIPNET_P_soilRespQ10};
   const int slots[4] = {kLogVegQ10, kLogCoarseQ10, kLogFineQ10, kLogSoilQ10};
@@ -373,30 +415,35 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
 
-template <class FL, bool DEBUG, int BLOCK>
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
   const size_t smem = sizeof(double) * kNParamDev * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) + 2 * sizeof(uint64_t);
-  auto kern = run_kernel<FL, DEBUG, BLOCK>;
+  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<nblocks, BLOCK, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
+// mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members (exact)
 template <int BLOCK>
-static cudaError_t launch_block(const RunArgs &a, int nblocks, bool debug, cudaStream_t stream) {
+static cudaError_t launch_block(const RunArgs &a, int nblocks, bool debug, int mode, cudaStream_t stream) {
   const uint32_t arith = a.flags & ~(uint32_t)F_SNOW;  // ctx.snow has no arithmetic effect (SURVEY 8a trap 6)
-  if (debug) return launch_one<RuntimeFlags, true, BLOCK>(a, nblocks, stream);
-  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW)) return launch_one<StaticFlags<kMaskDefault>, false, BLOCK>(a, nblocks, stream);
-  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW)) return launch_one<StaticFlags<kMaskCropN>, false, BLOCK>(a, nblocks, stream);
-  return launch_one<RuntimeFlags, false, BLOCK>(a, nblocks, stream);
+  if (mode == 2) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, true>(a, nblocks, stream);
+  if (debug) return launch_one<RuntimeFlags, true, ExactNum, BLOCK, false>(a, nblocks, stream);
+  if (mode == 0) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, false>(a, nblocks, stream);
+  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW))
+    return launch_one<StaticFlags<kMaskDefault>, false, FastNum, BLOCK, false>(a, nblocks, stream);
+  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW))
+    return launch_one<StaticFlags<kMaskCropN>, false, FastNum, BLOCK, false>(a, nblocks, stream);
+  return launch_one<RuntimeFlags, false, FastNum, BLOCK, false>(a, nblocks, stream);
 }
 
-cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, cudaStream_t stream) {
+cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream) {
   switch (blockThreads) {
-    case 32: return launch_block<32>(a, nblocks, debug, stream);
-    case 64: return launch_block<64>(a, nblocks, debug, stream);
-    case 128: return launch_block<128>(a, nblocks, debug, stream);
+    case 32: return launch_block<32>(a, nblocks, debug, mode, stream);
+    case 64: return launch_block<64>(a, nblocks, debug, mode, stream);
+    case 128: return launch_block<128>(a, nblocks, debug, mode, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -419,5 +466,5 @@ cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers
   return cudaGetLastError();
 }
 
-}  // namespace SIP_NS
+}  // namespace k1
 }  // namespace sip

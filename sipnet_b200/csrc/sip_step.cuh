@@ -25,6 +25,7 @@
 // reference's gcc -O0 binary.
 #pragma once
 #include "sip_math.cuh"
+#include "sip_num.cuh"
 #include "sip_types.cuh"
 
 namespace sip {
@@ -181,75 +182,122 @@ struct StepTrack {
       nLeaching, nFixation, nUptake, meanNPP;
 };
 
-// ---- nitrogen helpers, nitrogen.c ----------------------------------------------------
-template <class PT>
-__device__ __forceinline__ double n_leafon_from_c(const PT &prm, double c) {  // nitrogen.c:86-88
-  return fmax(0.0, c / SIP_P(leafCN) - c / SIP_P(woodCN));
+// kernel-lifetime constants: log_inline(2.0) and the division seeds of the literal divisors
+struct StepConsts {
+  double log2Hi, log2Lo;
+  double seed10, seed5, seed18, seed24;  // 10.0 (Q10 exponents), MEAN_NPP_DAYS, 3.0 * NUM_LAYERS, 24.0 (hours)
+};
+template <class NM>
+__device__ __forceinline__ StepConsts make_consts(const NM &nm, double log2Hi, double log2Lo) {
+  StepConsts k;
+  k.log2Hi = log2Hi;
+  k.log2Lo = log2Lo;
+  k.seed10 = nm.seed(10.0);
+  k.seed5 = nm.seed(kMeanNppDays);
+  k.seed18 = nm.seed(3.0 * 6);
+  k.seed24 = nm.seed(24.0);
+  return k;
 }
-template <class FL, class PT>
-__device__ __forceinline__ double n_demand(const FL &fl, const PT &prm, const Rates &r) {  // nitrogen.c:91-106
+
+// per-step divisor context: x / length and the member-constant C:N divisors
+template <class NM, class PT>
+struct Div {
+  NM &nm;
+  const PT &prm;
+  double len, seedLen, invLenPow2;
+  // x / climate->length
+  __device__ __forceinline__ double byLen(double a) const {
+    if (NM::kFast && invLenPow2 != 0.0) return a * invLenPow2;  // exact: length is a power of two
+    return nm.divs(a, len, seedLen);
+  }
+  __device__ __forceinline__ double byLeafCN(double a) const { return nm.divs(a, SIP_P(leafCN), prm(kSeedLeafCN)); }
+  __device__ __forceinline__ double byWoodCN(double a) const { return nm.divs(a, SIP_P(woodCN), prm(kSeedWoodCN)); }
+  __device__ __forceinline__ double byFineCN(double a) const {
+    return nm.divs(a, SIP_P(fineRootCN), prm(kSeedFineRootCN));
+  }
+  __device__ __forceinline__ double byWhc(double a) const { return nm.divs(a, SIP_P(soilWHC), prm(kSeedWhc)); }
+};
+
+// ---- nitrogen helpers, nitrogen.c ----------------------------------------------------
+template <class DV>
+__device__ __forceinline__ double n_leafon_from_c(const DV &dv, double c) {  // nitrogen.c:86-88
+  return fmax(0.0, dv.byLeafCN(c) - dv.byWoodCN(c));
+}
+template <class FL, class DV>
+__device__ __forceinline__ double n_demand(const FL &fl, const DV &dv, const Rates &r) {  // nitrogen.c:91-106
   if (!fl.on(F_NITROGEN)) return 0.0;
-  const double d = r.woodCreation / SIP_P(woodCN) + r.leafCreation / SIP_P(leafCN) +
-                   r.fineRootCreation / SIP_P(fineRootCN) + r.coarseRootCreation / SIP_P(woodCN);
+  const double d = dv.byWoodCN(r.woodCreation) + dv.byLeafCN(r.leafCreation) + dv.byFineCN(r.fineRootCreation) +
+                   dv.byWoodCN(r.coarseRootCreation);
   return fmax(0.0, d);
 }
 __device__ __forceinline__ double n_non_uptake(const Rates &r) {  // nitrogen.c:124-126
   return r.nMin - r.nVolatilization - r.nLeaching;
 }
-template <class PT>
-__device__ __forceinline__ double n_unclaimed_storage(const PT &prm, const Member &mb, const Rates &r,
+template <class DV>
+__device__ __forceinline__ double n_unclaimed_storage(const DV &dv, const Member &mb, const Rates &r,
                                                       double len) {  // nitrogen.c:129-136
   const double cflux = r.leafOnCreation + r.eventLeafOnCreation;
-  const double nflux = n_leafon_from_c(prm, cflux);
+  const double nflux = n_leafon_from_c(dv, cflux);
   return fmax(0.0, mb.storN - nflux * len);
 }
-template <class PT>
-__device__ __forceinline__ double n_fix_frac(const PT &prm, const Member &mb) {  // nitrogen.c:139-153
+template <class DV>
+__device__ __forceinline__ double n_fix_frac(const DV &dv, const Member &mb) {  // nitrogen.c:139-153
+  const auto &prm = dv.prm;
   double inhib;
   const double denom = SIP_P(halfNFixationMax) + mb.minN;
   if (denom < kTiny) {
     inhib = 1;
   } else {
-    inhib = SIP_P(halfNFixationMax) / denom;
+    inhib = dv.nm.div(SIP_P(halfNFixationMax), denom);
   }
   return SIP_P(nFixationFracMax) * inhib;
 }
-template <class FL, class PT>
-__device__ __forceinline__ void n_fix_and_uptake(const FL &fl, const PT &prm, const Member &mb, Rates &r,
+template <class FL, class DV>
+__device__ __forceinline__ void n_fix_and_uptake(const FL &fl, const DV &dv, const Member &mb, Rates &r,
                                                  double len) {  // nitrogen.c:156-168
-  const double demand = n_demand(fl, prm, r);
-  const double storage = n_unclaimed_storage(prm, mb, r, len) / len;
+  const double demand = n_demand(fl, dv, r);
+  const double storage = dv.byLen(n_unclaimed_storage(dv, mb, r, len));
   const double rem = fmax(0.0, demand - storage);
-  const double ff = n_fix_frac(prm, mb);
+  const double ff = n_fix_frac(dv, mb);
   r.nFixation = ff * rem;
   r.nUptake = (1 - ff) * rem;
 }
 
 // checkLeafOnLimitation, limitations.c:13-64
-template <class FL, class PT>
-__device__ __forceinline__ void limit_leaf_on(const FL &fl, const PT &prm, const Member &mb, double len,
+template <class FL, class DV>
+__device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, const Member &mb, double len,
                                               double &flux) {
+  const auto &prm = dv.prm;
   const double demandC = flux * len;
   if (demandC < kTiny) return;
   const double availC = (mb.wood + mb.coarse) * SIP_P(leafOnReallocFrac);
-  const double cLim = availC / demandC;
+  const double cLim = dv.nm.div(availC, demandC);
   double nLim = 1.0;
   if (fl.on(F_NITROGEN)) {
-    const double demandN = n_leafon_from_c(prm, demandC);
-    if (demandN > kTiny) nLim = mb.storN / demandN;
+    const double demandN = n_leafon_from_c(dv, demandC);
+    if (demandN > kTiny) nLim = dv.nm.div(mb.storN, demandN);
   }
   const double lim = clip01(fmin(cLim, nLim));
   if (lim < 1) flux *= lim;
 }
 
+// calcRatio, common/util.c:72-75
+template <class NM>
+__device__ __forceinline__ double ratio(NM &nm, double num, double den) {
+  const double d = den < kTiny ? kTiny : den;
+  return nm.div(num, d);
+}
+
 // ---- the step ----------------------------------------------------------------------
 // Emit is a functor: emit.out(col, value) for outputState() columns and, in the
 // DEBUG instantiation, emit.dbg(index, value) for the debug-log fields.
-template <class FL, bool DEBUG, class PT, class Emit>
-__device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec &c, const EventDev *events,
+// NM is the numerics policy (sip_num.cuh): ExactNum or FastNum -- same bits.
+template <class FL, bool DEBUG, class NM, class PT, class Emit>
+__device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const ClimRec &c, const EventDev *events,
                                      Member &mb, MemberExt &ext, const RingRef &rg, const RecSink &rec,
-                                     Emit &emit, const double log2Hi, const double log2Lo) {
+                                     Emit &emit, const StepConsts &kc) {
   const double len = c.length;
+  const Div<NM, PT> dv{nm, prm, len, (NM::kFast && c.invLenPow2 == 0.0) ? nm.seed(len) : 0.0, c.invLenPow2};
   const double oldSoilWater = mb.water;  // sipnet.c:1821
   Rates r = {};                          // resetFluxes, sipnet.c:1222
   bool alive = has_biomass(mb);          // initPlantSurvivalTracker, sipnet.c:1538
@@ -269,24 +317,23 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
           evapAmt = 0.0;
           soilAmt = amount;
         }
-        r.eventEvap += evapAmt / len;
-        r.eventSoilWater += soilAmt / len;
+        r.eventEvap += dv.byLen(evapAmt);
+        r.eventSoilWater += dv.byLen(soilAmt);
         const double v[2] = {soilAmt, evapAmt};
         rec.add(mb, ev.type, 0, 2, v);
       } break;
       case SIPNET_EV_PLANTING: {  // :507-542
         const double leafC = ev.p[0], woodC = ev.p[1], fineC = ev.p[2], coarseC = ev.p[3];
-        r.eventLeafC += leafC / len;
-        r.eventWoodC += woodC / len;
-        r.eventFineRootC += fineC / len;
-        r.eventCoarseRootC += coarseC / len;
+        r.eventLeafC += dv.byLen(leafC);
+        r.eventWoodC += dv.byLen(woodC);
+        r.eventFineRootC += dv.byLen(fineC);
+        r.eventCoarseRootC += dv.byLen(coarseC);
         const double inC = leafC + woodC + fineC + coarseC;
         double inN = 0.0;
-        r.eventInputC += inC / len;
+        r.eventInputC += dv.byLen(inC);
         if (fl.on(F_NITROGEN)) {
-          inN = leafC / SIP_P(leafCN) + woodC / SIP_P(woodCN) + fineC / SIP_P(fineRootCN) +
-                coarseC / SIP_P(woodCN);
-          r.eventInputN += inN / len;
+          inN = dv.byLeafCN(leafC) + dv.byWoodCN(woodC) + dv.byFineCN(fineC) + dv.byWoodCN(coarseC);
+          r.eventInputN += dv.byLen(inN);
         }
         const double v[6] = {leafC, woodC, fineC, coarseC, inC, inN};
         rec.add(mb, ev.type, 0, 6, v);
@@ -300,8 +347,8 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
         if (total > kTiny) {
           const double removed = fRA * above + fRB * below;
           const double moved = fTA * above + fTB * below;
-          harvRemoved += removed / total;
-          harvTransferred += moved / total;
+          harvRemoved += nm.div(removed, total);
+          harvTransferred += nm.div(moved, total);
         }
         double litterAdd = fTA * (mb.leaf + woodC);
         double soilAdd = fTB * (mb.fine + mb.coarse);
@@ -313,28 +360,28 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
           soilAdd += litterAdd;
           litterAdd = 0.0;
         }
-        r.eventLitterC += litterAdd / len;
-        r.eventSoilC += soilAdd / len;
-        r.eventLeafC += dLeaf / len;
-        r.eventWoodC += dWood / len;
-        r.eventFineRootC += dFine / len;
-        r.eventCoarseRootC += dCoarse / len;
+        r.eventLitterC += dv.byLen(litterAdd);
+        r.eventSoilC += dv.byLen(soilAdd);
+        r.eventLeafC += dv.byLen(dLeaf);
+        r.eventWoodC += dv.byLen(dWood);
+        r.eventFineRootC += dv.byLen(dFine);
+        r.eventCoarseRootC += dv.byLen(dCoarse);
         double litterNAdd = 0.0, soilNAdd = 0.0;
         if (fl.on(F_NITROGEN)) {
-          const double nAbove = (mb.leaf / SIP_P(leafCN)) + (mb.wood / SIP_P(woodCN));
-          const double nBelow = (mb.fine / SIP_P(fineRootCN)) + (mb.coarse / SIP_P(woodCN));
+          const double nAbove = (dv.byLeafCN(mb.leaf)) + (dv.byWoodCN(mb.wood));
+          const double nBelow = (dv.byFineCN(mb.fine)) + (dv.byWoodCN(mb.coarse));
           litterNAdd = fTA * nAbove;
           soilNAdd = fTB * nBelow;
-          r.eventSoilOrgN += soilNAdd / len;
-          r.eventLitterN += litterNAdd / len;
+          r.eventSoilOrgN += dv.byLen(soilNAdd);
+          r.eventLitterN += dv.byLen(litterNAdd);
         }
         const double outC = ((woodC + mb.leaf) * fRA + (mb.fine + mb.coarse) * fRB);
         double outN = 0.0;
-        r.eventOutputC += outC / len;
+        r.eventOutputC += dv.byLen(outC);
         if (fl.on(F_NITROGEN)) {
-          outN = (mb.wood / SIP_P(woodCN) + mb.leaf / SIP_P(leafCN)) * fRA +
-                 (mb.fine / SIP_P(fineRootCN) + mb.coarse / SIP_P(woodCN)) * fRB;
-          r.eventOutputN += outN / len;
+          outN = (dv.byWoodCN(mb.wood) + dv.byLeafCN(mb.leaf)) * fRA +
+                 (dv.byFineCN(mb.fine) + dv.byWoodCN(mb.coarse)) * fRB;
+          r.eventOutputN += dv.byLen(outN);
         }
         const double v[10] = {soilAdd, litterAdd, dLeaf, dWood, dFine, dCoarse, soilNAdd, litterNAdd, outC, outN};
         rec.add(mb, ev.type, 0, 10, v);
@@ -352,37 +399,37 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
           minN = ev.p[2];
         }
         if (fl.on(F_LITTER_POOL)) {
-          r.eventLitterC += orgC / len;
+          r.eventLitterC += dv.byLen(orgC);
         } else {
-          r.eventSoilC += orgC / len;
+          r.eventSoilC += dv.byLen(orgC);
         }
         if (fl.on(F_NITROGEN)) {
-          r.eventLitterN += orgN / len;
-          r.eventMinN += minN / len;
+          r.eventLitterN += dv.byLen(orgN);
+          r.eventMinN += dv.byLen(minN);
         }
-        r.eventInputC += orgC / len;
-        if (fl.on(F_NITROGEN)) r.eventInputN += (orgN + minN) / len;
+        r.eventInputC += dv.byLen(orgC);
+        if (fl.on(F_NITROGEN)) r.eventInputN += dv.byLen(orgN + minN);
         const double v[6] = {fl.on(F_LITTER_POOL) ? orgC : 0.0, fl.on(F_LITTER_POOL) ? 0.0 : orgC, minN, orgN, orgC,
                              (orgN + minN)};
         rec.add(mb, ev.type, 0, 6, v);
       } break;
       case SIPNET_EV_LEAFON: {  // :686-705
-        double flux = SIP_P(leafGrowth) / len;
-        limit_leaf_on(fl, prm, mb, len, flux);
+        double flux = dv.byLen(SIP_P(leafGrowth));
+        limit_leaf_on(fl, dv, mb, len, flux);
         r.eventLeafOnCreation += flux;
         const double src = mb.wood + mb.coarse;
-        if (src > kTiny) r.eventLeafOnCreationFromWood += flux * mb.wood / src;
+        if (src > kTiny) r.eventLeafOnCreationFromWood += nm.div(flux * mb.wood, src);
       } break;
       case SIPNET_EV_LEAFOFF: {  // :706-728
         const double leafOff = mb.leaf * SIP_P(fracLeafFall);
-        r.eventLeafOffLitter += leafOff / len;
+        r.eventLeafOffLitter += dv.byLen(leafOff);
         double litterNAdd = 0.0, resorb = 0.0;
         if (fl.on(F_NITROGEN)) {
-          const double leafN = leafOff / SIP_P(leafCN);
+          const double leafN = dv.byLeafCN(leafOff);
           resorb = leafN * SIP_P(leafNResorptionFrac);
           litterNAdd = leafN - resorb;
-          r.eventLeafOffNResorption += resorb / len;
-          r.eventLitterN += litterNAdd / len;
+          r.eventLeafOffNResorption += dv.byLen(resorb);
+          r.eventLitterN += dv.byLen(litterNAdd);
         }
         const double v[3] = {leafOff, resorb, litterNAdd};
         rec.add(mb, ev.type, 1, 3, v);
@@ -394,36 +441,59 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
 
   // ---------------- calculateFluxes, sipnet.c:1256-1336 -------------------------------
   const double whc = SIP_P(soilWHC);
-  const double lai = mb.leaf / SIP_P(leafCSpWt);  // :1274
-  const double meanNpp = mb.ringSum / kMeanNppDays;  // getMeanTrackerMean, runmean.c:118
-  const double woodTot = mb.wood + mb.delta;         // getTotalWoodC
+  const double lai = nm.divs(mb.leaf, SIP_P(leafCSpWt), prm(kSeedLeafCSpWt));  // :1274
+  const double meanNpp = nm.divs(mb.ringSum, kMeanNppDays, kc.seed5);          // getMeanTrackerMean, runmean.c:118
+  const double woodTot = mb.wood + mb.delta;                                   // getTotalWoodC
+
+  // state-independent Q10 / VPD factors first: six independent exp-class evaluations
+  const double q10Fol = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
+                                nm.divs(c.tair - SIP_P(psnTOpt), 10.0, kc.seed10));      // sipnet.c:1056
+  const double q10Wood = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
+                                 nm.divs(c.tair, 10.0, kc.seed10));                        // :1067
+  const double tsoil10 = nm.divs(c.tsoil, 10.0, kc.seed10);
+  const double q10Coarse = nm.powc(SIP_P(coarseRootQ10), prm(kLogCoarseQ10), prm(kLogCoarseQ10 + 1), tsoil10);  // :1076
+  const double q10Fine = nm.powc(SIP_P(fineRootQ10), prm(kLogFineQ10), prm(kLogFineQ10 + 1), tsoil10);
+  const double tempEffect = nm.powc(SIP_P(soilRespQ10), prm(kLogSoilQ10), prm(kLogSoilQ10 + 1), tsoil10);  // depeffects.c:72-75
+  const double vpdPow = nm.powc(c.vpd, c.logVpdHi, c.logVpdLo, SIP_P(dVpdExp));                // :626
 
   // potPsn, :590-641
-  const double respPerGram = SIP_P(baseFolRespFrac) * SIP_P(aMax);
-  const double grossAMax = SIP_P(aMax) * SIP_P(aMaxFrac) + respPerGram;
-  // psnTRangeSq holds pow((psnTMax - psnTMin) / 2.0, 2) evaluated once per member by the setup kernel
-  double dTemp = (SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)) / prm(kPsnTRangeSqSlot);
+  const double respPerGram = prm(kRespPerGram);
+  const double grossAMax = prm(kGrossAMax);
+  // kPsnTRangeSqSlot holds pow((psnTMax - psnTMin) / 2.0, 2), evaluated once per member by the setup kernel
+  double dTemp = nm.divs((SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)), prm(kPsnTRangeSqSlot),
+                         prm(kSeedPsnTRangeSq));
   dTemp = fmax(dTemp, 0.0);
-  double dVpd = 1.0 - SIP_P(dVpdSlope) * sip_pow_cached(c.vpd, c.logVpdHi, c.logVpdLo, SIP_P(dVpdExp));
+  double dVpd = 1.0 - SIP_P(dVpdSlope) * vpdPow;
   dVpd = fmax(dVpd, 0.0);
   double dLight;
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
-    double cum = 0.0, cur = 0.0;
-    const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar);
+    const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = prm(kSeedHalfSatPar);
+    double eff[7];
+    // the seven layers are independent: each stage is issued for all layers before the next one
 #pragma unroll
     for (int layer = 0; layer <= 6; ++layer) {
       const double cumLai = lai * ((double)layer / 6);
-      const double inten = c.par * sip_exp(-1.0 * att * cumLai);
-      cur = (1 - sip_pow_cached(2.0, log2Hi, log2Lo, -1.0 * inten / hsp));
-      const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
-      cum += coeff * cur;
+      eff[layer] = nm.exp(-1.0 * att * cumLai);
     }
-    cum -= cur;
-    dLight = cum / (3.0 * 6);
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) {
+      const double inten = c.par * eff[layer];
+      eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
+    }
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
+    double cum = 0.0;
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) {
+      const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
+      cum += coeff * eff[layer];
+    }
+    cum -= eff[6];
+    dLight = nm.divs(cum, 3.0 * 6, kc.seed18);
   } else {
     dLight = 0;
   }
-  const double conv = 12.0 * (1.0 / 1000000000.0) * (SIP_P(leafCSpWt) / SIP_P(cFracLeaf)) * lai * 86400.0;
+  const double conv = prm(kConvBase) * lai * 86400.0;
   const double potPsn = grossAMax * dTemp * dVpd * dLight * conv;
   const double baseFolResp = respPerGram * conv;
 
@@ -433,21 +503,21 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     r.transpiration = 0.0;
     dWater = 1;
   } else {
-    const double wue = SIP_P(wueConst) / c.vpd;
-    const double potTrans = potPsn / wue * 1000.0 * (44.0 / 12.0) * (1.0 / 10000.0);
+    const double wue = nm.div(SIP_P(wueConst), c.vpd);
+    const double potTrans = nm.div(potPsn, wue) * 1000.0 * (44.0 / 12.0) * (1.0 / 10000.0);
     double removable = fmin(mb.water, whc) * SIP_P(waterRemoveFrac);
     if (c.tsoil < SIP_P(frozenSoilThreshold)) removable *= SIP_P(frozenSoilEff);
     r.transpiration = fmin(removable, potTrans);
-    dWater = r.transpiration / potTrans;
+    dWater = nm.div(r.transpiration, potTrans);
   }
 
   // calcPrecip, :848-882
   if (c.tair <= 0) {
-    r.snowFall = c.precip / len;
+    r.snowFall = dv.byLen(c.precip);
     r.rain = 0;
   } else {
     r.snowFall = 0;
-    r.rain = c.precip / len;
+    r.rain = dv.byLen(c.precip);
   }
   r.immedEvap = r.rain * SIP_P(immedEvapFrac);
   if (fl.on(F_LEAF_WATER)) {
@@ -463,12 +533,12 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
       r.snowMelt = 0;
       r.sublimation = 0;
     } else {
-      const double rd = SIP_P(rdConst) / c.wspd;
-      r.sublimation = k * (0.6 - c.vPress) / rd;
+      const double rd = nm.div(SIP_P(rdConst), c.wspd);
+      r.sublimation = nm.div(k * (0.6 - c.vPress), rd);
       double left = mb.snow + (r.snowFall * len);
       if (r.sublimation < 0) r.sublimation = 0;
       if (left - (r.sublimation * len) < 0) {
-        r.sublimation = left / len;
+        r.sublimation = dv.byLen(left);
         left = 0;
       } else {
         left -= (r.sublimation * len);
@@ -477,13 +547,13 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
         r.snowMelt = 0;
       } else {
         r.snowMelt = SIP_P(snowMelt) * c.tair;
-        if (left - (r.snowMelt * len) < 0) r.snowMelt = left / len;
+        if (left - (r.snowMelt * len) < 0) r.snowMelt = dv.byLen(left);
       }
     }
   }
 
   // calcSoilWaterFluxes, :963-1031
-  const double waterFrac = clip01(mb.water / whc);  // getClippedWaterFrac, depeffects.c:11
+  const double waterFrac = clip01(dv.byWhc(mb.water));  // getClippedWaterFrac, depeffects.c:11
   {
     const double k = (1.3 * 1005.) / 66. * (1. / 2501000.) * 1000. * 1000. * (1. / 10000) * 86400.0;
     double netIn = netRain + r.snowMelt;
@@ -493,12 +563,12 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     if (mb.snow > 0) {
       r.evaporation = 0;
     } else {
-      const double rd = SIP_P(rdConst) / c.wspd;
-      const double rsoil = sip_exp(SIP_P(rSoilConst1) - SIP_P(rSoilConst2) * waterFrac);
-      r.evaporation = k * c.vpdSoil / (rd + rsoil);
+      const double rd = nm.div(SIP_P(rdConst), c.wspd);
+      const double rsoil = nm.exp(SIP_P(rSoilConst1) - SIP_P(rSoilConst2) * waterFrac);
+      r.evaporation = nm.div(k * c.vpdSoil, rd + rsoil);
       if (r.evaporation < 0) r.evaporation = 0;
       if (left - (r.evaporation * len) < kTiny) {
-        r.evaporation = (left - kTiny) / len;
+        r.evaporation = dv.byLen(left - kTiny);
         left = 0;
       } else {
         left -= (r.evaporation * len);
@@ -507,9 +577,9 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     if (left > whc) {
       const double excess = left - whc;
       if (fl.on(F_FLOODING)) {
-        r.drainage = fmin(excess * SIP_P(waterDrainFrac), excess / len);
+        r.drainage = fmin(excess * SIP_P(waterDrainFrac), dv.byLen(excess));
       } else {
-        r.drainage = excess / len;
+        r.drainage = dv.byLen(excess);
       }
     } else {
       r.drainage = 0;
@@ -520,11 +590,9 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
 
   // vegResp / vegResp2, :1051-1103
   {
-    double fol = baseFolResp * sip_pow_cached(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
-                                              (c.tair - SIP_P(psnTOpt)) / 10.0);
+    double fol = baseFolResp * q10Fol;
     if (c.tsoil < SIP_P(frozenSoilThreshold)) fol *= SIP_P(frozenSoilFolREff);
-    const double woodR = SIP_P(baseVegResp) * woodTot *
-                         sip_pow_cached(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1), c.tair / 10.0);
+    const double woodR = SIP_P(baseVegResp) * woodTot * q10Wood;
     if (fl.on(F_GROWTH_RESP)) {
       double growth = SIP_P(growthRespFrac) * meanNpp;
       if (growth < 0) growth = 0;
@@ -556,25 +624,25 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
       } else if (fl.on(F_SOIL_PHENOL)) {
         past = c.tsoil >= SIP_P(soilTempLeafOn);
       } else if (SIP_P(leafOnDay) > 0) {
-        const double now = (double)c.day + c.time / 24.0;
+        const double now = (double)c.day + nm.divs(c.time, 24.0, kc.seed24);
         past = now >= SIP_P(leafOnDay);
       } else {
         past = false;
       }
       if (past) {
-        double on = SIP_P(leafGrowth) / len;
-        limit_leaf_on(fl, prm, mb, len, on);
+        double on = dv.byLen(SIP_P(leafGrowth));
+        limit_leaf_on(fl, dv, mb, len, on);
         r.leafOnCreation += on;
         const double src = mb.wood + mb.coarse;
-        if (src > kTiny) r.leafOnCreationFromWood += on * mb.wood / src;
+        if (src > kTiny) r.leafOnCreationFromWood += nm.div(on * mb.wood, src);
         mb.didGrowth = 1;
       }
     }
     if (!mb.didFall) {
       bool past = false;  // pastLeafFall, :733-742
-      if (SIP_P(leafOffDay) > 0) past = (c.day + c.time / 24.0) >= SIP_P(leafOffDay);
+      if (SIP_P(leafOffDay) > 0) past = (c.day + nm.divs(c.time, 24.0, kc.seed24)) >= SIP_P(leafOffDay);
       if (past) {
-        const double off = (mb.leaf * SIP_P(fracLeafFall)) / len;
+        const double off = dv.byLen(mb.leaf * SIP_P(fracLeafFall));
         r.leafLitter += off;
         mb.didFall = 1;
         if (off > kTiny && fl.on(F_EVENTS)) {
@@ -586,31 +654,35 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   }
 
   // shared dependency terms (depeffects.c); each is a pure function of (tsoil, soilWater, params)
-  const double tempEffect =
-      sip_pow_cached(SIP_P(soilRespQ10), prm(kLogSoilQ10), prm(kLogSoilQ10 + 1), c.tsoil / 10);  // calcTempEffect :72-75
-  double anaerobicIdx = 0.0;                                              // calcAnaerobicIndex :15-22
+  double anaerobicIdx = 0.0;  // calcAnaerobicIndex :15-22
   if (fl.on(F_ANAEROBIC) || fl.on(F_NITROGEN)) {
-    const double fa = SIP_P(fAnoxia);
-    anaerobicIdx = clip01((waterFrac - fa) / (1 - fa));
+    anaerobicIdx = clip01(nm.divs(waterFrac - SIP_P(fAnoxia), prm(kOneMinusFa), prm(kSeedOneMinusFa)));
   }
   double moistEffect;  // calcRespMoistEffect :24-63
   if (!fl.on(F_WATER_HRESP) || c.tsoil < 0) {
     moistEffect = 1.0;
   } else if (!fl.on(F_ANAEROBIC)) {
-    moistEffect = sip_pow(waterFrac, SIP_P(soilRespMoistEffect));
+    moistEffect = nm.pow(waterFrac, SIP_P(soilRespMoistEffect));
   } else {
-    const double dAer = clip01(waterFrac / SIP_P(fAnoxia));
+    const double dAer = clip01(nm.divs(waterFrac, SIP_P(fAnoxia), prm(kSeedFAnoxia)));
     moistEffect = (1 - anaerobicIdx) * dAer + SIP_P(anaerobicDecompRate) * anaerobicIdx;
   }
   const double tillEffect = 1 + mb.dTill;  // calcTillageEffect :77
 
+  // C:N ratios of the litter and soil pools (calcRatio); shared by calcCNEffect and calcNPoolFluxes
+  double litterCN = 0.0, soilCN = 0.0;
+  if (fl.on(F_NITROGEN)) {
+    litterCN = ratio(nm, mb.litter, mb.litN);
+    soilCN = ratio(nm, mb.soil, mb.orgN);
+  }
+
   // calcLitterFluxes, :1150-1171
   if (fl.on(F_LITTER_POOL)) {
     double cn = 1.0;  // calcCNEffect, depeffects.c:79-88
-    if (fl.on(F_NITROGEN)) cn = SIP_P(kCN) / (SIP_P(kCN) + safe_ratio(mb.litter, mb.litN));
+    if (fl.on(F_NITROGEN)) cn = nm.div(SIP_P(kCN), SIP_P(kCN) + litterCN);
     const double breakdown = mb.litter * SIP_P(litterBreakdownRate) * tempEffect * moistEffect * tillEffect * cn;
     r.rLitter = breakdown * SIP_P(fracLitterRespired);
-    r.litterToSoil = breakdown * (1.0 - SIP_P(fracLitterRespired));
+    r.litterToSoil = breakdown * prm(kOneMinusFracLitResp);
   }
 
   // calcRootFluxes, :1176-1196
@@ -618,21 +690,19 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   r.fineRootLoss += SIP_P(fineRootTurnoverRate) * mb.fine;
   r.coarseRootCreation += SIP_P(coarseRootAllocation) * meanNpp;
   r.fineRootCreation += SIP_P(fineRootAllocation) * meanNpp;
-  r.rCoarseRoot = SIP_P(baseCoarseRootResp) * mb.coarse *
-                  sip_pow_cached(SIP_P(coarseRootQ10), prm(kLogCoarseQ10), prm(kLogCoarseQ10 + 1), c.tsoil / 10.0);
-  r.rFineRoot = SIP_P(baseFineRootResp) * mb.fine *
-                sip_pow_cached(SIP_P(fineRootQ10), prm(kLogFineQ10), prm(kLogFineQ10 + 1), c.tsoil / 10.0);
+  r.rCoarseRoot = SIP_P(baseCoarseRootResp) * mb.coarse * q10Coarse;
+  r.rFineRoot = SIP_P(baseFineRootResp) * mb.fine * q10Fine;
 
   // calcSoilRespiration, :1132-1148
   {
     double cn = 1.0;
-    if (fl.on(F_NITROGEN)) cn = SIP_P(kCN) / (SIP_P(kCN) + safe_ratio(mb.soil, mb.orgN));
+    if (fl.on(F_NITROGEN)) cn = nm.div(SIP_P(kCN), SIP_P(kCN) + soilCN);
     r.rSoil = mb.soil * SIP_P(baseSoilResp) * moistEffect * tempEffect * tillEffect * cn;
   }
 
   // calcMethaneFlux, :1201-1214
   if (fl.on(F_ANAEROBIC)) {
-    const double mm = sip_pow(anaerobicIdx, SIP_P(anaerobicTransExp));  // calcMethaneMoistEffect
+    const double mm = nm.pow(anaerobicIdx, SIP_P(anaerobicTransExp));  // calcMethaneMoistEffect
     r.soilMethane = SIP_P(soilMethaneRate) * mb.soil * tempEffect * mm;
     if (fl.on(F_LITTER_POOL)) r.litterMethane = SIP_P(litterMethaneRate) * mb.litter * tempEffect * mm;
   }
@@ -640,13 +710,13 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   // checkNegativeCreation, limitations.c:146-182
   {
     const double turnover = mb.leaf * SIP_P(leafTurnoverRate);
-    const double leafDef = mb.leaf / len + r.leafCreation - turnover;
+    const double leafDef = dv.byLen(mb.leaf) + r.leafCreation - turnover;
     if (leafDef < 0) {
       r.woodCreation += leafDef;
       r.leafCreation -= leafDef;
     }
-    const double fineDef = mb.fine / len + r.fineRootCreation - r.fineRootLoss;
-    const double coarseDef = mb.coarse / len + r.coarseRootCreation - r.coarseRootLoss;
+    const double fineDef = dv.byLen(mb.fine) + r.fineRootCreation - r.fineRootLoss;
+    const double coarseDef = dv.byLen(mb.coarse) + r.coarseRootCreation - r.coarseRootLoss;
     if ((fineDef < 0.0) != (coarseDef < 0.0)) {
       if (fineDef < 0.0) {
         r.coarseRootCreation += fineDef;
@@ -662,10 +732,10 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   if (fl.on(F_NITROGEN)) {
     // calcNResorptionFluxes, nitrogen.c:170-196
     if (r.woodCreation + r.leafCreation + r.fineRootCreation + r.coarseRootCreation < 0.0) {
-      r.reductionNResorption -= (r.leafCreation / SIP_P(leafCN) + r.woodCreation / SIP_P(woodCN) +
-                                 r.coarseRootCreation / SIP_P(woodCN) + r.fineRootCreation / SIP_P(fineRootCN));
+      r.reductionNResorption -= (dv.byLeafCN(r.leafCreation) + dv.byWoodCN(r.woodCreation) +
+                                 dv.byWoodCN(r.coarseRootCreation) + dv.byFineCN(r.fineRootCreation));
     }
-    r.leafOffNResorption += SIP_P(leafNResorptionFrac) * r.leafLitter / SIP_P(leafCN);
+    r.leafOffNResorption += dv.byLeafCN(SIP_P(leafNResorptionFrac) * r.leafLitter);
     // calcNVolatilizationFlux, nitrogen.c:15-25 (+ calcVolatilizationMoistEffect, depeffects.c:90-96)
     {
       const double dw = 0.05 + 3.8 * anaerobicIdx * (1 - anaerobicIdx);
@@ -673,36 +743,31 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     }
     // calcNLeachingFlux, nitrogen.c:30-40
     {
-      double phi;
-      if ((r.drainage / whc) < 1) {
-        phi = r.drainage / whc;
-      } else {
-        phi = 1;
-      }
+      const double dOverWhc = dv.byWhc(r.drainage);
+      const double phi = (dOverWhc < 1) ? dOverWhc : 1;
       r.nLeaching = mb.minN * phi * SIP_P(nLeachingFrac);
     }
     // calcNPoolFluxes, nitrogen.c:45-83
     {
-      const double litterCN = safe_ratio(mb.litter, mb.litN);
-      const double soilCN = safe_ratio(mb.soil, mb.orgN);
-      const double litterMin = r.rLitter / litterCN;
-      const double soilMin = r.rSoil / soilCN;
-      const double inputs =
-          r.litterToSoil / litterCN + r.fineRootLoss / SIP_P(fineRootCN) + r.coarseRootLoss / SIP_P(woodCN);
-      const double sat = fl.on(F_CSAT) ? clip01(mb.soil / SIP_P(soilCSaturation)) : 0.0;
-      r.nOrgLitter = r.leafLitter / SIP_P(leafCN) - r.leafOffNResorption + r.woodLitter / SIP_P(woodCN) -
-                     litterMin - r.litterToSoil / litterCN + (inputs * sat);
+      const double litterMin = nm.div(r.rLitter, litterCN);
+      const double soilMin = nm.div(r.rSoil, soilCN);
+      const double l2sN = nm.div(r.litterToSoil, litterCN);
+      const double inputs = l2sN + dv.byFineCN(r.fineRootLoss) + dv.byWoodCN(r.coarseRootLoss);
+      const double sat =
+          fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), prm(kSeedCSat))) : 0.0;
+      r.nOrgLitter = dv.byLeafCN(r.leafLitter) - r.leafOffNResorption + dv.byWoodCN(r.woodLitter) - litterMin -
+                     l2sN + (inputs * sat);
       r.nOrgSoil = inputs * (1 - sat) - soilMin;
       r.nMin = litterMin + soilMin;
     }
-    n_fix_and_uptake(fl, prm, mb, r, len);  // nitrogen.c:156-168
+    n_fix_and_uptake(fl, dv, mb, r, len);  // nitrogen.c:156-168
 
     // checkMineralNLimitation, limitations.c:119-130
     {
       const double pool = mb.minN + (r.nMin + r.eventMinN) * len;
       const double loss = (r.nLeaching + r.nVolatilization) * len;
       if (loss > kTiny && loss > pool) {
-        const double red = pool / loss;
+        const double red = nm.div(pool, loss);
         r.nLeaching *= red;
         r.nVolatilization *= red;
       }
@@ -713,15 +778,15 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
       const double nonUptake = n_non_uptake(r) * len;
       const double avail = mb.minN + nonUptake;
       if (uptakeDemand > kTiny && uptakeDemand > avail) {
-        const double unclaimed = n_unclaimed_storage(prm, mb, r, len);
-        const double demand = n_demand(fl, prm, r) * len;
-        const double uptakeFrac = 1 - n_fix_frac(prm, mb);
-        const double red = (avail / uptakeFrac + unclaimed) / demand;
+        const double unclaimed = n_unclaimed_storage(dv, mb, r, len);
+        const double demand = n_demand(fl, dv, r) * len;
+        const double uptakeFrac = 1 - n_fix_frac(dv, mb);
+        const double red = nm.div(nm.div(avail, uptakeFrac) + unclaimed, demand);
         r.woodCreation *= red;
         r.leafCreation *= red;
         r.fineRootCreation *= red;
         r.coarseRootCreation *= red;
-        n_fix_and_uptake(fl, prm, mb, r, len);
+        n_fix_and_uptake(fl, dv, mb, r, len);
       }
     }
   }
@@ -762,7 +827,7 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
     mb.minN += r.eventMinN * len;
     mb.orgN += r.eventSoilOrgN * len;
     mb.litN += r.eventLitterN * len;
-    const double onN = n_leafon_from_c(prm, r.eventLeafOnCreation);
+    const double onN = n_leafon_from_c(dv, r.eventLeafOnCreation);
     mb.storN += (r.eventLeafOffNResorption - onN) * len;
   }
 
@@ -780,7 +845,7 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   // updatePoolsForSoil, sipnet.c:1634-1680
   if (fl.on(F_LITTER_POOL)) {
     const double inputs = r.coarseRootLoss + r.fineRootLoss + r.litterToSoil;
-    const double sat = fl.on(F_CSAT) ? clip01(mb.soil / SIP_P(soilCSaturation)) : 0.0;
+    const double sat = fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), prm(kSeedCSat))) : 0.0;
     mb.litter +=
         (r.woodLitter + r.leafLitter + (inputs * sat) - r.litterToSoil - r.rLitter - r.litterMethane) * len;
     mb.soil += (inputs * (1 - sat) - r.rSoil - r.soilMethane) * len;
@@ -795,9 +860,9 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
 
   // updateNitrogenPools, nitrogen.c:210-239
   if (fl.on(F_NITROGEN)) {
-    const double demand = n_demand(fl, prm, r);
+    const double demand = n_demand(fl, dv, r);
     const double fromStorage = demand - r.nUptake - r.nFixation;
-    const double onN = n_leafon_from_c(prm, r.leafOnCreation);
+    const double onN = n_leafon_from_c(dv, r.leafOnCreation);
     mb.storN += (r.leafOffNResorption + r.reductionNResorption - fromStorage - onN) * len;
     const double nonUptake = n_non_uptake(r);
     mb.minN += (nonUptake - r.nUptake) * len;
@@ -820,8 +885,8 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
       mb.soil += mb.wood + mb.leaf + mb.delta;
     }
     if (fl.on(F_NITROGEN)) {
-      mb.orgN += mb.fine / SIP_P(fineRootCN) + mb.coarse / SIP_P(woodCN);
-      mb.litN += mb.wood / SIP_P(woodCN) + mb.leaf / SIP_P(leafCN) + mb.storN;
+      mb.orgN += dv.byFineCN(mb.fine) + dv.byWoodCN(mb.coarse);
+      mb.litN += dv.byWoodCN(mb.wood) + dv.byLeafCN(mb.leaf) + mb.storN;
     }
     mb.wood = 0.0;
     mb.leaf = 0.0;
@@ -883,14 +948,14 @@ __device__ __forceinline__ void step(const FL &fl, const PT &prm, const ClimRec 
   t.woodCreation = r.woodCreation * len;
   t.methane = (r.soilMethane + r.litterMethane) * len;
   t.evapotranspiration = (r.transpiration + r.immedEvap + r.evaporation + r.sublimation + r.eventEvap) * len;
-  mb.wetFrac = (oldSoilWater + mb.water) / (2.0 * whc);
+  mb.wetFrac = nm.divs(oldSoilWater + mb.water, prm(kTwoWhc), prm(kSeedTwoWhc));
   if (DEBUG) ext.yLitter += r.leafLitter + r.eventLeafOffLitter;
   if (fl.on(F_GDD)) {
     mb.gdd += c.gdd;
   } else {
     mb.gdd = 0.0;
   }
-  t.meanNPP = mb.ringSum / kMeanNppDays;  // read before this step's insert (sipnet.c:1486 precedes :1852)
+  t.meanNPP = nm.divs(mb.ringSum, kMeanNppDays, kc.seed5);  // read before this step's insert (sipnet.c:1486 precedes :1852)
   if (fl.on(F_NITROGEN)) {
     t.n2o = r.nVolatilization * len;
     t.nLeaching = r.nLeaching * len;

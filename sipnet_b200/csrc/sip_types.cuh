@@ -30,7 +30,26 @@ constexpr int kLogVegQ10 = SIPNET_GPU_NPARAMS + 1;     // vegRespQ10, sipnet.c:1
 constexpr int kLogCoarseQ10 = SIPNET_GPU_NPARAMS + 3;  // coarseRootQ10, sipnet.c:1076
 constexpr int kLogFineQ10 = SIPNET_GPU_NPARAMS + 5;    // fineRootQ10, sipnet.c:1076
 constexpr int kLogSoilQ10 = SIPNET_GPU_NPARAMS + 7;    // soilRespQ10, depeffects.c:74
-constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 9;
+// division seeds (sip_num.cuh FastNum::seed) of the member-constant divisors
+constexpr int kSeedLeafCSpWt = SIPNET_GPU_NPARAMS + 9;
+constexpr int kSeedPsnTRangeSq = SIPNET_GPU_NPARAMS + 10;
+constexpr int kSeedHalfSatPar = SIPNET_GPU_NPARAMS + 11;
+constexpr int kSeedWhc = SIPNET_GPU_NPARAMS + 12;
+constexpr int kSeedTwoWhc = SIPNET_GPU_NPARAMS + 13;
+constexpr int kSeedLeafCN = SIPNET_GPU_NPARAMS + 14;
+constexpr int kSeedWoodCN = SIPNET_GPU_NPARAMS + 15;
+constexpr int kSeedFineRootCN = SIPNET_GPU_NPARAMS + 16;
+constexpr int kSeedFAnoxia = SIPNET_GPU_NPARAMS + 17;
+constexpr int kSeedOneMinusFa = SIPNET_GPU_NPARAMS + 18;
+constexpr int kSeedCSat = SIPNET_GPU_NPARAMS + 19;
+// member-constant sub-expressions of potPsn() / depeffects (same operations, evaluated once)
+constexpr int kRespPerGram = SIPNET_GPU_NPARAMS + 20;  // baseFolRespFrac * aMax, sipnet.c:614
+constexpr int kGrossAMax = SIPNET_GPU_NPARAMS + 21;    // aMax * aMaxFrac + respPerGram, sipnet.c:617
+constexpr int kConvBase = SIPNET_GPU_NPARAMS + 22;     // 12 * (1/1e9) * (leafCSpWt / cFracLeaf), sipnet.c:632-633
+constexpr int kOneMinusFa = SIPNET_GPU_NPARAMS + 23;   // 1 - fAnoxia, depeffects.c:21
+constexpr int kTwoWhc = SIPNET_GPU_NPARAMS + 24;       // 2.0 * soilWHC, sipnet.c:1474
+constexpr int kOneMinusFracLitResp = SIPNET_GPU_NPARAMS + 25;  // 1.0 - fracLitterRespired, sipnet.c:1165
+constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 26;
 
 // flag bits (runtime mask / compile-time specialisation)
 enum : uint32_t {
@@ -48,7 +67,7 @@ enum : uint32_t {
   F_CSAT = 1u << 11,
 };
 
-// One climate step as staged to shared memory: 16 x 8 bytes = 128 bytes
+// One climate step as staged to shared memory: 17 x 8 bytes = 136 -> padded to 144 bytes
 // (multiple of 16 so a chunk is a legal cp.async.bulk size).
 struct alignas(16) ClimRec {
   double time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
@@ -58,10 +77,12 @@ struct alignas(16) ClimRec {
   double tillDecay;
   // log_inline(vpd) as hi + lo (sip_libm.cuh pow_log) for pow(vpd, dVpdExp), sipnet.c:626; NaN = not regular
   double logVpdHi, logVpdLo;
+  // 1 / length when length is a power of two (then x / length == x * invLen exactly), else 0
+  double invLenPow2;
   int32_t year, day;
   int32_t evBegin, evEnd;  // events of this step: [evBegin, evEnd) in the site's EventDev array
 };
-static_assert(sizeof(ClimRec) == 128, "ClimRec must be 128 bytes");
+static_assert(sizeof(ClimRec) == 144 && sizeof(ClimRec) % 16 == 0, "ClimRec must be a multiple of 16 bytes");
 
 struct alignas(16) EventDev {
   double p[4];
@@ -89,6 +110,14 @@ struct RunArgs {
   double *ringV;
   double *ringW;
   uint32_t *status;
+  // segment-start copies used when a member is replayed by the general kernel
+  const double *stateBackup;
+  const double *ringVBackup;
+  const double *ringWBackup;
+  const uint32_t *statusBackup;
+  const double *loglikBackup;
+  const double *loglikNBackup;
+  const int32_t *recCountBackup;
   const BlockDesc *blocks;
   const SiteDev *sites;
   int64_t stepBegin, stepEnd;

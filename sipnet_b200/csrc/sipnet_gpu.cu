@@ -26,17 +26,15 @@
 #include "sip_types.cuh"
 
 namespace sip {
-#define SIP_DECLARE_NS(ns)                                                                                          \
-  namespace ns {                                                                                                    \
-  cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, cudaStream_t stream);         \
-  cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);   \
-  cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,      \
-                                const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,  \
-                                uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,               \
-                                cudaStream_t stream);                                                               \
-  }
-SIP_DECLARE_NS(val)
-SIP_DECLARE_NS(fast)
+namespace k1 {
+// mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members
+cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream);
+cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);
+cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
+                              const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
+                              uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
+                              cudaStream_t stream);
+}  // namespace k1
 cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
                            int64_t nsites, double *mean, double *var, cudaStream_t stream);
 cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
@@ -100,6 +98,10 @@ struct sipnet_gpu_handle {
   sipnet_gpu_event_record *recs = nullptr;
   int32_t *recCount = nullptr;
   double *mean = nullptr, *var = nullptr, *quant = nullptr, *qprobs = nullptr, *qscratch = nullptr;
+  // segment-start copies for the replay of members flagged by the optimistic kernel (MATH_FAST only)
+  double *stateBk = nullptr, *ringVBk = nullptr, *ringWBk = nullptr, *loglikBk = nullptr, *loglikNBk = nullptr;
+  uint32_t *statusBk = nullptr;
+  int32_t *recCountBk = nullptr;
   bool summariesValid = false;
   std::vector<SiteDev> hostSites;
 };
@@ -166,6 +168,11 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimR
       c.logVpdHi = l.hi;
       c.logVpdLo = l.lo;
     }
+    {
+      int ex = 0;
+      const double mant = std::frexp(c.length, &ex);  // power of two <=> mantissa 0.5: then x / length == x * (1 / length)
+      c.invLenPow2 = (mant == 0.5 && ex > -500 && ex < 500) ? 1.0 / c.length : 0.0;
+    }
     c.evBegin = (int32_t)e;
     while (e < nev && s.events[e].year <= c.year && s.events[e].day <= c.day) {  // events.c:471
       const sipnet_gpu_event &ev = s.events[e];
@@ -197,7 +204,8 @@ static void free_handle(sipnet_gpu_handle *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
                   h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant, h->qprobs,
-                  h->qscratch};
+                  h->qscratch, h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
+                  h->recCountBk};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : h->siteAllocs)
@@ -216,13 +224,8 @@ static cudaError_t dalloc(T **p, size_t count) {
 }
 
 static int run_init_state(sipnet_gpu_handle *h) {
-  cudaError_t e;
-  if (h->math == SIPNET_GPU_MATH_FAST)
-    e = fast::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state, h->ringV,
-                                h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
-  else
-    e = val::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state, h->ringV,
-                               h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
+  cudaError_t e = k1::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state,
+                                        h->ringV, h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "init_state launch failed: %s", cudaGetErrorString(e));
   h->stepsDone = 0;
@@ -437,6 +440,17 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     INIT_CUDA(dalloc(&h->recCount, (size_t)h->ld));
     if (h->maxRecs > 0) INIT_CUDA(dalloc(&h->recs, (size_t)h->nmembers * h->maxRecs));
   }
+  if (h->math == SIPNET_GPU_MATH_FAST) {
+    INIT_CUDA(dalloc(&h->stateBk, (size_t)SIPNET_GPU_NSTATE * h->ld));
+    INIT_CUDA(dalloc(&h->ringVBk, (size_t)h->ringCap * h->ld));
+    INIT_CUDA(dalloc(&h->ringWBk, (size_t)h->ringCap * h->ld));
+    INIT_CUDA(dalloc(&h->statusBk, (size_t)h->ld));
+    if (h->loglik) {
+      INIT_CUDA(dalloc(&h->loglikBk, (size_t)h->ld));
+      INIT_CUDA(dalloc(&h->loglikNBk, (size_t)h->ld));
+    }
+    if (h->recCount) INIT_CUDA(dalloc(&h->recCountBk, (size_t)h->ld));
+  }
   const size_t nsum = (size_t)h->nsites * h->summaryCols.size() * h->outCap;
   if (cfg->outputs & SIPNET_GPU_OUT_MOMENTS) {
     INIT_CUDA(dalloc(&h->mean, nsum));
@@ -471,9 +485,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
 }
 
 static int derive_params(sipnet_gpu_handle *h) {
-  cudaError_t e = (h->math == SIPNET_GPU_MATH_FAST)
-                      ? fast::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream)
-                      : val::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream);
+  cudaError_t e = k1::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "derive launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -567,13 +579,38 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
     if (h->dbg)
       CUDA_OK(cudaMemsetAsync(h->dbg, 0xFF, (size_t)SIPNET_GPU_NDEBUG * a.outSteps * h->ld * sizeof(double), h->stream));
   }
+  const bool debug = h->dbg != nullptr;
+  const bool optimistic = (h->math == SIPNET_GPU_MATH_FAST) && !debug;
+  if (optimistic) {  // keep the segment's start state so flagged members can be replayed exactly
+    const size_t ldB = (size_t)h->ld * sizeof(double);
+    CUDA_OK(cudaMemcpyAsync(h->stateBk, h->state, SIPNET_GPU_NSTATE * ldB, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->ringVBk, h->ringV, h->ringCap * ldB, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->ringWBk, h->ringW, h->ringCap * ldB, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->statusBk, h->status, (size_t)h->ld * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->loglik) {
+      CUDA_OK(cudaMemcpyAsync(h->loglikBk, h->loglik, ldB, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_OK(cudaMemcpyAsync(h->loglikNBk, h->loglikN, ldB, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->recCount)
+      CUDA_OK(cudaMemcpyAsync(h->recCountBk, h->recCount, (size_t)h->ld * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    a.stateBackup = h->stateBk;
+    a.ringVBackup = h->ringVBk;
+    a.ringWBackup = h->ringWBk;
+    a.statusBackup = h->statusBk;
+    a.loglikBackup = h->loglikBk;
+    a.loglikNBackup = h->loglikNBk;
+    a.recCountBackup = h->recCountBk;
+  }
   CUDA_OK(cudaEventRecord(h->evStart, h->stream));
-  cudaError_t e = (h->math == SIPNET_GPU_MATH_FAST)
-                      ? fast::launch_run(a, h->nblocks, h->blockThreads, h->dbg != nullptr, h->stream)
-                      : val::launch_run(a, h->nblocks, h->blockThreads, h->dbg != nullptr, h->stream);
+  cudaError_t e = k1::launch_run(a, h->nblocks, h->blockThreads, debug, optimistic ? 1 : 0, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "run launch failed: %s", cudaGetErrorString(e));
   CUDA_OK(cudaEventRecord(h->evStop, h->stream));
+  if (optimistic) {  // members outside the optimistic guards (normally none) are re-run by the general kernel
+    e = k1::launch_run(a, h->nblocks, h->blockThreads, false, 2, h->stream);
+    h->launches++;
+    if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "replay launch failed: %s", cudaGetErrorString(e));
+  }
   h->stepsDone = step_end;
   return SIPNET_GPU_OK;
 }
