@@ -20,7 +20,7 @@ import numpy as np
 from . import _abi as A
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libsipnet_gpu.so")
+LIB_PATH = os.environ.get("SIPNET_GPU_LIB") or os.path.join(_PKG_DIR, "libsipnet_gpu.so")
 
 
 class SipnetGpuError(RuntimeError):

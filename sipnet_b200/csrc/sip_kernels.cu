@@ -57,6 +57,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ---- per-step output sink -----------------------------------------------------------
+// FULL = all 32 outputState() columns are kept, slot == column: the store address is one running
+// pointer bumped by a column stride (the emit calls come in column order).  Otherwise only the
+// columns with a slot (summary outputs) are stored.
+template <bool FULL>
 struct Emitter {
   const RunArgs *a;
   double *outp;  // a->out + m (null => no column output)
@@ -65,8 +69,18 @@ struct Emitter {
   const double *obs;  // site's observations or null
   int64_t tSite;
   double ll, lln;
-  __device__ __forceinline__ void out(int col, double v) const {
-    if (outp != nullptr) {
+  double *cur;
+  int64_t colStride;  // elements between consecutive columns = outSteps * ld
+  __device__ __forceinline__ void begin(int64_t tl, int64_t ts) {
+    tLocal = tl;
+    tSite = ts;
+    if (FULL) cur = outp + tl * a->ld;
+  }
+  __device__ __forceinline__ void out(int col, double v) {
+    if (FULL) {
+      __stcs(cur, v);
+      cur += colStride;
+    } else if (outp != nullptr) {
       const int s = a->colSlot[col];
       if (s >= 0) __stcs(outp + ((int64_t)s * a->outSteps + tLocal) * a->ld, v);
     }
@@ -185,12 +199,19 @@ __device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const 
 // ---- K1: fused [events -> fluxes -> pools -> trackers -> mean tracker] over a step range ----
 // REPLAY = true: only members the optimistic kernel flagged (SIPNET_GPU_ST_REPLAY set during this
 // segment) are integrated, starting again from the segment's start state (RunArgs::*Backup).
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY>
-__global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunArgs a) {
+constexpr int kLibmTabWords = 2 * 128 + 4 * 128;  // exp table + pow-log table, 6 KB
+
+#ifndef SIP_MIN_BLOCKS_128
+#define SIP_MIN_BLOCKS_128 1
+#endif
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
+    run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNParamDev][BLOCK]
   ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNParamDev * BLOCK);  // [2][kChunkSteps]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);              // [2]
+  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
+  uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
 
   const BlockDesc bd = a.blocks[blockIdx.x];
   const SiteDev site = a.sites[bd.site];
@@ -214,6 +235,10 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
   }
   // parameter tile: coalesced global reads, column-per-thread shared layout
   for (int k = 0; k < kNParamDev; ++k) tile[k * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+  if (NM::kFast) {  // libm tables -> shared memory (table lookups become LDS)
+    for (int i = tid; i < 2 * 128; i += BLOCK) libmTab[i] = libm::d_exp_tab[i];
+    for (int i = tid; i < 4 * 128; i += BLOCK) libmTab[2 * 128 + i] = libm::d_powlog_tab[i];
+  }
   __syncthreads();
 
   auto issue = [&](int64_t chunk) {
@@ -245,6 +270,13 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) active = false;  // reference would have exited (sipnet.c:1117-1122)
   }
   NM nm;
+  if constexpr (NM::kFast) {
+    nm.expTab = libmTab;
+    nm.powlogTab = libmTab + 2 * 128;
+    // the member-constant division seeds must be ordinary numbers (divisor non-zero, normal, finite)
+    for (int k = kSeedLeafCSpWt; k <= kSeedCSat; ++k)
+      if (k != kSeedCSat || fl.on(F_CSAT)) nm.seed_check(tile[k * BLOCK + tid]);
+  }
   const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
   const ParamTile prm{tile + tid, BLOCK};
   const RingRef rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
@@ -253,8 +285,8 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     rec.count = a.recCount + m;
     rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
   }
-  Emitter emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
-               site.neeObs, 0, 0.0, 0.0};
+  Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
+                     site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld};
 
   for (int64_t chunk = 0; chunk < nChunks; ++chunk) {
     if (tid == 0 && chunk + 1 < nChunks) issue(chunk + 1);  // buffer (chunk+1)&1 was released by the barrier below
@@ -265,8 +297,7 @@ __global__ void __launch_bounds__(BLOCK) run_kernel(const __grid_constant__ RunA
     if (active) {
       for (int i = 0; i < n; ++i) {
         const int64_t t = cs + i;
-        emit.tLocal = t - t0;
-        emit.tSite = t;
+        emit.begin(t - t0, t);
         rec.step = (int32_t)t;
         step<FL, DEBUG>(fl, nm, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, kc);
       }
@@ -415,34 +446,40 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
 
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY>
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * kNParamDev * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) + 2 * sizeof(uint64_t);
-  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY>;
+  const size_t smem = sizeof(double) * kNParamDev * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
+                      kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
+  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<nblocks, BLOCK, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
+template <class FL, int BLOCK>
+static cudaError_t launch_fast(const RunArgs &a, int nblocks, bool full, cudaStream_t stream) {
+  return full ? launch_one<FL, false, FastNum, BLOCK, false, true>(a, nblocks, stream)
+              : launch_one<FL, false, FastNum, BLOCK, false, false>(a, nblocks, stream);
+}
+
 // mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members (exact)
 template <int BLOCK>
 static cudaError_t launch_block(const RunArgs &a, int nblocks, bool debug, int mode, cudaStream_t stream) {
   const uint32_t arith = a.flags & ~(uint32_t)F_SNOW;  // ctx.snow has no arithmetic effect (SURVEY 8a trap 6)
-  if (mode == 2) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, true>(a, nblocks, stream);
-  if (debug) return launch_one<RuntimeFlags, true, ExactNum, BLOCK, false>(a, nblocks, stream);
-  if (mode == 0) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, false>(a, nblocks, stream);
-  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW))
-    return launch_one<StaticFlags<kMaskDefault>, false, FastNum, BLOCK, false>(a, nblocks, stream);
-  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW))
-    return launch_one<StaticFlags<kMaskCropN>, false, FastNum, BLOCK, false>(a, nblocks, stream);
-  return launch_one<RuntimeFlags, false, FastNum, BLOCK, false>(a, nblocks, stream);
+  bool full = a.out != nullptr;
+  for (int c = 0; c < SIPNET_GPU_NOUT; ++c) full = full && a.colSlot[c] == c;
+  if (mode == 2) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, true, false>(a, nblocks, stream);
+  if (debug) return launch_one<RuntimeFlags, true, ExactNum, BLOCK, false, false>(a, nblocks, stream);
+  if (mode == 0) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, false, false>(a, nblocks, stream);
+  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW)) return launch_fast<StaticFlags<kMaskDefault>, BLOCK>(a, nblocks, full, stream);
+  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW)) return launch_fast<StaticFlags<kMaskCropN>, BLOCK>(a, nblocks, full, stream);
+  return launch_fast<RuntimeFlags, BLOCK>(a, nblocks, full, stream);
 }
 
 cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream) {
   switch (blockThreads) {
     case 32: return launch_block<32>(a, nblocks, debug, mode, stream);
-    case 64: return launch_block<64>(a, nblocks, debug, mode, stream);
     case 128: return launch_block<128>(a, nblocks, debug, mode, stream);
     default: return cudaErrorInvalidValue;
   }

@@ -297,7 +297,14 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
                                      Member &mb, MemberExt &ext, const RingRef &rg, const RecSink &rec,
                                      Emit &emit, const StepConsts &kc) {
   const double len = c.length;
-  const Div<NM, PT> dv{nm, prm, len, (NM::kFast && c.invLenPow2 == 0.0) ? nm.seed(len) : 0.0, c.invLenPow2};
+  double seedLen = 0.0;
+  if constexpr (NM::kFast) {
+    if (c.invLenPow2 == 0.0) {  // block-uniform: the step length is not a power of two
+      seedLen = nm.seed(len);
+      nm.seed_check(seedLen);
+    }
+  }
+  const Div<NM, PT> dv{nm, prm, len, seedLen, c.invLenPow2};
   const double oldSoilWater = mb.water;  // sipnet.c:1821
   Rates r = {};                          // resetFluxes, sipnet.c:1222
   bool alive = has_biomass(mb);          // initPlantSurvivalTracker, sipnet.c:1538

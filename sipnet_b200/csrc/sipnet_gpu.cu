@@ -247,8 +247,8 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   if (cfg->params_ld < cfg->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "params_ld < nmembers");
   if (cfg->math != SIPNET_GPU_MATH_VALIDATION && cfg->math != SIPNET_GPU_MATH_FAST)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "unknown math mode %d", cfg->math);
-  if (cfg->block_threads != 0 && cfg->block_threads != 32 && cfg->block_threads != 64 && cfg->block_threads != 128)
-    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "block_threads must be 0, 32, 64 or 128");
+  if (cfg->block_threads != 0 && cfg->block_threads != 32 && cfg->block_threads != 128)
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "block_threads must be 0, 32 or 128");
   if ((cfg->outputs & SIPNET_GPU_OUT_LOGLIK) && !(cfg->nee_sigma > 0))
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "nee_sigma must be > 0");
   if ((cfg->outputs & (SIPNET_GPU_OUT_MOMENTS | SIPNET_GPU_OUT_QUANTILES)) &&
@@ -384,7 +384,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     int smCount = 148;
     cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, cfg->device);
     h->blockThreads = 32;
-    for (int bt : {128, 64}) {  // largest block that still gives every SM >= 2 blocks
+    for (int bt : {128}) {  // largest block that still gives every SM >= 2 blocks
       if (count_blocks(bt) >= 2 * (int64_t)smCount) {
         h->blockThreads = bt;
         break;
