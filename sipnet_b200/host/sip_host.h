@@ -1,0 +1,92 @@
+/*
+ * sip_host.h -- host side of the drop-in (plain C11).
+ *
+ * Restates the semantics of the reference's input readers and text writers so
+ * that `sipnet_gpu -i sipnet.in` is a drop-in for `sipnet -i sipnet.in`:
+ *
+ *   configuration   sipnet.in + command line        reference src/sipnet/frontend.c:35-128,
+ *                                                    src/sipnet/cli.c:144-233, src/common/context.c
+ *   <prefix>.param  name/value parameter file       src/sipnet/sipnet.c:290-427, src/common/modelParams.c:136-230
+ *   <prefix>.clim   12- or legacy 14-column forcing  src/sipnet/sipnet.c:128-277
+ *   events.in       agronomic events                 src/sipnet/events.c:39-367
+ *   <prefix>.out    per-step text rows               src/sipnet/sipnet.c:434-473
+ *   events.out      applied / computed events        src/sipnet/events.c:369-418
+ *   <prefix>.config final configuration dump         src/common/context.c:225-267
+ *
+ * No function here calls exit(): each returns 0 or the reference's exit code
+ * (src/common/exitCodes.h:16-27) and leaves a message in sip_host_error().
+ * Nothing here touches the GPU; the driver (sipnet_gpu_main.c) hands the parsed
+ * inputs to the device through include/sipnet_gpu.h.
+ */
+#ifndef SIP_HOST_H
+#define SIP_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sipnet_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIP_NAME_MAX 256 /* CONTEXT_CHAR_MAXLEN, context.h:8 */
+
+/* where a setting came from; higher wins (context.h:18-26) */
+enum sip_source { SIP_SRC_DEFAULT = 0, SIP_SRC_INPUT_FILE = 1, SIP_SRC_COMMAND_LINE = 2, SIP_SRC_CALCULATED = 3 };
+
+/* the reference's struct Context (context.h:42-92), without the hash map */
+typedef struct sip_context {
+  sipnet_gpu_flags flags; /* the 12 model flags */
+  int32_t doMainOutput, doSingleOutputs, dumpConfig, printHeader, quiet;
+  char paramFile[SIP_NAME_MAX], climFile[SIP_NAME_MAX], outFile[SIP_NAME_MAX], outConfigFile[SIP_NAME_MAX];
+  char eventsPrefix[SIP_NAME_MAX], eventsInFile[SIP_NAME_MAX], eventsOutFile[SIP_NAME_MAX];
+  char inputFile[SIP_NAME_MAX], restartIn[SIP_NAME_MAX], restartOut[SIP_NAME_MAX], debugLogPrefix[SIP_NAME_MAX];
+  char filePrefix[SIP_NAME_MAX];
+  /* provenance per setting, indexed like sip_setting_name() */
+  int32_t source[32];
+  /* extensions of this implementation (not in the reference) */
+  char ensembleParamList[SIP_NAME_MAX]; /* --ensemble-params FILE: one .param path per line => one member each */
+  int32_t validationMath;               /* --validation-math: run the general kernel */
+  int32_t helpOrVersion;                /* 1 = --help printed, 2 = --version printed (caller exits 0) */
+} sip_context;
+
+const char *sip_host_error(void);
+
+/* ---- configuration ------------------------------------------------------------------------ */
+void sip_context_init(sip_context *ctx);                               /* initContext(), context.c:26-67 */
+int sip_parse_cli(sip_context *ctx, int argc, char **argv);           /* parseCommandLineArgs(), cli.c:144-233 */
+int sip_read_input_file(sip_context *ctx);                             /* readInputFile(), frontend.c:35-128 */
+int sip_validate_context(const sip_context *ctx);                      /* validateContext(), context.c:195-223 */
+int sip_derive_file_names(sip_context *ctx);                           /* frontend.c:164-209 */
+int sip_print_config(const sip_context *ctx, FILE *out, const char *timestamp); /* printConfig(), context.c:225-267 */
+
+/* ---- inputs --------------------------------------------------------------------------------- */
+/* One site's forcing as left by readClimData() plus its events as left by readEventData(). */
+typedef struct sip_site_data {
+  int64_t nsteps;
+  int32_t *year, *day;
+  double *time, *length, *tair, *tsoil, *par, *precip, *vpd, *vpdSoil, *vPress, *wspd, *gdd;
+  int64_t nevents;
+  sipnet_gpu_event *events;
+} sip_site_data;
+
+int sip_read_params(const char *path, const sipnet_gpu_flags *flags, int quiet, double out[SIPNET_GPU_NPARAMS]);
+int sip_read_clim(const char *path, int gddFlag, int quiet, sip_site_data *site);
+int sip_read_events(const char *path, const sipnet_gpu_flags *flags, const double params[SIPNET_GPU_NPARAMS],
+                    int quiet, sip_site_data *site);
+void sip_site_free(sip_site_data *site);
+void sip_site_view(const sip_site_data *site, sipnet_gpu_site *view); /* borrow as the ABI's site struct */
+
+/* ---- outputs ---------------------------------------------------------------------------------- */
+void sip_write_header(FILE *out);                                                         /* outputHeader() */
+void sip_write_state_row(FILE *out, int year, int day, double time, const double *out32, int64_t stride);
+                                                                                          /* outputState(); out32[c*stride] */
+void sip_write_events_header(FILE *out);                                                  /* openEventOutFile() header */
+int sip_write_event_row(FILE *out, int year, int day, const sipnet_gpu_event_record *rec); /* doWriteEventOut() */
+const char *sip_event_type_name(int type);                                                /* eventTypeToString() */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

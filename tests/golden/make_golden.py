@@ -67,8 +67,12 @@ def run_case(shim: RefShim, name: str, flags: dict, params: np.ndarray, site, pr
         rc, done, out, dbg = shim.run(flags, params, site, events_out=ev_out, main_out=main_out,
                                       print_header=print_header)
         ev_text = open(ev_out, "rb").read() if os.path.exists(ev_out) else b""
-        main_md5 = hashlib.md5(open(main_out, "rb").read()).hexdigest()
+        main_bytes = open(main_out, "rb").read()
+        main_md5 = hashlib.md5(main_bytes).hexdigest()
+        main_lines = main_bytes.split(b"\n")
     rows = keep_rows(done)
+    hdr = 1 if print_header else 0
+    out_text = b"\n".join(main_lines[hdr + int(r)] for r in rows) + b"\n"   # the reference's own text rows
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
         flags=flags_array(flags), params=params, year=site.year, day=site.day,
@@ -76,11 +80,33 @@ def run_case(shim: RefShim, name: str, flags: dict, params: np.ndarray, site, pr
         rows=rows, out32=out[rows], dbg=dbg[rows], colsum=out[:done].sum(axis=0),
         colabs=np.abs(out[:done]).max(axis=0), nsteps=np.int64(done), rc=np.int64(rc),
         print_header=np.int64(print_header),
-        events_out=np.frombuffer(ev_text, dtype=np.uint8), main_out_md5=np.frombuffer(main_md5.encode(), dtype=np.uint8))
+        events_out=np.frombuffer(ev_text, dtype=np.uint8), main_out_md5=np.frombuffer(main_md5.encode(), dtype=np.uint8),
+        out_text=np.frombuffer(out_text, dtype=np.uint8))
     print(f"{name}: rc={rc} steps={done} rows={rows.size} events.out={len(ev_text)}B")
 
 
+def pack_smoke_inputs():
+    """Raw input files of the reference's smoke cases (data, not code) so the drop-in CLI can be
+    run end to end where /root/reference does not exist (the GPU box)."""
+    import io
+    import tarfile
+    path = os.path.join(OUT, "smoke_inputs.tar.gz")
+    with tarfile.open(path, "w:gz", compresslevel=9) as tar:
+        for name in SMOKE:
+            d = os.path.join(REF, "tests", "smoke", name)
+            for fn in ("sipnet.in", "sipnet.param", "sipnet.clim", "events.in"):
+                if fn == "sipnet.clim" and name in ("russell_2", "russell_3"):
+                    continue  # byte-identical to russell_1/sipnet.clim; tests copy that one
+                data = open(os.path.join(d, fn), "rb").read()
+                ti = tarfile.TarInfo(f"{name}/{fn}")
+                ti.size = len(data)
+                ti.mtime = 0
+                tar.addfile(ti, io.BytesIO(data))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    pack_smoke_inputs()
     shim = RefShim()
     for name, flags in SMOKE.items():
         d = os.path.join(REF, "tests", "smoke", name)

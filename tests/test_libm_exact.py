@@ -38,26 +38,24 @@ def test_tables_match_system_libm():
 
 @pytest.mark.gpu
 def test_device_libm_is_bit_exact():
-    import math
     from sipnet_b200 import api
     rng = np.random.default_rng(12345)
     n = 400000
     xs = np.concatenate([rng.uniform(-60, 20, n), rng.uniform(-750, 710, n), rng.uniform(-1100, 1100, n // 4),
                          np.array([0.0, -0.0, 1e-300, -1e-17, 709.78, -745.13, 512.0, -512.0, np.inf, -np.inf, np.nan])])
     got = api.device_libm("exp", xs)
-    want = np.array([math.exp(v) if abs(v) < 709.7 else (np.exp(v)) for v in xs]) if False else np.exp(xs)
-    # numpy's exp may use SIMD kernels; use the C library through math/ctypes for the oracle value
+    # numpy's exp may use its own SIMD kernels; the expected values come from the C library itself
     import ctypes
     libm = ctypes.CDLL("libm.so.6")
     libm.exp.restype = ctypes.c_double
     libm.exp.argtypes = [ctypes.c_double]
     libm.pow.restype = ctypes.c_double
     libm.pow.argtypes = [ctypes.c_double, ctypes.c_double]
-    idx = rng.choice(xs.size, 60000, replace=False)
+    idx = np.concatenate([rng.choice(xs.size - 11, 60000, replace=False), np.arange(xs.size - 11, xs.size)])
     want = np.array([libm.exp(float(xs[i])) for i in idx])
-    assert np.array_equal(got[idx].view(np.uint64), want.view(np.uint64)) or \
-        np.array_equal(np.isnan(got[idx]), np.isnan(want)) and np.array_equal(
-            got[idx][~np.isnan(want)].view(np.uint64), want[~np.isnan(want)].view(np.uint64))
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(got[idx]), np.isnan(want))
+    assert np.array_equal(got[idx][ok].view(np.uint64), want[ok].view(np.uint64))
     bx = np.concatenate([np.full(n, 2.0), rng.uniform(1, 6, n), rng.uniform(1e-6, 6, n), rng.uniform(0, 1, n),
                          rng.uniform(0, 2, n // 4), -rng.uniform(0, 10, n // 4)])
     by = np.concatenate([rng.uniform(-300, 10, n), rng.uniform(-6, 6, n), rng.uniform(0.5, 4, n), rng.uniform(0, 4, n),
