@@ -361,6 +361,17 @@ int sipnet_gpu_abi_version(void);
  * returns achieved TFLOP/s (the FP64 roofline denominator; SURVEY 7 hard part 7). */
 int sipnet_gpu_measure_fp64_peak(int device, double *tflops);
 
+/*
+ * Row summaries on caller-owned DEVICE memory: rows[r * ld + j], r < nrows, j < ncols.  For every row:
+ * mean / population variance over the finite entries and the requested quantiles (numpy "linear" rule).
+ * Used for exact cross-GPU quantiles: after an all-to-all time-transpose each rank holds complete
+ * ensembles for its share of the steps and summarises them locally.  d_mean/d_var are [nrows],
+ * d_quant is [nq][nrows] (any of them may be NULL); `probs` is a host array; `stream` a cudaStream_t or NULL.
+ */
+int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t nrows, int64_t ncols, int64_t ld,
+                            const double *probs, int32_t nq, double *d_mean, double *d_var, double *d_quant,
+                            void *stream);
+
 /* Validation hook: evaluate the device exp (op 0: out = exp(x)) or pow (op 1: out = pow(x, y))
  * on host arrays of n doubles, so the device libm can be compared bit for bit with the
  * reference's host libm (glibc) -- see sipnet_b200/csrc/sip_libm.cuh. */

@@ -79,6 +79,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_abi_version.argtypes = []
     lib.sipnet_gpu_measure_fp64_peak.restype = C.c_int
     lib.sipnet_gpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.sipnet_gpu_rows_summary.restype = C.c_int
+    lib.sipnet_gpu_rows_summary.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sipnet_gpu_eval_libm.restype = C.c_int
     lib.sipnet_gpu_eval_libm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     if path is None:

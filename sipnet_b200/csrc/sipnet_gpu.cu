@@ -775,3 +775,35 @@ extern "C" int sipnet_gpu_eval_libm(int device, int op, const double *x, const d
   CUDA_OK(eval_libm(device, op, x, y, out, n));
   return 0;
 }
+
+extern "C" int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t nrows, int64_t ncols, int64_t ld,
+                                       const double *probs, int32_t nq, double *d_mean, double *d_var, double *d_quant,
+                                       void *stream) {
+  if (!d_rows || nrows <= 0 || ncols <= 0 || ld < ncols || nq < 0 || (nq > 0 && (!probs || !d_quant)))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "bad rows_summary arguments");
+  if ((d_mean == nullptr) != (d_var == nullptr)) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "mean and var go together");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", device);
+  CUDA_OK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // one pseudo-site covering all columns: the reducers take (rows = steps) x (members of a site)
+  SiteDev host{};
+  host.member0 = 0;
+  host.memberCount = (int32_t)ncols;
+  host.nsteps = nrows;
+  SiteDev *dsite = nullptr;
+  double *dprobs = nullptr;
+  CUDA_OK(cudaMalloc(&dsite, sizeof(SiteDev)));
+  CUDA_OK(cudaMemcpyAsync(dsite, &host, sizeof host, cudaMemcpyHostToDevice, st));
+  if (d_mean) CUDA_OK(launch_moments(d_rows, ld, nrows, 1, dsite, 1, d_mean, d_var, st));
+  if (nq > 0) {
+    CUDA_OK(cudaMalloc(&dprobs, (size_t)nq * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(dprobs, probs, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_OK(launch_quantiles(d_rows, ld, nrows, 1, dsite, 1, dprobs, nq, nullptr, d_quant, st));
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
+  cudaFree(dsite);
+  if (dprobs) cudaFree(dprobs);
+  return 0;
+}

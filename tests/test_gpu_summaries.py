@@ -1,0 +1,94 @@
+"""GPU: on-device ensemble summaries.  The reference has no ensemble code (parity
+unpinned for these outputs); they are defined in sip_reduce.cu and checked here against a
+trivially-written numpy computation over the oracle-validated per-step output."""
+import numpy as np
+import pytest
+
+from sipnet_b200 import _abi as A, api, synth
+
+pytestmark = pytest.mark.gpu
+
+COLS = [A.O["nee"], A.O["gpp"], A.O["soilWater"]]
+QS = [0.05, 0.25, 0.5, 0.95, 1.0]
+
+
+def test_loglik_matches_numpy(oracle):
+    site = synth.synth_site(0, 3, "half-daily", with_events=True)
+    P = synth.synth_params(70)
+    rc, done, o_out, _, _ = oracle.run(synth.SYNTH_FLAGS, P[:, 0], site, want_debug=False)
+    site.nee_obs = synth.synth_obs(o_out[:, A.O["nee"]].copy())
+    sigma = 0.5
+    for math in (A.MATH_FAST, A.MATH_VALIDATION):
+        ens = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL | A.OUT_LOGLIK, nee_sigma=sigma, math=math)
+        ens.run()
+        nee = ens.output()[A.O["nee"]]                       # [T][M]
+        ll, lln = ens.loglik(), ens.loglik_n()
+        ens.close()
+        mask = ~np.isnan(site.nee_obs)
+        assert np.all(lln == mask.sum())
+        d = (nee[mask, :] - site.nee_obs[mask, None]) / sigma
+        want = (-0.5 * d * d - np.log(sigma) - 0.5 * np.log(2 * np.pi)).sum(axis=0)
+        np.testing.assert_allclose(ll, want, rtol=1e-12)
+    # segmented runs accumulate the same likelihood (same order of additions => same bits)
+    ens = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_LOGLIK, nee_sigma=sigma)
+    for t0 in range(0, site.nsteps, 700):
+        ens.run(t0, min(site.nsteps, t0 + 700))
+    assert np.array_equal(ens.loglik(), ll)
+    ens.close()
+
+
+def test_moments_and_quantiles_match_numpy():
+    sites, P, ms, flags = synth.config_c3(nsites=3, members_per_site=37, nyears=2)
+    P[A.P["leafAllocation"], 5] = 0.9                         # one failed member (bad allocation): excluded
+    ens = api.Ensemble(sites, P, ms, flags, outputs=A.OUT_FULL | A.OUT_MOMENTS | A.OUT_QUANTILES, summary_cols=COLS,
+                       quantiles=QS)
+    ens.run()
+    out = ens.output()
+    mean, var, q = ens.mean(), ens.variance(), ens.quantiles()
+    ens.close()
+    assert np.isnan(out[:, :, 5]).all()
+    for s in range(3):
+        sel = ms == s
+        for i, c in enumerate(COLS):
+            x = out[c][:, sel]                                # [T][members of site]
+            with np.errstate(invalid="ignore"):
+                np.testing.assert_allclose(mean[s, i], np.nanmean(x, axis=1), rtol=1e-12, atol=1e-300)
+                np.testing.assert_allclose(var[s, i], np.nanvar(x, axis=1), rtol=1e-9, atol=1e-300)
+                assert np.array_equal(q[s, i], np.nanquantile(x, QS, axis=1))   # order statistics: exact
+
+
+def test_summary_only_mode_matches_full_mode():
+    """Without OUT_FULL only the summary columns are kept on the device; same numbers."""
+    site = synth.synth_site(2, 2, "unequal", with_events=True)
+    P = synth.synth_params(300, stream=2)
+    kw = dict(summary_cols=COLS, quantiles=QS)
+    a = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL | A.OUT_MOMENTS | A.OUT_QUANTILES, **kw)
+    b = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_MOMENTS | A.OUT_QUANTILES, **kw)
+    a.run(); b.run()
+    assert np.array_equal(a.mean(), b.mean(), equal_nan=True)
+    assert np.array_equal(a.variance(), b.variance(), equal_nan=True)
+    assert np.array_equal(a.quantiles(), b.quantiles(), equal_nan=True)
+    a.close(); b.close()
+
+
+def test_rows_summary_and_zero_copy_view():
+    import torch
+    from sipnet_b200 import distributed as D
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(300, 4097))
+    x[7, 11] = np.nan
+    x[:, 100:110] = 1.25                                       # ties
+    t = torch.from_numpy(x).cuda()
+    mean, var, q = D.rows_summary(t, QS)
+    np.testing.assert_allclose(mean.cpu().numpy(), np.nanmean(x, axis=1), rtol=1e-12)
+    np.testing.assert_allclose(var.cpu().numpy(), np.nanvar(x, axis=1), rtol=1e-10)
+    assert np.array_equal(q.cpu().numpy(), np.nanquantile(x, QS, axis=1))
+    # zero-copy torch view of the library's device output
+    site = synth.synth_site(0, 1, "half-daily")
+    P = synth.synth_params(48)
+    ens = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL)
+    ens.run()
+    ens.sync()
+    view = D.DeviceArray(ens.device_ptr(A.GATHER_FULL), (A.NOUT, site.nsteps, 48)).tensor()
+    assert np.array_equal(view.cpu().numpy(), ens.output(), equal_nan=True)
+    ens.close()
