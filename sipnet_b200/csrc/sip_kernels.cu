@@ -267,7 +267,19 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
     }
     load_member(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
     if (REPLAY) mb.status |= SIPNET_GPU_ST_REPLAY;
-    if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) active = false;  // reference would have exited (sipnet.c:1117-1122)
+    if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) {  // reference would have exited (sipnet.c:1117-1122)
+      active = false;
+      // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
+      const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+      const int64_t n = (a.stepEnd < site.nsteps ? a.stepEnd : site.nsteps) - a.stepBegin;
+      if (a.out != nullptr)
+        for (int c = 0; c < SIPNET_GPU_NOUT; ++c)
+          if (a.colSlot[c] >= 0)
+            for (int64_t t = 0; t < n; ++t) a.out[((int64_t)a.colSlot[c] * a.outSteps + t) * a.ld + m] = nanv;
+      if (a.dbg != nullptr)
+        for (int k = 0; k < SIPNET_GPU_NDEBUG; ++k)
+          for (int64_t t = 0; t < n; ++t) a.dbg[((int64_t)k * a.outSteps + t) * a.ld + m] = nanv;
+    }
   }
   NM nm;
   if constexpr (NM::kFast) {
@@ -287,6 +299,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
   }
   Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
                      site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld};
+  if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
+    emit.ll = a.loglik[m];
+    emit.lln = a.loglikN[m];
+  }
 
   for (int64_t chunk = 0; chunk < nChunks; ++chunk) {
     if (tid == 0 && chunk + 1 < nChunks) issue(chunk + 1);  // buffer (chunk+1)&1 was released by the barrier below
@@ -308,9 +324,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
   if (active) {
     if (NM::kFast && nm.bad) mb.status |= SIPNET_GPU_ST_REPLAY;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
-    if (a.loglik != nullptr && site.neeObs != nullptr) {
-      a.loglik[m] += emit.ll;
-      a.loglikN[m] += emit.lln;
+    if (a.loglik != nullptr && site.neeObs != nullptr) {  // running sums continue across segments in step order
+      a.loglik[m] = emit.ll;
+      a.loglikN[m] = emit.lln;
     }
   }
 }

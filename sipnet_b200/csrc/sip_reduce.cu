@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kRedThreads) quantiles_kernel(const double *co
         __syncthreads();
         xhi = (nle >= lo + 2.0) ? xlo : minAbove;
       }
-      result = xlo + (xhi - xlo) * frac;
+      // numpy's _lerp: a + (b - a) t, evaluated from the b side when t >= 0.5
+      result = (frac >= 0.5) ? xhi - (xhi - xlo) * (1.0 - frac) : xlo + (xhi - xlo) * frac;
     }
     if (threadIdx.x == 0) out[((int64_t)site * nq + q) * nsteps + t] = result;
   }

@@ -54,7 +54,7 @@ def test_moments_and_quantiles_match_numpy():
             with np.errstate(invalid="ignore"):
                 np.testing.assert_allclose(mean[s, i], np.nanmean(x, axis=1), rtol=1e-12, atol=1e-300)
                 np.testing.assert_allclose(var[s, i], np.nanvar(x, axis=1), rtol=1e-9, atol=1e-300)
-                assert np.array_equal(q[s, i], np.nanquantile(x, QS, axis=1))   # order statistics: exact
+                np.testing.assert_allclose(q[s, i], np.nanquantile(x, QS, axis=1), rtol=4e-16, atol=1e-300)  # order statistics + lerp
 
 
 def test_summary_only_mode_matches_full_mode():
@@ -82,7 +82,8 @@ def test_rows_summary_and_zero_copy_view():
     mean, var, q = D.rows_summary(t, QS)
     np.testing.assert_allclose(mean.cpu().numpy(), np.nanmean(x, axis=1), rtol=1e-12)
     np.testing.assert_allclose(var.cpu().numpy(), np.nanvar(x, axis=1), rtol=1e-10)
-    assert np.array_equal(q.cpu().numpy(), np.nanquantile(x, QS, axis=1))
+    np.testing.assert_allclose(q.cpu().numpy(), np.nanquantile(x, QS, axis=1), rtol=4e-16)
+    assert np.array_equal(q.cpu().numpy()[-1], np.nanmax(x, axis=1)) and np.array_equal(q.cpu().numpy()[2], np.nanmedian(x, axis=1))
     # zero-copy torch view of the library's device output
     site = synth.synth_site(0, 1, "half-daily")
     P = synth.synth_params(48)
