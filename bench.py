@@ -308,9 +308,8 @@ def run_ours(args):
         C.memmove(hpar, params.ctypes.data, par_bytes)
 
         def e2e_step():
-            ens.set_params(hpar, M)
-            ens.run(0, T)
-            ens.gather_raw(A.GATHER_FULL, hout, out_bytes)
+            ens.set_params(hpar, M)                               # H2D of the ensemble + setupModel()
+            ens.run_to_host(hout, 0, T, nbytes=out_bytes)         # run, D2H pipelined behind the next segment
 
         e2e_step()
         barrier()

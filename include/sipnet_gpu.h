@@ -318,6 +318,18 @@ int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end);
  */
 int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size_t bytes);
 
+/*
+ * sipnet_gpu_run_to_host -- run steps [step_begin, step_end) and deliver the FULL per-step output
+ * straight into a host buffer laid out double [NOUT][step_end - step_begin][M], pipelined: the range is
+ * integrated in segments of `chunk_steps` (0 => library default) that alternate between the two halves
+ * of the device output buffer while a copy stream drains the previous segment (use pinned memory,
+ * sipnet_gpu_host_alloc, for the copies to overlap).  Equivalent to run() + gather(FULL) and bit-identical
+ * to it; this is the reference loop's `updateState(); outputState();` pair with the device->host copy
+ * hidden behind the next segment's arithmetic.  Returns when the data is in `dst`.
+ */
+int sipnet_gpu_run_to_host(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end, double *dst, size_t bytes,
+                           int64_t chunk_steps);
+
 /* Size in bytes gather(what) will write for the last run range. */
 size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what);
 

@@ -49,6 +49,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     lib.sipnet_gpu_gather.restype = C.c_int
     lib.sipnet_gpu_gather.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.sipnet_gpu_run_to_host.restype = C.c_int
+    lib.sipnet_gpu_run_to_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_int64]
     lib.sipnet_gpu_gather_bytes.restype = C.c_size_t
     lib.sipnet_gpu_gather_bytes.argtypes = [C.c_void_p, C.c_int]
     lib.sipnet_gpu_sync.restype = C.c_int
@@ -246,6 +248,21 @@ class Ensemble:
         if rc != 0:
             raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
         self.last_range = (step_begin, step_end)
+
+    def run_to_host(self, dst, step_begin: int = 0, step_end: Optional[int] = None, chunk_steps: int = 0,
+                    nbytes: Optional[int] = None) -> None:
+        """Pipelined run + delivery of the full output into a host buffer [32][n][M]
+        (numpy array, or a raw pointer with `nbytes`, ideally pinned)."""
+        if step_end is None:
+            step_end = self.max_steps
+        if isinstance(dst, np.ndarray):
+            ptr, nbytes = dst.ctypes.data, dst.nbytes
+        else:
+            ptr = int(dst)
+        rc = self.lib.sipnet_gpu_run_to_host(self.handle, step_begin, step_end, C.c_void_p(ptr), nbytes, chunk_steps)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (step_end, step_end)
 
     def _gather(self, what: int, dtype, shape) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)

@@ -85,6 +85,8 @@ struct sipnet_gpu_handle {
   cudaStream_t stream = nullptr;
   bool ownStream = false;
   cudaEvent_t evStart = nullptr, evStop = nullptr, evT0 = nullptr, evT1 = nullptr;
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evRunDone[2] = {nullptr, nullptr}, evCopyDone[2] = {nullptr, nullptr};
   int64_t launches = 0;
 
   // device memory
@@ -214,6 +216,11 @@ static void free_handle(sipnet_gpu_handle *h) {
   if (h->evStop) cudaEventDestroy(h->evStop);
   if (h->evT0) cudaEventDestroy(h->evT0);
   if (h->evT1) cudaEventDestroy(h->evT1);
+  for (int i = 0; i < 2; ++i) {
+    if (h->evRunDone[i]) cudaEventDestroy(h->evRunDone[i]);
+    if (h->evCopyDone[i]) cudaEventDestroy(h->evCopyDone[i]);
+  }
+  if (h->copyStream) cudaStreamDestroy(h->copyStream);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -524,7 +531,8 @@ extern "C" int sipnet_gpu_reset(sipnet_gpu_handle *h) {
   return run_init_state(h);
 }
 
-extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end) {
+// one contiguous segment; `outbuf` = where the column outputs of this segment go (h->out or one of its halves)
+static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end, double *outbuf, int64_t outCapSteps) {
   if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
   if (step_begin != h->stepsDone)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "step_begin %lld is not the next step (%lld): segments must be contiguous",
@@ -533,9 +541,9 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "bad step range [%lld, %lld) for %lld steps", (long long)step_begin,
                 (long long)step_end, (long long)h->maxSteps);
   const bool keeps = (h->out != nullptr) || (h->dbg != nullptr);
-  if (keeps && step_end - step_begin > h->outCap)
+  if (keeps && step_end - step_begin > outCapSteps)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "run range of %lld steps exceeds out_steps_capacity %lld",
-                (long long)(step_end - step_begin), (long long)h->outCap);
+                (long long)(step_end - step_begin), (long long)outCapSteps);
   CUDA_OK(cudaSetDevice(h->device));
   h->lastBegin = step_begin;
   h->lastEnd = step_end;
@@ -555,7 +563,7 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
   a.sites = h->sites;
   a.stepBegin = step_begin;
   a.stepEnd = step_end;
-  a.out = h->out;
+  a.out = outbuf;
   a.outSteps = step_end - step_begin;
   a.dbg = h->dbg;
   a.loglik = h->loglik;
@@ -575,7 +583,7 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
   memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);
 
   if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
-    if (h->out) CUDA_OK(cudaMemsetAsync(h->out, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
+    if (outbuf) CUDA_OK(cudaMemsetAsync(outbuf, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
     if (h->dbg)
       CUDA_OK(cudaMemsetAsync(h->dbg, 0xFF, (size_t)SIPNET_GPU_NDEBUG * a.outSteps * h->ld * sizeof(double), h->stream));
   }
@@ -612,6 +620,62 @@ extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t 
     if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "replay launch failed: %s", cudaGetErrorString(e));
   }
   h->stepsDone = step_end;
+  return SIPNET_GPU_OK;
+}
+
+extern "C" int sipnet_gpu_run(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end) {
+  if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
+  return run_segment(h, step_begin, step_end, h->out, h->outCap);
+}
+
+extern "C" int sipnet_gpu_run_to_host(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_end, double *dst,
+                                      size_t bytes, int64_t chunk_steps) {
+  if (!h || !dst) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle or destination");
+  if (!(h->outputs & SIPNET_GPU_OUT_FULL)) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "run_to_host needs SIPNET_GPU_OUT_FULL");
+  if (h->dbg) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "run_to_host is not available with the debug dump");
+  const int64_t total = step_end - step_begin;
+  if (total <= 0) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "empty step range");
+  const size_t M = (size_t)h->nmembers;
+  if (bytes != (size_t)SIPNET_GPU_NOUT * (size_t)total * M * sizeof(double))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "run_to_host: buffer is %zu bytes, expected %zu", bytes,
+                (size_t)SIPNET_GPU_NOUT * (size_t)total * M * sizeof(double));
+  const int64_t half = h->outCap / 2;
+  if (half < 1) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "out_steps_capacity must be at least 2 for run_to_host");
+  int64_t tc = chunk_steps > 0 ? chunk_steps : 512;
+  if (tc > half) tc = half;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!h->copyStream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(cudaEventCreateWithFlags(&h->evRunDone[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&h->evCopyDone[i], cudaEventDisableTiming));
+    }
+  }
+  double *bufs[2] = {h->out, h->out + (size_t)h->ncols * (size_t)half * (size_t)h->ld};
+  int64_t k = 0;
+  for (int64_t t0 = step_begin; t0 < step_end; t0 += tc, ++k) {
+    const int64_t t1 = t0 + tc < step_end ? t0 + tc : step_end;
+    const int64_t n = t1 - t0;
+    const int b = (int)(k & 1);
+    if (k >= 2) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evCopyDone[b], 0));  // this half has been drained
+    int rc = run_segment(h, t0, t1, bufs[b], half);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(h->evRunDone[b], h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->copyStream, h->evRunDone[b], 0));
+    for (int c = 0; c < SIPNET_GPU_NOUT; ++c) {
+      double *d = dst + ((size_t)c * (size_t)total + (size_t)(t0 - step_begin)) * M;
+      const double *src = bufs[b] + (size_t)c * (size_t)n * (size_t)h->ld;
+      CUDA_OK(cudaMemcpy2DAsync(d, M * sizeof(double), src, (size_t)h->ld * sizeof(double), M * sizeof(double), (size_t)n,
+                                cudaMemcpyDeviceToHost, h->copyStream));
+    }
+    CUDA_OK(cudaEventRecord(h->evCopyDone[b], h->copyStream));
+  }
+  // join: later work on the handle's stream (and the stopwatch) sees the copies as done
+  CUDA_OK(cudaStreamWaitEvent(h->stream, h->evCopyDone[(k - 1) & 1], 0));
+  if (k >= 2) CUDA_OK(cudaStreamWaitEvent(h->stream, h->evCopyDone[k & 1], 0));
+  CUDA_OK(cudaStreamSynchronize(h->copyStream));
+  h->lastBegin = step_end;  // the device buffer no longer holds one contiguous range: gather(FULL) is not valid
+  h->lastEnd = step_end;
   return SIPNET_GPU_OK;
 }
 

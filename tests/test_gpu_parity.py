@@ -262,3 +262,24 @@ def test_zz_validation_build_is_bit_identical():
     assert BITEXACT["checked"] > 0
     print(f"bit-identical members: {BITEXACT['exact']} of {BITEXACT['checked']}")
     assert BITEXACT["exact"] == BITEXACT["checked"]
+
+
+def test_run_to_host_pipeline_equals_run_plus_gather():
+    """sipnet_gpu_run_to_host (chunked, double-buffered, copy stream) delivers the same bytes."""
+    sites, P, ms, flags = synth.config_c3(nsites=2, members_per_site=50, nyears=3)
+    ref = run_gpu(sites, P, ms, flags, outputs=A.OUT_FULL, math=A.MATH_FAST)
+    ens = api.Ensemble(sites, P, ms, flags, outputs=A.OUT_FULL, math=A.MATH_FAST)
+    T = ens.max_steps
+    for chunk in (0, 100, 777):
+        ens.reset()
+        dst = np.full((A.NOUT, T, P.shape[1]), -1.0)
+        ens.run_to_host(dst, 0, T, chunk_steps=chunk)
+        assert np.array_equal(dst, ref["out"], equal_nan=True), chunk
+    # a sub-range after a plain run
+    ens.reset()
+    ens.run(0, 1000)
+    dst = np.empty((A.NOUT, T - 1000, P.shape[1]))
+    ens.run_to_host(dst, 1000, T, chunk_steps=300)
+    assert np.array_equal(dst, ref["out"][:, 1000:], equal_nan=True)
+    assert np.array_equal(ens.state(), ref["state"], equal_nan=True)
+    ens.close()
