@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--years", type=int, default=10)
     ap.add_argument("--math", default="fast", choices=["fast", "validation"])
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = the bench workload (default); c3/c4/c5 = the other BASELINE.json configs (extra lines)")
+    ap.add_argument("--sites", type=int, default=0, help="c3: number of sites on this GPU (default 10000 / n_gpus)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -372,10 +375,116 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_other_config(args):
+    """BASELINE.json configs[2..4] (C3, C4, C5) on N GPUs: members sharded, no data-path collective,
+    NCCL only for the final gather.  One JSON line; not the headline bench workload."""
+    import torch
+    import torch.distributed as dist
+
+    from sipnet_b200 import _abi as A, api, distributed as D, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_build = time.perf_counter()
+    if args.workload == "c3":      # 10k sites x 100 members, events; per-site ensemble mean/variance of NEE
+        nsites_total = 10000
+        nsites = args.sites or nsites_total // world
+        sites, params, ms, flags = synth.config_c3(nsites=nsites, members_per_site=100, nyears=args.years,
+                                                   site0=rank * nsites)
+        kw = dict(outputs=A.OUT_MOMENTS, summary_cols=[A.O["nee"]], out_steps_capacity=256)
+        name = f"C3: {nsites * world} sites x 100 members, {args.years} yr half-daily, events.in schedule, per-site NEE mean/variance"
+    elif args.workload == "c4":    # 1M members, 1 site, ensemble mean + quantiles of NEE and GPP
+        total = args.members if args.members != 4096 else 1 << 20
+        M = total // world
+        sites = [synth.synth_site(0, args.years, "half-daily")]
+        params = synth.synth_params(M, stream=100 + rank)
+        ms, flags = np.zeros(M, np.int32), dict(synth.SYNTH_FLAGS)
+        kw = dict(outputs=A.OUT_MOMENTS, summary_cols=[A.O["nee"], A.O["gpp"]], out_steps_capacity=512)
+        name = f"C4: {total} members x {args.years} yr on {world} GPU(s), on-device mean/variance + exact quantiles (NEE, GPP)"
+    else:                          # c5: 256k draws scored by NEE log-likelihood
+        total = args.members if args.members != 4096 else 1 << 18
+        M = total // world
+        sites = [synth.synth_site(0, args.years, "half-daily")]
+        rngobs = np.random.default_rng(7)
+        sites[0].nee_obs = np.where(rngobs.uniform(size=sites[0].nsteps) < 0.2, np.nan, rngobs.normal(0, 1.5, sites[0].nsteps))
+        params = synth.synth_params(M, stream=200 + rank)
+        ms, flags = np.zeros(M, np.int32), dict(synth.SYNTH_FLAGS)
+        kw = dict(outputs=A.OUT_LOGLIK, nee_sigma=0.5)
+        name = f"C5: {total} parameter draws x {args.years} yr, on-device NEE log-likelihood, NCCL all_gather"
+    t_build = time.perf_counter() - t_build
+    ens = api.Ensemble(sites, params, ms, flags, math=A.MATH_FAST, device=local, **kw)
+    T = ens.max_steps
+    M_local = params.shape[1]
+    cap = kw.get("out_steps_capacity", T)
+    qs = [0.05, 0.5, 0.95]
+
+    def one_pass():
+        ens.reset()
+        extra = 0.0
+        if args.workload == "c5":
+            ens.run(0, T)
+            ll = D.DeviceArray(ens.device_ptr(A.GATHER_LOGLIK), (M_local,)).tensor(local)
+            if world > 1:
+                D.all_gather_members(ll, [M_local] * world)
+            return
+        for t0 in range(0, T, cap):
+            t1 = min(T, t0 + cap)
+            ens.run(t0, t1)
+            n = t1 - t0
+            mean, var = ens.mean(), ens.variance()              # local shard's per-step moments
+            if args.workload == "c4":
+                if world > 1:
+                    cnt = np.full_like(mean[0], float(M_local))
+                    D.all_gather_moments(torch.from_numpy(cnt).cuda(), torch.from_numpy(mean[0]).cuda(),
+                                         torch.from_numpy(var[0]).cuda())
+                ld = (M_local + 15) // 16 * 16
+                colbuf = D.DeviceArray(ens.device_ptr(A.GATHER_FULL), (2, n, M_local), (n * ld, ld, 1)).tensor(local)
+                for i in range(2):
+                    rows = colbuf[i]
+                    if world > 1:
+                        rows, _, _ = D.time_transpose(rows, [M_local] * world)
+                    D.rows_summary(rows, qs)
+
+    one_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_pass()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.steps
+    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    status = ens.status()
+    ens.close()
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "workload": name, "value": world * M_local * T / float(tmax.item()),
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "s_per_pass": float(tmax.item()),
+                          "members_per_gpu": M_local, "model_steps": T, "input_build_s": t_build,
+                          "replayed_members": int((status & A.ST_REPLAY).astype(bool).sum()),
+                          "timing": "wall clock around barrier+synchronize (includes summaries and the NCCL gather)",
+                          "dtype": "f64", "data": "synthetic"}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "c2":
+        run_other_config(args)
     else:
         run_ours(args)
 
