@@ -36,8 +36,10 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
 }
 
 // grid = (nsteps, nsites); block = kRedThreads
+// output element (site, t) at [site * siteStride + t]
 __global__ void __launch_bounds__(kRedThreads) moments_kernel(const double *cols, int64_t ld, int64_t nsteps,
-                                                              const SiteDev *sites, double *mean, double *var) {
+                                                              const SiteDev *sites, double *mean, double *var,
+                                                              int64_t siteStride) {
   __shared__ double sh[kRedThreads];
   const int64_t t = blockIdx.x;
   const int site = blockIdx.y;
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(kRedThreads) moments_kernel(const double *cols
   }
   const double ss = block_sum(q, sh);
   if (threadIdx.x == 0) {
-    mean[(int64_t)site * nsteps + t] = mu;
-    var[(int64_t)site * nsteps + t] = n > 0 ? ss / n : nan("");
+    mean[(int64_t)site * siteStride + t] = mu;
+    var[(int64_t)site * siteStride + t] = n > 0 ? ss / n : nan("");
   }
 }
 
@@ -109,10 +111,10 @@ __device__ uint64_t radix_select(const double *row, int count, unsigned long lon
   return prefix;
 }
 
-// grid = (nsteps, nsites); block = kRedThreads.  out[(site * nq + q) * nsteps + t]
+// grid = (nsteps, nsites); block = kRedThreads.  out[site * siteStride + q * nsteps + t]
 __global__ void __launch_bounds__(kRedThreads) quantiles_kernel(const double *cols, int64_t ld, int64_t nsteps,
                                                                 const SiteDev *sites, const double *probs, int nq,
-                                                                double *out) {
+                                                                double *out, int64_t siteStride) {
   __shared__ unsigned int hist[256];
   __shared__ double sh[kRedThreads];
   const int64_t t = blockIdx.x;
@@ -155,32 +157,32 @@ __global__ void __launch_bounds__(kRedThreads) quantiles_kernel(const double *co
       // numpy's _lerp: a + (b - a) t, evaluated from the b side when t >= 0.5
       result = (frac >= 0.5) ? xhi - (xhi - xlo) * (1.0 - frac) : xlo + (xhi - xlo) * frac;
     }
-    if (threadIdx.x == 0) out[((int64_t)site * nq + q) * nsteps + t] = result;
+    if (threadIdx.x == 0) out[(int64_t)site * siteStride + (int64_t)q * nsteps + t] = result;
   }
 }
 
-cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int /*ncols*/, const SiteDev *sites,
+cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
                            int64_t nsites, double *mean, double *var, cudaStream_t stream) {
   // gridDim.y is limited to 65535: tile sites
   for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
     const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
     dim3 grid((unsigned)nsteps, (unsigned)ns);
-    moments_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, mean + s0 * nsteps,
-                                                     var + s0 * nsteps);
+    moments_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, mean + s0 * siteStride,
+                                                     var + s0 * siteStride, siteStride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
 
-cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int /*ncols*/, const SiteDev *sites,
+cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
                              int64_t nsites, const double *probs, int nq, double * /*scratch*/, double *out,
                              cudaStream_t stream) {
   for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
     const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
     dim3 grid((unsigned)nsteps, (unsigned)ns);
     quantiles_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, probs, nq,
-                                                       out + s0 * nq * nsteps);
+                                                       out + s0 * siteStride, siteStride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -35,9 +35,9 @@ cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers
                               uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
                               cudaStream_t stream);
 }  // namespace k1
-cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
+cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
                            int64_t nsites, double *mean, double *var, cudaStream_t stream);
-cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int ncols, const SiteDev *sites,
+cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
                              int64_t nsites, const double *probs, int nq, double *scratch, double *out,
                              cudaStream_t stream);
 cudaError_t measure_fp64_peak(int device, double *tflops);
@@ -683,21 +683,22 @@ static int ensure_summaries(sipnet_gpu_handle *h) {
   if (h->summariesValid) return 0;
   const int64_t n = h->lastEnd - h->lastBegin;
   if (n <= 0) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no run range to summarise");
-  // summary columns occupy `out` slots; with OUT_FULL the slot of column c is c itself
+  // summary columns occupy `out` slots; with OUT_FULL the slot of column c is c itself.
+  // Device layout = the ABI's: mean/var [site][col][n], quantiles [site][col][q][n].
   const int ns = (int)h->summaryCols.size();
+  const int64_t nq = (int64_t)h->quantiles.size();
   for (int i = 0; i < ns; ++i) {
     const int slot = h->colSlot[h->summaryCols[(size_t)i]];
     const double *cols = h->out + (size_t)slot * n * h->ld;
     if (h->mean) {
-      cudaError_t e = launch_moments(cols, h->ld, n, 1, h->sites, h->nsites, h->mean + (size_t)i * h->nsites * n,
-                                     h->var + (size_t)i * h->nsites * n, h->stream);
+      cudaError_t e = launch_moments(cols, h->ld, n, (int64_t)ns * n, h->sites, h->nsites, h->mean + (size_t)i * n,
+                                     h->var + (size_t)i * n, h->stream);
       h->launches++;
       if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "moments launch failed: %s", cudaGetErrorString(e));
     }
     if (h->quant) {
-      cudaError_t e = launch_quantiles(cols, h->ld, n, 1, h->sites, h->nsites, h->qprobs, (int)h->quantiles.size(),
-                                       h->qscratch, h->quant + (size_t)i * h->nsites * h->quantiles.size() * n,
-                                       h->stream);
+      cudaError_t e = launch_quantiles(cols, h->ld, n, (int64_t)ns * nq * n, h->sites, h->nsites, h->qprobs, (int)nq,
+                                       h->qscratch, h->quant + (size_t)i * nq * n, h->stream);
       h->launches++;
       if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "quantile launch failed: %s", cudaGetErrorString(e));
     }
@@ -760,14 +761,8 @@ extern "C" int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size
     case SIPNET_GPU_GATHER_QUANTILES: {
       int rc = ensure_summaries(h);
       if (rc) return rc;
-      // device layout is [col][site][...][n]; the ABI promises [site][col][...][n]
-      const size_t ns = h->summaryCols.size();
-      const size_t inner = (what == SIPNET_GPU_GATHER_QUANTILES ? h->quantiles.size() : 1) * n;
       const double *src = what == SIPNET_GPU_GATHER_MEAN ? h->mean : what == SIPNET_GPU_GATHER_VARIANCE ? h->var : h->quant;
-      for (size_t c = 0; c < ns; ++c)
-        for (size_t s = 0; s < (size_t)h->nsites; ++s)
-          CUDA_OK(cudaMemcpyAsync((double *)dst + (s * ns + c) * inner, src + (c * (size_t)h->nsites + s) * inner,
-                                  inner * 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, h->stream));
       CUDA_OK(cudaStreamSynchronize(h->stream));
       return 0;
     }
@@ -860,11 +855,11 @@ extern "C" int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t
   double *dprobs = nullptr;
   CUDA_OK(cudaMalloc(&dsite, sizeof(SiteDev)));
   CUDA_OK(cudaMemcpyAsync(dsite, &host, sizeof host, cudaMemcpyHostToDevice, st));
-  if (d_mean) CUDA_OK(launch_moments(d_rows, ld, nrows, 1, dsite, 1, d_mean, d_var, st));
+  if (d_mean) CUDA_OK(launch_moments(d_rows, ld, nrows, nrows, dsite, 1, d_mean, d_var, st));
   if (nq > 0) {
     CUDA_OK(cudaMalloc(&dprobs, (size_t)nq * sizeof(double)));
     CUDA_OK(cudaMemcpyAsync(dprobs, probs, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_OK(launch_quantiles(d_rows, ld, nrows, 1, dsite, 1, dprobs, nq, nullptr, d_quant, st));
+    CUDA_OK(launch_quantiles(d_rows, ld, nrows, (int64_t)nq * nrows, dsite, 1, dprobs, nq, nullptr, d_quant, st));
   }
   CUDA_OK(cudaStreamSynchronize(st));
   cudaFree(dsite);
