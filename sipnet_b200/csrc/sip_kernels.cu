@@ -208,8 +208,8 @@ template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
     run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNParamDev][BLOCK]
-  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNParamDev * BLOCK);  // [2][kChunkSteps]
+  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNTileRows][BLOCK]
+  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNTileRows * BLOCK);  // [2][kChunkSteps]
   uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
   uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
 
@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // parameter tile: coalesced global reads, column-per-thread shared layout
-  for (int k = 0; k < kNParamDev; ++k) tile[k * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+  for (int k = 0; k < kNParamDev; ++k) {
+    const int slot = tile_slot(k);
+    if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+  }
   if (NM::kFast) {  // libm tables -> shared memory (table lookups become LDS)
     for (int i = tid; i < 2 * 128; i += BLOCK) libmTab[i] = libm::d_exp_tab[i];
     for (int i = tid; i < 4 * 128; i += BLOCK) libmTab[2 * 128 + i] = libm::d_powlog_tab[i];
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
     nm.powlogTab = libmTab + 2 * 128;
     // the member-constant division seeds must be ordinary numbers (divisor non-zero, normal, finite)
     for (int k = kSeedLeafCSpWt; k <= kSeedCSat; ++k)
-      if (k != kSeedCSat || fl.on(F_CSAT)) nm.seed_check(tile[k * BLOCK + tid]);
+      if (k != kSeedCSat || fl.on(F_CSAT)) nm.seed_check(tile[tile_slot(k) * BLOCK + tid]);
   }
   const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
   const ParamTile prm{tile + tid, BLOCK};
@@ -464,7 +467,7 @@ constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_N
 
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * kNParamDev * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
+  const size_t smem = sizeof(double) * kNTileRows * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
                       kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
   auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

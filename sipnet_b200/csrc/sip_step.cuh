@@ -46,7 +46,8 @@ struct RuntimeFlags {
 struct ParamTile {
   const double *base;  // already offset by threadIdx.x
   int stride;
-  __device__ __forceinline__ double operator()(int k) const { return base[k * stride]; }
+  // k is always a compile-time constant at the call sites, so tile_slot(k) folds to a constant
+  __device__ __forceinline__ double operator()(int k) const { return base[tile_slot(k) * stride]; }
 };
 #define SIP_P(name) prm(SIPNET_P_##name)
 

@@ -51,6 +51,29 @@ constexpr int kTwoWhc = SIPNET_GPU_NPARAMS + 24;       // 2.0 * soilWHC, sipnet.
 constexpr int kOneMinusFracLitResp = SIPNET_GPU_NPARAMS + 25;  // 1.0 - fracLitterRespired, sipnet.c:1165
 constexpr int kNParamDev = SIPNET_GPU_NPARAMS + 26;
 
+// Rows the time loop never reads (initial conditions and factors already folded into derived rows):
+// they stay in HBM only.  The shared-memory tile holds the remaining kNTileRows rows, which is what lets
+// two 128-member blocks share an SM (2 x (90 x 128 x 8 B + 15 KB) < 227 KB).
+// tests/test_abi.py::test_tile_skips_only_unused_rows keeps this list honest.
+#define SIP_TILE_SKIP_LIST                                                                                         \
+  SIPNET_P_plantWoodInit, SIPNET_P_laiInit, SIPNET_P_soilInit, SIPNET_P_soilWFracInit, SIPNET_P_aMax,                \
+      SIPNET_P_aMaxFrac, SIPNET_P_baseFolRespFrac, SIPNET_P_cFracLeaf, SIPNET_P_litterInit, SIPNET_P_snowInit,       \
+      SIPNET_P_fineRootFrac, SIPNET_P_coarseRootFrac, SIPNET_P_minNInit, SIPNET_P_soilOrgNInit,                      \
+      SIPNET_P_litterOrgNInit, SIPNET_P_plantStorageNInit
+constexpr int kTileSkip[] = {SIP_TILE_SKIP_LIST};
+constexpr int kNTileSkip = (int)(sizeof(kTileSkip) / sizeof(kTileSkip[0]));
+constexpr int kNTileRows = kNParamDev - kNTileSkip;
+// device row k -> tile row, or -1 when the row is not staged (the list is ascending)
+__host__ __device__ constexpr int tile_slot(int k) {
+  constexpr int skip[] = {SIP_TILE_SKIP_LIST};
+  int below = 0;
+  for (int i = 0; i < kNTileSkip; ++i) {
+    if (skip[i] == k) return -1;
+    if (skip[i] < k) ++below;
+  }
+  return k - below;
+}
+
 // flag bits (runtime mask / compile-time specialisation)
 enum : uint32_t {
   F_EVENTS = 1u << 0,

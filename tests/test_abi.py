@@ -85,3 +85,17 @@ def test_product_does_not_import_oracle():
                 assert "pyoracle" not in txt and "sipnet_oracle" not in txt and "oracle/" not in txt, (dirpath, f)
     out = subprocess.run(["nm", "-D", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "sipnet_oracle" not in out and "sipref_" not in out
+
+
+def test_tile_skips_only_unused_rows():
+    """The parameter rows left out of the shared-memory tile (sip_types.cuh kTileSkip) are never read by
+    the step, and the list is ascending (tile_slot() relies on it)."""
+    types = open(os.path.join(ROOT, "sipnet_b200", "csrc", "sip_types.cuh")).read()
+    step = open(os.path.join(ROOT, "sipnet_b200", "csrc", "sip_step.cuh")).read()
+    body = re.search(r"#define SIP_TILE_SKIP_LIST(.*?)\nconstexpr", types, re.S).group(1)
+    names = re.findall(r"SIPNET_P_(\w+)", body)
+    assert len(names) >= 10
+    idx = [A.P[n] for n in names]
+    assert idx == sorted(idx)
+    for n in names:
+        assert f"SIP_P({n})" not in step and f"SIPNET_P_{n}" not in step, n
