@@ -339,16 +339,23 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if M == 4096 and T == 7306:
+                traffic = tj["traffic_bytes_per_launch"]      # from one ncu --set full capture of this workload
+        except Exception:
+            pass
         steps_per_s_kernel = M * T / (kern_ms * 1e-3)
         fp64_ach = steps_per_s_kernel * FLOP_PER_MEMBER_STEP / 1e12
         hbm_ach = steps_per_s_kernel * BYTES_PER_MEMBER_STEP / 1e9
         roof_fp64 = {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                     "frac": fp64_ach / fp64_peak_tflops if fp64_peak_tflops > 0 else None, "traffic": None,
+                     "frac": fp64_ach / fp64_peak_tflops if fp64_peak_tflops > 0 else None, "traffic": traffic,
                      "peak_source": "measured live (sipnet_gpu_measure_fp64_peak, DFMA chains)",
                      "kernel": "sip::run_kernel", "kernel_ms": kern_ms,
                      "algorithmic": f"{FLOP_PER_MEMBER_STEP:.0f} FP64 flop/member-step x {M * T} member-steps"}
         roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": hbm_ach / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                     "algorithmic": f"{BYTES_PER_MEMBER_STEP:.0f} B/member-step x {M * T} member-steps"}
         primary, alt = (roof_fp64, roof_hbm) if (roof_fp64["frac"] or 0) >= roof_hbm["frac"] else (roof_hbm, roof_fp64)
         line = {
