@@ -69,16 +69,16 @@ struct Emitter {
   const double *obs;  // site's observations or null
   int64_t tSite;
   double ll, lln;
-  double *cur;
-  int64_t colStride;  // elements between consecutive columns = outSteps * ld
+  char *cur;
+  int64_t colStride;  // BYTES between consecutive columns = outSteps * ld * 8
   __device__ __forceinline__ void begin(int64_t tl, int64_t ts) {
     tLocal = tl;
     tSite = ts;
-    if (FULL) cur = outp + tl * a->ld;
+    if (FULL) cur = reinterpret_cast<char *>(outp + tl * a->ld);
   }
   __device__ __forceinline__ void out(int col, double v) {
     if (FULL) {
-      __stcs(cur, v);
+      __stcs(reinterpret_cast<double *>(cur), v);
       cur += colStride;
     } else if (outp != nullptr) {
       const int s = a->colSlot[col];
@@ -288,9 +288,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
   if constexpr (NM::kFast) {
     nm.expTab = libmTab;
     nm.powlogTab = libmTab + 2 * 128;
-    // the member-constant division seeds must be ordinary numbers (divisor non-zero, normal, finite)
-    for (int k = kSeedLeafCSpWt; k <= kSeedCSat; ++k)
-      if (k != kSeedCSat || fl.on(F_CSAT)) nm.seed_check(tile[tile_slot(k) * BLOCK + tid]);
+    // the member-constant divisors must be ordinary numbers (sip_num.cuh divisor_check)
+    const int divisors[] = {SIPNET_P_leafCSpWt, kPsnTRangeSqSlot, SIPNET_P_halfSatPar, SIPNET_P_soilWHC, kTwoWhc,
+                            SIPNET_P_leafCN,    SIPNET_P_woodCN,  SIPNET_P_fineRootCN, SIPNET_P_fAnoxia, kOneMinusFa};
+    for (int k : divisors) nm.divisor_check(tile[tile_slot(k) * BLOCK + tid]);
+    if (fl.on(F_CSAT)) nm.divisor_check(tile[tile_slot(SIPNET_P_soilCSaturation) * BLOCK + tid]);
   }
   const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
   const ParamTile prm{tile + tid, BLOCK};
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
     rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
   }
   Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
-                     site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld};
+                     site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
   if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
     emit.ll = a.loglik[m];
     emit.lln = a.loglikN[m];

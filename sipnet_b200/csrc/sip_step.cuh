@@ -136,7 +136,7 @@ __device__ __forceinline__ bool has_biomass(const Member &mb) {  // hasSufficien
 __device__ __forceinline__ void clamp_stock(double &v, double floorv, uint32_t &status) {
   // ensureNonNegative, sipnet.c:1346-1356
   if (v < floorv) {
-    if (fabs(v) > kEps) status |= SIPNET_GPU_ST_CLAMPED;
+    if (fabs(v) > kEps) status |= SIPNET_GPU_ST_CLAMPED;  // the reference's warning (informational)
     v = 0.;
   }
 }
@@ -302,7 +302,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   if constexpr (NM::kFast) {
     if (c.invLenPow2 == 0.0) {  // block-uniform: the step length is not a power of two
       seedLen = nm.seed(len);
-      nm.seed_check(seedLen);
+      nm.divisor_check(len);
     }
   }
   const Div<NM, PT> dv{nm, prm, len, seedLen, c.invLenPow2};
