@@ -85,6 +85,11 @@ void sip_write_state_row(FILE *out, int year, int day, double time, const double
 void sip_write_events_header(FILE *out);                                                  /* openEventOutFile() header */
 int sip_write_event_row(FILE *out, int year, int day, const sipnet_gpu_event_record *rec); /* doWriteEventOut() */
 const char *sip_event_type_name(int type);                                                /* eventTypeToString() */
+/* --debug-log <prefix>: <prefix>_envi.log, _fluxes.log, _trackers.log (debug_log.c:196-312); dbg[k * stride] is
+ * field k of SIPNET_GPU_GATHER_DEBUG for this member-step */
+void sip_write_debug_headers(FILE *envi, FILE *fluxes, FILE *trackers);
+void sip_write_debug_rows(FILE *envi, FILE *fluxes, FILE *trackers, int year, int day, double time, const double *dbg,
+                          int64_t stride);
 
 #ifdef __cplusplus
 }

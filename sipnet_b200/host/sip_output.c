@@ -81,3 +81,40 @@ int sip_write_event_row(FILE *out, int year, int day, const sipnet_gpu_event_rec
   fprintf(out, "%s=%-.2f\n", names[n - 1], rec->val[n - 1]);
   return 0;
 }
+
+/* ---- debug logs: field order of debug_log.c:51-170 ---------------------------------------------------------- */
+static const char *const kEnviNames[] = {"plantWoodC", "plantLeafC", "soilC", "soilWater", "litterC", "snow", "coarseRootC", "fineRootC", "minN", "soilOrgN", "litterN", "plantStorageN", "plantCAccountingDelta"};
+static const char *const kFluxNames[] = {"photosynthesis", "leafLitter", "woodLitter", "rVeg", "rSoil", "rain", "transpiration", "drainage", "litterToSoil", "rLitter", "snowFall", "snowMelt", "sublimation", "immedEvap", "fastFlow", "evaporation", "fineRootLoss", "coarseRootLoss", "fineRootCreation", "coarseRootCreation", "rCoarseRoot", "rFineRoot", "leafCreation", "woodCreation", "leafOnCreation", "leafOnCreationFromWood", "nVolatilization", "nLeaching", "nOrgSoil", "nOrgLitter", "nMin", "nFixation", "nUptake", "leafOffNResorption", "reductionNResorption", "eventLeafC", "eventWoodC", "eventFineRootC", "eventCoarseRootC", "eventEvap", "eventSoilWater", "eventSoilC", "eventLitterC", "eventMinN", "eventSoilOrgN", "eventLitterN", "eventInputC", "eventOutputC", "eventInputN", "eventOutputN", "eventLeafOnCreation", "eventLeafOnCreationFromWood", "eventLeafOffLitter", "eventLeafOffNResorption", "soilMethane", "litterMethane"};
+static const char *const kTrackerNames[] = {"gpp", "rtot", "ra", "rh", "rRoot", "rSoil", "rAboveground", "npp", "nee", "woodCreation", "gdd", "evapotranspiration", "soilWetnessFrac", "yearlyGpp", "yearlyRtot", "yearlyRa", "yearlyRh", "yearlyNpp", "yearlyNee", "yearlyLitter", "totGpp", "totRtot", "totRa", "totRh", "totNpp", "totNee", "lastYear", "methane", "n2o", "nLeaching", "nFixation", "nUptake", "meanNPP"};
+
+void sip_write_debug_headers(FILE *envi, FILE *fluxes, FILE *trackers) { /* outputDebugHeaders(), debug_log.c:250-275 */
+  fprintf(envi, "year day time");
+  for (int k = 0; k < SIPNET_GPU_NDEBUG_ENVI; ++k) fprintf(envi, " %s", kEnviNames[k]);
+  fprintf(envi, "\n");
+  fprintf(fluxes, "year day time");
+  for (int k = 0; k < SIPNET_GPU_NDEBUG_FLUX; ++k) fprintf(fluxes, " %s", kFluxNames[k]);
+  fprintf(fluxes, "\n");
+  fprintf(trackers, "year day time");
+  for (int k = 0; k < SIPNET_GPU_NDEBUG_TRACK; ++k) fprintf(trackers, " t.%s", kTrackerNames[k]);
+  fprintf(trackers, " pt.didLeafGrowth pt.didLeafFall pt.lastYear s.isAlive\n");
+}
+
+void sip_write_debug_rows(FILE *envi, FILE *fluxes, FILE *trackers, int year, int day, double time, const double *d,
+                          int64_t stride) { /* outputDebugState(), debug_log.c:277-312: "%4d %3d %5.2f" then " %.15g" / " %d" */
+  int k = 0;
+  fprintf(envi, "%4d %3d %5.2f", year, day, time);
+  for (int i = 0; i < SIPNET_GPU_NDEBUG_ENVI; ++i, ++k) fprintf(envi, " %.15g", d[(int64_t)k * stride]);
+  fprintf(envi, "\n");
+  fprintf(fluxes, "%4d %3d %5.2f", year, day, time);
+  for (int i = 0; i < SIPNET_GPU_NDEBUG_FLUX; ++i, ++k) fprintf(fluxes, " %.15g", d[(int64_t)k * stride]);
+  fprintf(fluxes, "\n");
+  fprintf(trackers, "%4d %3d %5.2f", year, day, time);
+  for (int i = 0; i < SIPNET_GPU_NDEBUG_TRACK; ++i, ++k) {
+    if (i == 26) /* trackers.lastYear is an int field */
+      fprintf(trackers, " %d", (int)d[(int64_t)k * stride]);
+    else
+      fprintf(trackers, " %.15g", d[(int64_t)k * stride]);
+  }
+  for (int i = 0; i < 4; ++i, ++k) fprintf(trackers, " %d", (int)d[(int64_t)k * stride]);
+  fprintf(trackers, "\n");
+}

@@ -8,8 +8,8 @@
  * include/sipnet_gpu.h.  Extension: --ensemble-params FILE runs one member per
  * listed .param file on the same site in one launch; member k's outputs go to
  * <prefix>.out.<k> / events.out.<k>.
- * Not supported (outside the hot-path scope): --restart-in/--restart-out,
- * --debug-log, --do-single-outputs (exit 8 with a message).
+ * --debug-log <prefix> writes the reference's three per-step debug logs from the device's validation dump.
+ * Not supported (outside the hot-path scope): --restart-in/--restart-out, --do-single-outputs (exit 8).
  */
 #define _GNU_SOURCE
 #include <stdlib.h>
@@ -31,10 +31,12 @@ int main(int argc, char **argv) {
   if (ctx.helpOrVersion) return 0;
   if ((rc = sip_read_input_file(&ctx))) return die(rc, sip_host_error());
   if ((rc = sip_validate_context(&ctx))) return die(rc, sip_host_error());
-  if (ctx.restartIn[0] || ctx.restartOut[0] || ctx.debugLogPrefix[0] || ctx.doSingleOutputs)
+  if (ctx.restartIn[0] || ctx.restartOut[0] || ctx.doSingleOutputs)
     return die(SIPNET_GPU_ERR_BAD_CLI,
-               "restart checkpoints, --debug-log and single-variable outputs are not part of the GPU hot path; "
+               "restart checkpoints and single-variable outputs are not part of the GPU hot path; "
                "use the reference binary for those");
+  if (ctx.debugLogPrefix[0] && ctx.ensembleParamList[0])
+    return die(SIPNET_GPU_ERR_BAD_CLI, "--debug-log is a single-member feature");
   if ((rc = sip_derive_file_names(&ctx))) return die(rc, sip_host_error());
 
   FILE *out = NULL;
@@ -99,7 +101,8 @@ int main(int argc, char **argv) {
   cfg.nmembers = M;
   cfg.params = params;
   cfg.params_ld = M;
-  cfg.outputs = (ctx.doMainOutput ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0);
+  cfg.outputs = (ctx.doMainOutput ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0) |
+                (ctx.debugLogPrefix[0] ? SIPNET_GPU_OUT_DEBUG : 0);
   cfg.math = ctx.validationMath ? SIPNET_GPU_MATH_VALIDATION : SIPNET_GPU_MATH_FAST;
   cfg.max_event_records = ctx.flags.events ? (int32_t)(site.nevents + 4 * (site.nsteps / 300 + 8)) : 0;
   sipnet_gpu_handle *h = NULL;
@@ -139,6 +142,25 @@ int main(int argc, char **argv) {
       fclose(o);
     }
     free(buf);
+  }
+  if (ctx.debugLogPrefix[0]) { /* outputDebugState() per step, debug_log.c:277-312 */
+    const size_t n = (size_t)SIPNET_GPU_NDEBUG * (size_t)T;
+    double *dbg = (double *)malloc(n * sizeof(double));
+    if (!dbg) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
+    if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_DEBUG, dbg, n * sizeof(double)))) return die(rc, sipnet_gpu_last_error());
+    char name[SIP_NAME_MAX + 32];
+    FILE *f[3];
+    const char *suffix[3] = {"_envi.log", "_fluxes.log", "_trackers.log"};
+    for (int k = 0; k < 3; ++k) {
+      snprintf(name, sizeof name, "%s%s", ctx.debugLogPrefix, suffix[k]);
+      f[k] = fopen(name, "w");
+      if (!f[k]) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open debug log file");
+    }
+    if (ctx.printHeader) sip_write_debug_headers(f[0], f[1], f[2]);
+    for (int64_t t = 0; t < T; ++t)
+      sip_write_debug_rows(f[0], f[1], f[2], site.year[t], site.day[t], site.time[t], dbg + t, T);
+    for (int k = 0; k < 3; ++k) fclose(f[k]);
+    free(dbg);
   }
   if (ctx.flags.events) {
     const size_t nrec = (size_t)M * (size_t)cfg.max_event_records;

@@ -105,8 +105,27 @@ def pack_smoke_inputs():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def debug_log_md5():
+    """md5 of the reference binary's --debug-log files for the smoke cases -> tests/golden/debug_log_md5.json"""
+    import json
+    import shutil
+    import subprocess
+    res = {}
+    for name in SMOKE:
+        with tempfile.TemporaryDirectory() as td:
+            for fn in ("sipnet.in", "sipnet.param", "sipnet.clim", "events.in"):
+                shutil.copy(os.path.join(REF, "tests", "smoke", name, fn), td)
+            subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sipnet_ref"), "-i", "sipnet.in", "--quiet",
+                                   "--debug-log", "dbg"], cwd=td, stdout=subprocess.DEVNULL)
+            res[name] = {k: hashlib.md5(open(os.path.join(td, f"dbg_{k}.log"), "rb").read()).hexdigest()
+                         for k in ("envi", "fluxes", "trackers")}
+    json.dump(res, open(os.path.join(OUT, "debug_log_md5.json"), "w"), indent=1)
+    print("debug log md5:", res)
+
+
 def main():
     pack_smoke_inputs()
+    debug_log_md5()
     shim = RefShim()
     for name, flags in SMOKE.items():
         d = os.path.join(REF, "tests", "smoke", name)

@@ -74,3 +74,16 @@ def test_driver_exit_codes(smoke_dir):
         assert r.returncode == 5            # first event before the climate record (frontend.c:217-222)
     finally:
         open(os.path.join(d, "events.in"), "w").write(ev)
+
+
+@pytest.mark.parametrize("case", SMOKE)
+def test_debug_log_byte_identical(smoke_dir, case):
+    """--debug-log: the three per-step logs (%.15g of every Envi/Fluxes/Trackers field) equal the reference's."""
+    import json
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "debug_log_md5.json")))[case]
+    d = os.path.join(smoke_dir, case)
+    r = subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--debug-log", "dbg"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for k in ("envi", "fluxes", "trackers"):
+        got = hashlib.md5(open(os.path.join(d, f"dbg_{k}.log"), "rb").read()).hexdigest()
+        assert got == want[k], f"{case}: dbg_{k}.log differs from the reference's"
