@@ -222,6 +222,9 @@ struct Div {
 // ---- nitrogen helpers, nitrogen.c ----------------------------------------------------
 template <class DV>
 __device__ __forceinline__ double n_leafon_from_c(const DV &dv, double c) {  // nitrogen.c:86-88
+  // c is the leaf-on flux: zero on all but one step a year.  fmax(0.0, (+-0)/a - (+-0)/b) is +0 exactly,
+  // so the two divisions are skipped (same bits).
+  if (c == 0.0) return 0.0;
   return fmax(0.0, dv.byLeafCN(c) - dv.byWoodCN(c));
 }
 template <class FL, class DV>
@@ -710,7 +713,15 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // calcMethaneFlux, :1201-1214
   if (fl.on(F_ANAEROBIC)) {
-    const double mm = nm.pow(anaerobicIdx, SIP_P(anaerobicTransExp));  // calcMethaneMoistEffect
+    // calcMethaneMoistEffect: pow(A, e).  A is exactly +0 whenever the soil is below the anoxia threshold, and
+    // pow(+0, e) = +0 for every finite e > 0 (e_pow.c zero branch): skip the evaluation in that (common) case.
+    const double te = SIP_P(anaerobicTransExp);
+    double mm;
+    if (__double_as_longlong(anaerobicIdx) == 0ll && te > 0.0 && te < 1e300) {
+      mm = 0.0;
+    } else {
+      mm = nm.pow(anaerobicIdx, te);
+    }
     r.soilMethane = SIP_P(soilMethaneRate) * mb.soil * tempEffect * mm;
     if (fl.on(F_LITTER_POOL)) r.litterMethane = SIP_P(litterMethaneRate) * mb.litter * tempEffect * mm;
   }
