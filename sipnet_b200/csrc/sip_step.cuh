@@ -256,15 +256,17 @@ __device__ __forceinline__ double n_fix_frac(const DV &dv, const Member &mb) {  
   }
   return SIP_P(nFixationFracMax) * inhib;
 }
+// returns calcPlantNDemandFlux() of the current creation fluxes (reused by updateNitrogenPools: same inputs)
 template <class FL, class DV>
-__device__ __forceinline__ void n_fix_and_uptake(const FL &fl, const DV &dv, const Member &mb, Rates &r,
-                                                 double len) {  // nitrogen.c:156-168
+__device__ __forceinline__ double n_fix_and_uptake(const FL &fl, const DV &dv, const Member &mb, Rates &r,
+                                                   double len) {  // nitrogen.c:156-168
   const double demand = n_demand(fl, dv, r);
   const double storage = dv.byLen(n_unclaimed_storage(dv, mb, r, len));
   const double rem = fmax(0.0, demand - storage);
   const double ff = n_fix_frac(dv, mb);
   r.nFixation = ff * rem;
   r.nUptake = (1 - ff) * rem;
+  return demand;
 }
 
 // checkLeafOnLimitation, limitations.c:13-64
@@ -459,9 +461,8 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // state-independent Q10 / VPD factors first: six independent exp-class evaluations
   const double q10Fol = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
                                 nm.divs(c.tair - SIP_P(psnTOpt), 10.0, kc.seed10));      // sipnet.c:1056
-  const double q10Wood = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
-                                 nm.divs(c.tair, 10.0, kc.seed10));                        // :1067
-  const double tsoil10 = nm.divs(c.tsoil, 10.0, kc.seed10);
+  const double q10Wood = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1), c.tair10);  // :1067
+  const double tsoil10 = c.tsoil10;
   const double q10Coarse = nm.powc(SIP_P(coarseRootQ10), prm(kLogCoarseQ10), prm(kLogCoarseQ10 + 1), tsoil10);  // :1076
   const double q10Fine = nm.powc(SIP_P(fineRootQ10), prm(kLogFineQ10), prm(kLogFineQ10 + 1), tsoil10);
   const double tempEffect = nm.powc(SIP_P(soilRespQ10), prm(kLogSoilQ10), prm(kLogSoilQ10 + 1), tsoil10);  // depeffects.c:72-75
@@ -524,11 +525,11 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // calcPrecip, :848-882
   if (c.tair <= 0) {
-    r.snowFall = dv.byLen(c.precip);
+    r.snowFall = c.precipRate;
     r.rain = 0;
   } else {
     r.snowFall = 0;
-    r.rain = dv.byLen(c.precip);
+    r.rain = c.precipRate;
   }
   r.immedEvap = r.rain * SIP_P(immedEvapFrac);
   if (fl.on(F_LEAF_WATER)) {
@@ -539,13 +540,12 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // snowPack, :888-946
   {
-    const double k = (1.3 * 1005.) / 66. * (1. / 2835000.) * 1000. * 1000. * (1. / 10000) * 86400.0;
     if (mb.snow <= 0) {
       r.snowMelt = 0;
       r.sublimation = 0;
     } else {
       const double rd = nm.div(SIP_P(rdConst), c.wspd);
-      r.sublimation = nm.div(k * (0.6 - c.vPress), rd);
+      r.sublimation = nm.div(c.sublK, rd);
       double left = mb.snow + (r.snowFall * len);
       if (r.sublimation < 0) r.sublimation = 0;
       if (left - (r.sublimation * len) < 0) {
@@ -566,7 +566,6 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // calcSoilWaterFluxes, :963-1031
   const double waterFrac = clip01(dv.byWhc(mb.water));  // getClippedWaterFrac, depeffects.c:11
   {
-    const double k = (1.3 * 1005.) / 66. * (1. / 2501000.) * 1000. * 1000. * (1. / 10000) * 86400.0;
     double netIn = netRain + r.snowMelt;
     r.fastFlow = netIn * SIP_P(fastFlowFrac);
     netIn -= r.fastFlow;
@@ -576,7 +575,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     } else {
       const double rd = nm.div(SIP_P(rdConst), c.wspd);
       const double rsoil = nm.exp(SIP_P(rSoilConst1) - SIP_P(rSoilConst2) * waterFrac);
-      r.evaporation = nm.div(k * c.vpdSoil, rd + rsoil);
+      r.evaporation = nm.div(c.evapK, rd + rsoil);
       if (r.evaporation < 0) r.evaporation = 0;
       if (left - (r.evaporation * len) < kTiny) {
         r.evaporation = dv.byLen(left - kTiny);
@@ -748,6 +747,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     }
   }
 
+  double nDemand = 0.0;  // calcPlantNDemandFlux() of the final creation fluxes
   if (fl.on(F_NITROGEN)) {
     // calcNResorptionFluxes, nitrogen.c:170-196
     if (r.woodCreation + r.leafCreation + r.fineRootCreation + r.coarseRootCreation < 0.0) {
@@ -779,7 +779,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       r.nOrgSoil = inputs * (1 - sat) - soilMin;
       r.nMin = litterMin + soilMin;
     }
-    n_fix_and_uptake(fl, dv, mb, r, len);  // nitrogen.c:156-168
+    nDemand = n_fix_and_uptake(fl, dv, mb, r, len);  // nitrogen.c:156-168
 
     // checkMineralNLimitation, limitations.c:119-130
     {
@@ -805,7 +805,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         r.leafCreation *= red;
         r.fineRootCreation *= red;
         r.coarseRootCreation *= red;
-        n_fix_and_uptake(fl, dv, mb, r, len);
+        nDemand = n_fix_and_uptake(fl, dv, mb, r, len);
       }
     }
   }
@@ -879,7 +879,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // updateNitrogenPools, nitrogen.c:210-239
   if (fl.on(F_NITROGEN)) {
-    const double demand = n_demand(fl, dv, r);
+    const double demand = nDemand;  // the creation fluxes have not changed since n_fix_and_uptake() evaluated it
     const double fromStorage = demand - r.nUptake - r.nFixation;
     const double onN = n_leafon_from_c(dv, r.leafOnCreation);
     mb.storN += (r.leafOffNResorption + r.reductionNResorption - fromStorage - onN) * len;

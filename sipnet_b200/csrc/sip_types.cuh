@@ -90,7 +90,7 @@ enum : uint32_t {
   F_CSAT = 1u << 11,
 };
 
-// One climate step as staged to shared memory: 17 x 8 bytes = 136 -> padded to 144 bytes
+// One climate step as staged to shared memory: 20 doubles + 4 ints = 176 bytes
 // (multiple of 16 so a chunk is a legal cp.async.bulk size).
 struct alignas(16) ClimRec {
   double time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
@@ -102,10 +102,16 @@ struct alignas(16) ClimRec {
   double logVpdHi, logVpdLo;
   // 1 / length when length is a power of two (then x / length == x * invLen exactly), else 0
   double invLenPow2;
+  // site-level sub-expressions, evaluated on the host with the same IEEE operations:
+  double tair10;      // tair / 10.0            (vegResp, sipnet.c:1067)
+  double tsoil10;     // tsoil / 10 (== / 10.0) (calcRootResp sipnet.c:1076, calcTempEffect depeffects.c:74)
+  double precipRate;  // precip / length        (calcPrecip, sipnet.c:851,858)
+  double sublK;       // CONVERSION_S * (E_STAR_SNOW - vPress)   (snowPack, sipnet.c:910)
+  double evapK;       // CONVERSION * vpdSoil                    (calcSoilWaterFluxes, sipnet.c:1000)
   int32_t year, day;
   int32_t evBegin, evEnd;  // events of this step: [evBegin, evEnd) in the site's EventDev array
 };
-static_assert(sizeof(ClimRec) == 144 && sizeof(ClimRec) % 16 == 0, "ClimRec must be a multiple of 16 bytes");
+static_assert(sizeof(ClimRec) == 176 && sizeof(ClimRec) % 16 == 0, "ClimRec must be a multiple of 16 bytes");
 
 struct alignas(16) EventDev {
   double p[4];

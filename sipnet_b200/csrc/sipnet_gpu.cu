@@ -170,6 +170,11 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimR
       c.logVpdHi = l.hi;
       c.logVpdLo = l.lo;
     }
+    c.tair10 = c.tair / 10.0;
+    c.tsoil10 = c.tsoil / 10.0;
+    c.precipRate = c.precip / c.length;
+    c.sublK = ((1.3 * 1005.) / 66. * (1. / 2835000.) * 1000. * 1000. * (1. / 10000) * 86400.0) * (0.6 - c.vPress);
+    c.evapK = ((1.3 * 1005.) / 66. * (1. / 2501000.) * 1000. * 1000. * (1. / 10000) * 86400.0) * c.vpdSoil;
     {
       int ex = 0;
       const double mant = std::frexp(c.length, &ex);  // power of two <=> mantissa 0.5: then x / length == x * (1 / length)
