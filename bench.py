@@ -435,32 +435,48 @@ def run_other_config(args):
     cap = kw.get("out_steps_capacity", T)
     qs = [0.05, 0.5, 0.95]
 
-    def one_pass():
+    def one_pass(prof=None):
+        """prof: dict of phase -> seconds, filled with a device synchronize after every phase (an extra,
+        untimed pass; the timed passes run without those synchronizes)."""
+        def lap(name, t_prev):
+            if prof is None:
+                return 0.0
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            prof[name] = prof.get(name, 0.0) + now - t_prev
+            return now
+        tp = lap("_", time.perf_counter())
         ens.reset()
-        extra = 0.0
         if args.workload == "c5":
             ens.run(0, T)
+            tp = lap("run_kernel", tp)
             ll = D.DeviceArray(ens.device_ptr(A.GATHER_LOGLIK), (M_local,)).tensor(local)
             if world > 1:
                 D.all_gather_members(ll, [M_local] * world)
+            lap("gather", tp)
             return
         for t0 in range(0, T, cap):
             t1 = min(T, t0 + cap)
             ens.run(t0, t1)
+            tp = lap("run_kernel", tp)
             n = t1 - t0
             mean, var = ens.mean(), ens.variance()              # local shard's per-step moments
+            tp = lap("moments", tp)
             if args.workload == "c4":
                 if world > 1:
                     cnt = np.full_like(mean[0], float(M_local))
                     D.all_gather_moments(torch.from_numpy(cnt).cuda(), torch.from_numpy(mean[0]).cuda(),
                                          torch.from_numpy(var[0]).cuda())
+                    tp = lap("moments_gather", tp)
                 ld = (M_local + 15) // 16 * 16
                 colbuf = D.DeviceArray(ens.device_ptr(A.GATHER_FULL), (2, n, M_local), (n * ld, ld, 1)).tensor(local)
                 for i in range(2):
                     rows = colbuf[i]
                     if world > 1:
                         rows, _, _ = D.time_transpose(rows, [M_local] * world)
-                    D.rows_summary(rows, qs)
+                        tp = lap("time_transpose", tp)
+                    D.rows_summary(rows, qs, moments=False)
+                    tp = lap("quantile_select", tp)
 
     one_pass()
     barrier()
@@ -472,10 +488,13 @@ def run_other_config(args):
     tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    prof = {}
+    one_pass(prof)
+    prof.pop("_", None)
     status = ens.status()
     ens.close()
     if rank == 0:
-        print(json.dumps({"metric": METRIC, "workload": name, "value": world * M_local * T / float(tmax.item()),
+        print(json.dumps({"metric": METRIC, "workload": name, "phases_s": {k: round(v, 5) for k, v in prof.items()}, "value": world * M_local * T / float(tmax.item()),
                           "unit": UNIT, "n_gpus": world, "steps": args.steps, "s_per_pass": float(tmax.item()),
                           "members_per_gpu": M_local, "model_steps": T, "input_build_s": t_build,
                           "replayed_members": int((status & A.ST_REPLAY).astype(bool).sum()),

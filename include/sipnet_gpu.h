@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SIPNET_GPU_ABI_VERSION 1
+#define SIPNET_GPU_ABI_VERSION 2
 
 /* ---- return codes: reference src/common/exitCodes.h:16-27 ---------------- */
 #define SIPNET_GPU_OK 0
@@ -216,6 +216,7 @@ typedef struct sipnet_gpu_event_record {
 #define SIPNET_GPU_OUT_EVENTS 0x20u  /* per-member event records */
 
 /* ---- arithmetic build selection -------------------------------------------- */
+#define SIPNET_GPU_RING_SLOTS_REFERENCE 250
 #define SIPNET_GPU_MATH_VALIDATION 0 /* -fmad=false, IEEE div: mirrors the reference's gcc -O0 x86-64 arithmetic */
 #define SIPNET_GPU_MATH_FAST 1       /* -fmad=true perf build; re-gated at 1e-10 */
 
@@ -246,6 +247,11 @@ typedef struct sipnet_gpu_config {
   int32_t max_event_records;   /* per member, for SIPNET_GPU_OUT_EVENTS */
   int32_t block_threads;       /* 0 => library default */
   void *stream;                /* cudaStream_t to launch on; NULL => library-owned stream */
+  int32_t ring_slots;          /* slots of the 5-day mean-NPP ring per member.  0 => the smallest ring that cannot
+                                  overflow sooner than the reference's (a few slots);
+                                  SIPNET_GPU_RING_SLOTS_REFERENCE => the reference's own layout, slot for slot
+                                  (MEAN_NPP_MAX_ENTRIES, sipnet.c:40) -- needed when the ring is exchanged with the
+                                  reference through a restart checkpoint (restart.c:799-806) */
 } sipnet_gpu_config;
 
 typedef struct sipnet_gpu_handle sipnet_gpu_handle;
@@ -262,7 +268,9 @@ enum sipnet_gpu_gather_what {
   SIPNET_GPU_GATHER_QUANTILES = 8, /* double [nsites][n_summary_cols][n_quantiles][n] */
   SIPNET_GPU_GATHER_EVENT_COUNTS = 9, /* int32 [M] */
   SIPNET_GPU_GATHER_EVENT_RECORDS = 10, /* sipnet_gpu_event_record [M][max_event_records] */
-  SIPNET_GPU_GATHER_LOGLIK_N = 11 /* double [M]: number of observations that entered the likelihood */
+  SIPNET_GPU_GATHER_LOGLIK_N = 11, /* double [M]: number of observations that entered the likelihood */
+  SIPNET_GPU_GATHER_RING_VALUES = 12,  /* double [ring_slots][M]: MeanTracker.values, slot-major (runmean.h) */
+  SIPNET_GPU_GATHER_RING_WEIGHTS = 13  /* double [ring_slots][M]: MeanTracker.weights */
 };
 
 /* per-member status bits (instead of the reference's exit()) */
@@ -286,6 +294,7 @@ enum sipnet_gpu_state_row {
   SIPNET_S_totGpp, SIPNET_S_totRtot, SIPNET_S_totRa, SIPNET_S_totRh, SIPNET_S_totNpp, SIPNET_S_totNee,
   SIPNET_S_trackersLastYear, SIPNET_S_didLeafGrowth, SIPNET_S_didLeafFall, SIPNET_S_phenLastYear,
   SIPNET_S_dTillMod, SIPNET_S_meanSum, SIPNET_S_meanStart, SIPNET_S_meanLast,
+  SIPNET_S_harvestFracRemoved, SIPNET_S_harvestFracTransferred, /* eventTrackers of the last step (restart.c:295-296) */
   SIPNET_GPU_NSTATE
 };
 
@@ -338,6 +347,23 @@ int sipnet_gpu_sync(sipnet_gpu_handle *h);
 
 /* Reset every member to its post-setupModel() state (step counter back to 0). */
 int sipnet_gpu_reset(sipnet_gpu_handle *h);
+
+/*
+ * sipnet_gpu_set_state -- overwrite the carried state of every member, the way
+ * restartLoadCheckpoint() overwrites the globals after setupModel()+setupEvents()
+ * (sipnet.c:1963-1967, restart.c:963-983).  state is [SIPNET_GPU_NSTATE][state_ld]
+ * (rows of enum sipnet_gpu_state_row; the layout SIPNET_GPU_GATHER_STATE returns
+ * with state_ld = nmembers), ring_values / ring_weights are [ring_slots][ring_ld]
+ * (SIPNET_GPU_GATHER_RING_*; both NULL keeps the handle's rings).  The next run()
+ * must start at next_step.  The yearly*, tot* (except totNee) and harvestFrac* rows
+ * are carried only by handles created with SIPNET_GPU_OUT_DEBUG; they feed
+ * nothing back into the model (sipnet.c:1420-1496).
+ */
+int sipnet_gpu_set_state(sipnet_gpu_handle *h, const double *state, int64_t state_ld, const double *ring_values,
+                         const double *ring_weights, int64_t ring_ld, int64_t next_step);
+
+/* Slots of the mean-NPP ring this handle uses (config ring_slots, or the automatic choice). */
+int32_t sipnet_gpu_ring_slots(const sipnet_gpu_handle *h);
 
 /*
  * sipnet_gpu_set_params -- load a new parameter ensemble into an existing

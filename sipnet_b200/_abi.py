@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # reference src/common/context.h:45-56
 FLAG_NAMES = (
@@ -110,8 +110,10 @@ STATE_NAMES = (
     "yearlyRh", "yearlyNpp", "yearlyNee", "yearlyLitter", "totGpp", "totRtot",
     "totRa", "totRh", "totNpp", "totNee", "trackersLastYear", "didLeafGrowth",
     "didLeafFall", "phenLastYear", "dTillMod", "meanSum", "meanStart",
-    "meanLast",
+    "meanLast", "harvestFracRemoved", "harvestFracTransferred",
 )
+S = {n: i for i, n in enumerate(STATE_NAMES)}
+RING_SLOTS_REFERENCE = 250   # MEAN_NPP_MAX_ENTRIES, sipnet.c:40
 NSTATE = len(STATE_NAMES)
 
 # events.h:13-23
@@ -129,7 +131,7 @@ MATH_VALIDATION, MATH_FAST = 0, 1
 
 (GATHER_FULL, GATHER_DEBUG, GATHER_LOGLIK, GATHER_STATUS, GATHER_STATE,
  GATHER_MEAN, GATHER_VARIANCE, GATHER_QUANTILES, GATHER_EVENT_COUNTS,
- GATHER_EVENT_RECORDS, GATHER_LOGLIK_N) = range(1, 12)
+ GATHER_EVENT_RECORDS, GATHER_LOGLIK_N, GATHER_RING_VALUES, GATHER_RING_WEIGHTS) = range(1, 14)
 
 ST_BAD_ALLOCATION, ST_RING_OVERFLOW, ST_CLAMPED, ST_DIED, ST_EVREC_OVERFLOW, \
     ST_NONFINITE, ST_REPLAY = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
@@ -178,4 +180,5 @@ class Config(C.Structure):
         ("nee_sigma", C.c_double),
         ("max_event_records", C.c_int32), ("block_threads", C.c_int32),
         ("stream", C.c_void_p),
+        ("ring_slots", C.c_int32),
     ]

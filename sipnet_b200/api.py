@@ -59,6 +59,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_reset.argtypes = [C.c_void_p]
     lib.sipnet_gpu_set_params.restype = C.c_int
     lib.sipnet_gpu_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.sipnet_gpu_set_state.restype = C.c_int
+    lib.sipnet_gpu_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    lib.sipnet_gpu_ring_slots.restype = C.c_int32
+    lib.sipnet_gpu_ring_slots.argtypes = [C.c_void_p]
     lib.sipnet_gpu_timer_start.restype = C.c_int
     lib.sipnet_gpu_timer_start.argtypes = [C.c_void_p]
     lib.sipnet_gpu_timer_stop_ms.restype = C.c_int
@@ -186,7 +190,7 @@ class Ensemble:
                  device: int = 0, out_steps_capacity: int = 0,
                  summary_cols: Sequence[int] = (), quantiles: Sequence[float] = (),
                  nee_sigma: float = 1.0, max_event_records: int = 0,
-                 block_threads: int = 0, stream: int = 0, lib: Optional[C.CDLL] = None):
+                 block_threads: int = 0, stream: int = 0, ring_slots: int = 0, lib: Optional[C.CDLL] = None):
         self.lib = lib or load_library()
         params = np.ascontiguousarray(params, dtype=np.float64)
         if params.ndim != 2 or params.shape[0] != A.NPARAMS:
@@ -229,6 +233,7 @@ class Ensemble:
         cfg.max_event_records = max_event_records
         cfg.block_threads = block_threads
         cfg.stream = stream or None
+        cfg.ring_slots = ring_slots
         self.n_summary_cols = int(sc.size)
         self.n_quantiles = int(q.size)
         self.max_event_records = max_event_records
@@ -301,6 +306,33 @@ class Ensemble:
 
     def state(self) -> np.ndarray:
         return self._gather(A.GATHER_STATE, np.float64, (A.NSTATE, self.nmembers))
+
+    @property
+    def ring_slots(self) -> int:
+        return int(self.lib.sipnet_gpu_ring_slots(self.handle))
+
+    def ring(self):
+        """(values, weights), each [ring_slots][M]: the mean-NPP tracker's arrays (runmean.h)."""
+        shape = (self.ring_slots, self.nmembers)
+        return (self._gather(A.GATHER_RING_VALUES, np.float64, shape), self._gather(A.GATHER_RING_WEIGHTS, np.float64, shape))
+
+    def set_state(self, state: np.ndarray, ring_values: Optional[np.ndarray] = None,
+                  ring_weights: Optional[np.ndarray] = None, next_step: int = 0) -> None:
+        """Overwrite the carried state (restartLoadCheckpoint semantics); the next run starts at next_step."""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        if state.shape != (A.NSTATE, self.nmembers):
+            raise ValueError(f"state must be [{A.NSTATE}][{self.nmembers}]")
+        rv = rw = None
+        if ring_values is not None:
+            rv = np.ascontiguousarray(ring_values, dtype=np.float64)
+            rw = np.ascontiguousarray(ring_weights, dtype=np.float64)
+            if rv.shape != (self.ring_slots, self.nmembers) or rw.shape != rv.shape:
+                raise ValueError(f"rings must be [{self.ring_slots}][{self.nmembers}]")
+        rc = self.lib.sipnet_gpu_set_state(self.handle, state.ctypes.data, self.nmembers,
+                                           None if rv is None else rv.ctypes.data, None if rw is None else rw.ctypes.data,
+                                           self.nmembers, next_step)
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
 
     def mean(self) -> np.ndarray:
         return self._gather(A.GATHER_MEAN, np.float64, (self.nsites, self.n_summary_cols, self.nrun))

@@ -142,6 +142,8 @@ __device__ __forceinline__ void load_member(const RunArgs &a, const double *stat
     ext.tRa = s[SIPNET_S_totRa * ld];
     ext.tRh = s[SIPNET_S_totRh * ld];
     ext.tNpp = s[SIPNET_S_totNpp * ld];
+    ext.harvRemoved = s[SIPNET_S_harvestFracRemoved * ld];
+    ext.harvTransferred = s[SIPNET_S_harvestFracTransferred * ld];
   }
 }
 
@@ -193,6 +195,8 @@ __device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const 
     s[SIPNET_S_totRa * ld] = ext.tRa;
     s[SIPNET_S_totRh * ld] = ext.tRh;
     s[SIPNET_S_totNpp * ld] = ext.tNpp;
+    s[SIPNET_S_harvestFracRemoved * ld] = ext.harvRemoved;
+    s[SIPNET_S_harvestFracTransferred * ld] = ext.harvTransferred;
   }
 }
 

@@ -20,55 +20,28 @@
 
 namespace sip {
 
-constexpr int kRedThreads = 256;
+// ---- shared helpers -----------------------------------------------------------------------------
+constexpr int kSelThreads = 512;           // block size of the per-row kernel
+constexpr int kSelBins = 2048;             // 11 key bits per histogram level
+constexpr int kSelMaxQ = 4;                // quantiles per launch (the launcher loops over groups)
+constexpr int kSelMaxRanks = 2 * kSelMaxQ; // each quantile needs the order statistics lo and lo+1
+constexpr int kCandCap = 8192;             // candidate keys finished in shared memory (64 KB, shares the histograms' storage)
+constexpr int kSelDynBytes = kSelMaxRanks * kSelBins * 4;
+static_assert(kSelDynBytes == kCandCap * 8, "histograms and candidate buffer share one allocation");
+constexpr int kWarpRowMax = 256;           // rows up to this long take the warp-per-row moments kernel
 
+// fixed-order block sum (strided per-thread partials were accumulated by the caller)
 __device__ __forceinline__ double block_sum(double v, double *sh) {
   const int tid = threadIdx.x;
   sh[tid] = v;
   __syncthreads();
-  for (int s = kRedThreads / 2; s > 0; s >>= 1) {
+  for (int s = kSelThreads / 2; s > 0; s >>= 1) {
     if (tid < s) sh[tid] += sh[tid + s];
     __syncthreads();
   }
   const double r = sh[0];
   __syncthreads();
   return r;
-}
-
-// grid = (nsteps, nsites); block = kRedThreads
-// output element (site, t) at [site * siteStride + t]
-__global__ void __launch_bounds__(kRedThreads) moments_kernel(const double *cols, int64_t ld, int64_t nsteps,
-                                                              const SiteDev *sites, double *mean, double *var,
-                                                              int64_t siteStride) {
-  __shared__ double sh[kRedThreads];
-  const int64_t t = blockIdx.x;
-  const int site = blockIdx.y;
-  const SiteDev sd = sites[site];
-  const double *row = cols + t * ld + sd.member0;
-  double s = 0.0, cnt = 0.0;
-  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
-    const double x = row[i];
-    if (isfinite(x)) {
-      s += x;
-      cnt += 1.0;
-    }
-  }
-  const double total = block_sum(s, sh);
-  const double n = block_sum(cnt, sh);
-  const double mu = n > 0 ? total / n : nan("");
-  double q = 0.0;
-  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
-    const double x = row[i];
-    if (isfinite(x)) {
-      const double d = x - mu;
-      q += d * d;
-    }
-  }
-  const double ss = block_sum(q, sh);
-  if (threadIdx.x == 0) {
-    mean[(int64_t)site * siteStride + t] = mu;
-    var[(int64_t)site * siteStride + t] = n > 0 ? ss / n : nan("");
-  }
 }
 
 // order-preserving map double -> uint64 (ascending)
@@ -81,110 +54,345 @@ __device__ __forceinline__ double val_of(uint64_t k) {
   return __longlong_as_double((long long)b);
 }
 
-// k-th smallest (0-based) finite element of row[0..count) by MSB radix select, 8 bits per pass.
-__device__ uint64_t radix_select(const double *row, int count, unsigned long long k, unsigned int *hist) {
-  uint64_t prefix = 0, mask = 0;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += kRedThreads) hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < count; i += kRedThreads) {
-      const double x = row[i];
-      if (isfinite(x)) {
-        const uint64_t key = key_of(x);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
-      }
-    }
-    __syncthreads();
-    // every thread scans the 256 bins identically (cheap, avoids another barrier pattern)
-    unsigned long long acc = 0;
-    int bin = 0;
-    for (; bin < 256; ++bin) {
-      const unsigned long long c = hist[bin];
-      if (acc + c > k) break;
-      acc += c;
-    }
-    k -= acc;
-    prefix |= (uint64_t)bin << shift;
-    mask |= (uint64_t)0xFF << shift;
-    __syncthreads();
-  }
-  return prefix;
+// histogram levels over the 64-bit key: 11,11,11,11,11,9 bits from the top
+__device__ __forceinline__ int level_shift(int level) { return level < 5 ? 53 - 11 * level : 0; }
+__device__ __forceinline__ int level_bins(int level) { return level < 5 ? kSelBins : 512; }
+
+// one shared-memory atomic per distinct code in the warp (ensemble values crowd into a few bins of
+// the leading levels; unaggregated atomics would serialise 32-fold).  Executed by all 32 lanes.
+__device__ __forceinline__ void hist_add(unsigned int *hist, int code) {
+  const unsigned peers = __match_any_sync(0xffffffffu, code);
+  if (code >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[code], (unsigned)__popc(peers));
 }
 
-// grid = (nsteps, nsites); block = kRedThreads.  out[site * siteStride + q * nsteps + t]
-__global__ void __launch_bounds__(kRedThreads) quantiles_kernel(const double *cols, int64_t ld, int64_t nsteps,
-                                                                const SiteDev *sites, const double *probs, int nq,
-                                                                double *out, int64_t siteStride) {
-  __shared__ unsigned int hist[256];
-  __shared__ double sh[kRedThreads];
+struct SelState {
+  uint64_t prefix[kSelMaxRanks];       // resolved leading key bits of each wanted order statistic
+  unsigned long long k[kSelMaxRanks];  // its rank among the keys that share the prefix
+  unsigned int pop[kSelMaxRanks];      // how many keys share the prefix
+  int slotOf[kSelMaxRanks];            // ranks with equal prefixes share a histogram slot
+  uint64_t slotTop[kSelMaxRanks];      // prefix >> shift of the last resolved level
+  unsigned int slotBase[kSelMaxRanks + 1];
+  unsigned int slotFill[kSelMaxRanks];
+  double frac[kSelMaxQ];
+  int nslots;
+};
+
+// warp w resolves rank w on the histogram of its slot: find the bin holding the k-th key
+__device__ __forceinline__ void resolve_level(SelState &S, const unsigned int *hist, int nr, int level) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < nr) {
+    const unsigned int *h = hist + S.slotOf[warp] * kSelBins;
+    const int per = level_bins(level) / 32;
+    unsigned long long mine = 0;
+    for (int b = 0; b < per; ++b) mine += h[lane * per + b];
+    unsigned long long incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const unsigned long long k = S.k[warp];
+    const unsigned owner = __ballot_sync(0xffffffffu, incl > k);
+    const int who = __ffs(owner) - 1;  // first lane whose inclusive count exceeds k (exists: k < population)
+    if (lane == who) {
+      unsigned long long acc = incl - mine;
+      int bin = lane * per;
+      for (;; ++bin) {
+        const unsigned long long c = h[bin];
+        if (acc + c > k) break;
+        acc += c;
+      }
+      S.prefix[warp] |= (uint64_t)bin << level_shift(level);
+      S.k[warp] = k - acc;
+      S.pop[warp] = h[bin];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // ranks ascend, so equal prefixes are adjacent
+    int ns = 0;
+    unsigned int base = 0;
+    for (int r = 0; r < nr; ++r) {
+      if (r > 0 && S.prefix[r] == S.prefix[r - 1]) {
+        S.slotOf[r] = ns - 1;
+        continue;
+      }
+      S.slotOf[r] = ns;
+      S.slotTop[ns] = S.prefix[r] >> level_shift(level);
+      S.slotBase[ns] = base;
+      base += S.pop[r];
+      ++ns;
+    }
+    S.slotBase[ns] = base;
+    S.nslots = ns;
+  }
+  __syncthreads();
+}
+
+// which slot (if any) a key belongs to once `level` levels are resolved
+__device__ __forceinline__ int slot_of_key(const SelState &S, uint64_t key, int level, int nslots) {
+  if (level == 0) return 0;
+  const uint64_t top = key >> level_shift(level - 1);
+  int slot = -1;
+  for (int s = 0; s < nslots; ++s)
+    if (S.slotTop[s] == top) slot = s;
+  return slot;
+}
+
+// ---- per-row summary: moments and exact quantiles in (typically) three reads of the row ----------
+// grid = (nsteps, nsites); block = kSelThreads; dynamic shared = kSelDynBytes.
+//   mean/var[site * momStride + t]              (either both or neither)
+//   quant[site * qStride + q * nsteps + t]      (nq <= kSelMaxQ)
+// Pass 1: finite count + sum (+ level-0 histogram when the row is longer than kCandCap).
+// Pass 2: sum of squared deviations (+ level-1 histogram).  Further histogram passes only while the
+// wanted prefixes still hold more than kCandCap keys (heavily duplicated data).  Last pass: the few keys
+// sharing a wanted prefix are compacted to shared memory, sorted (bitonic) and indexed.
+__global__ void __launch_bounds__(kSelThreads, 2)
+    row_summary_kernel(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, const double *probs, int nq,
+                       double *mean, double *var, int64_t momStride, double *quant, int64_t qStride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  unsigned int *hist = reinterpret_cast<unsigned int *>(dyn);
+  uint64_t *cand = reinterpret_cast<uint64_t *>(dyn);
+  __shared__ double red[kSelThreads];
+  __shared__ SelState S;
+  const int tid = threadIdx.x;
   const int64_t t = blockIdx.x;
   const int site = blockIdx.y;
   const SiteDev sd = sites[site];
+  const int count = sd.memberCount;
   const double *row = cols + t * ld + sd.member0;
-  double cnt = 0.0;
-  for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads)
-    if (isfinite(row[i])) cnt += 1.0;
-  const double nfin = block_sum(cnt, sh);
-  for (int q = 0; q < nq; ++q) {
-    double result = nan("");
-    if (nfin > 0) {
-      const double pos = probs[q] * (nfin - 1.0);
+  const int nr = 2 * nq;
+  const bool big = nq > 0 && count > kCandCap;
+
+  // ---- pass 1
+  if (big) {
+    for (int i = tid; i < kSelBins; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+  }
+  double s = 0.0, c = 0.0;
+  for (int i0 = 0; i0 < count; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    const double x = i < count ? row[i] : nan("");
+    const bool fin = isfinite(x);
+    if (fin) {
+      s += x;
+      c += 1.0;
+    }
+    if (big) hist_add(hist, fin ? (int)(key_of(x) >> 53) : -1);
+  }
+  const double total = block_sum(s, red);
+  const double n = block_sum(c, red);
+  const double mu = n > 0 ? total / n : nan("");
+  bool needSS = mean != nullptr && n > 0;
+  double q2 = 0.0;
+
+  if (nq > 0 && n > 0) {
+    if (tid < nq) {
+      const double pos = probs[tid] * (n - 1.0);
       const double lo = floor(pos);
-      const double frac = pos - lo;
-      const uint64_t klo = radix_select(row, sd.memberCount, (unsigned long long)lo, hist);
-      const double xlo = val_of(klo);
-      double xhi = xlo;
-      if (frac > 0.0) {
-        // x[lo+1]: equals x[lo] if enough duplicates, else the smallest element above it
-        double le = 0.0, above = __longlong_as_double(0x7FF0000000000000ll);
-        for (int i = threadIdx.x; i < sd.memberCount; i += kRedThreads) {
-          const double x = row[i];
-          if (isfinite(x)) {
-            if (x <= xlo) le += 1.0; else above = fmin(above, x);
-          }
-        }
-        const double nle = block_sum(le, sh);
-        sh[threadIdx.x] = above;
+      const double fr = pos - lo;
+      S.frac[tid] = fr;
+      S.k[2 * tid] = (unsigned long long)lo;
+      S.k[2 * tid + 1] = (unsigned long long)(fr > 0.0 ? lo + 1.0 : lo);
+    }
+    if (tid < nr) {
+      S.prefix[tid] = 0;
+      S.slotOf[tid] = 0;
+    }
+    if (tid == 0) {
+      S.nslots = 1;
+      S.slotBase[0] = 0;
+      S.slotBase[1] = (unsigned int)n;
+    }
+    __syncthreads();
+    int level = 0;
+    if (big) {
+      resolve_level(S, hist, nr, 0);
+      level = 1;
+      while (S.slotBase[S.nslots] > (unsigned)kCandCap && level < 6) {
+        const int nslots = S.nslots;
+        const int shift = level_shift(level), bmask = level_bins(level) - 1;
+        for (int i = tid; i < nslots * kSelBins; i += kSelThreads) hist[i] = 0;
         __syncthreads();
-        for (int s = kRedThreads / 2; s > 0; s >>= 1) {
-          if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+        for (int i0 = 0; i0 < count; i0 += kSelThreads) {
+          const int i = i0 + tid;
+          const double x = i < count ? row[i] : nan("");
+          int code = -1;
+          if (isfinite(x)) {
+            if (needSS) {
+              const double d = x - mu;
+              q2 += d * d;
+            }
+            const uint64_t key = key_of(x);
+            const int slot = slot_of_key(S, key, level, nslots);
+            if (slot >= 0) code = slot * kSelBins + (int)((key >> shift) & (uint64_t)bmask);
+          }
+          hist_add(hist, code);
+        }
+        needSS = false;  // accumulated (reduced below)
+        __syncthreads();
+        resolve_level(S, hist, nr, level);
+        ++level;
+      }
+    }
+    if (level < 6) {
+      // ---- compaction pass: keys sharing a wanted prefix -> shared memory
+      const int nslots = S.nslots;
+      const unsigned int ctot = S.slotBase[nslots];
+      if (tid < nslots) S.slotFill[tid] = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < count; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        const double x = i < count ? row[i] : nan("");
+        int slot = -1;
+        uint64_t key = 0;
+        if (isfinite(x)) {
+          if (needSS) {
+            const double d = x - mu;
+            q2 += d * d;
+          }
+          key = key_of(x);
+          slot = slot_of_key(S, key, level, nslots);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        const int leader = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (slot >= 0 && (tid & 31) == leader) base = atomicAdd(&S.slotFill[slot], (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (slot >= 0) cand[S.slotBase[slot] + base + __popc(peers & ((1u << (tid & 31)) - 1u))] = key;
+      }
+      needSS = false;
+      unsigned int n2 = 2;
+      while (n2 < ctot) n2 <<= 1;
+      __syncthreads();
+      for (unsigned int i = ctot + tid; i < n2; i += kSelThreads) cand[i] = ~0ull;
+      __syncthreads();
+      // slots hold ascending key ranges in ascending order, so one sort of the whole buffer sorts each slot in place
+      for (unsigned int kk = 2; kk <= n2; kk <<= 1) {
+        for (unsigned int j = kk >> 1; j > 0; j >>= 1) {
+          for (unsigned int i = tid; i < n2; i += kSelThreads) {
+            const unsigned int ixj = i ^ j;
+            if (ixj > i) {
+              const uint64_t a = cand[i], b = cand[ixj];
+              if ((a > b) == ((i & kk) == 0)) {
+                cand[i] = b;
+                cand[ixj] = a;
+              }
+            }
+          }
           __syncthreads();
         }
-        const double minAbove = sh[0];
-        __syncthreads();
-        xhi = (nle >= lo + 2.0) ? xlo : minAbove;
       }
-      // numpy's _lerp: a + (b - a) t, evaluated from the b side when t >= 0.5
-      result = (frac >= 0.5) ? xhi - (xhi - xlo) * (1.0 - frac) : xlo + (xhi - xlo) * frac;
+      if (tid < nr) S.prefix[tid] = cand[S.slotBase[S.slotOf[tid]] + (unsigned int)S.k[tid]];
+      __syncthreads();
     }
-    if (threadIdx.x == 0) out[(int64_t)site * siteStride + (int64_t)q * nsteps + t] = result;
+    // S.prefix[r] is now the complete key of order statistic r
+    if (tid < nq) {
+      const double xlo = val_of(S.prefix[2 * tid]), xhi = val_of(S.prefix[2 * tid + 1]);
+      const double fr = S.frac[tid];
+      // numpy's _lerp: a + (b - a) t, evaluated from the b side when t >= 0.5
+      quant[(int64_t)site * qStride + (int64_t)tid * nsteps + t] =
+          (fr >= 0.5) ? xhi - (xhi - xlo) * (1.0 - fr) : xlo + (xhi - xlo) * fr;
+    }
+  } else if (nq > 0 && tid < nq) {
+    quant[(int64_t)site * qStride + (int64_t)tid * nsteps + t] = nan("");
+  }
+
+  if (mean != nullptr) {
+    if (needSS) {  // no later pass carried the squared deviations (moments only)
+      for (int i = tid; i < count; i += kSelThreads) {
+        const double x = row[i];
+        if (isfinite(x)) {
+          const double d = x - mu;
+          q2 += d * d;
+        }
+      }
+    }
+    const double ss = block_sum(q2, red);
+    if (tid == 0) {
+      mean[(int64_t)site * momStride + t] = mu;
+      var[(int64_t)site * momStride + t] = n > 0 ? ss / n : nan("");
+    }
   }
 }
 
-cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
-                           int64_t nsites, double *mean, double *var, cudaStream_t stream) {
-  // gridDim.y is limited to 65535: tile sites
-  for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
-    const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
-    dim3 grid((unsigned)nsteps, (unsigned)ns);
-    moments_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, mean + s0 * siteStride,
-                                                     var + s0 * siteStride, siteStride);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+// ---- moments of short rows: one warp per (site, step) row, values held in registers ---------------
+// C3-shaped runs have 10^4 sites x 100 members: a block per row would idle most of its threads.
+// grid.x covers sites in groups of (blockDim / 32) -- neighbouring warps read neighbouring members --, grid.y = steps
+constexpr int kWarpRowsPerBlock = 8;
+__global__ void __launch_bounds__(kWarpRowsPerBlock * 32)
+    moments_warp_kernel(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, int64_t nsites, double *mean,
+                        double *var, int64_t momStride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t site = (int64_t)blockIdx.x * kWarpRowsPerBlock + (threadIdx.x >> 5);
+  const int64_t t = blockIdx.y;
+  if (site >= nsites) return;
+  const SiteDev sd = sites[site];
+  const double *row = cols + t * ld + sd.member0;
+  constexpr int kPer = kWarpRowMax / 32;
+  double x[kPer];
+  double s = 0.0, c = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = j * 32 + lane;
+    x[j] = i < sd.memberCount ? row[i] : nan("");
   }
-  return cudaSuccess;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j)
+    if (isfinite(x[j])) {
+      s += x[j];
+      c += 1.0;
+    }
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    c += __shfl_xor_sync(0xffffffffu, c, d);
+  }
+  const double mu = c > 0 ? s / c : nan("");
+  double q = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j)
+    if (isfinite(x[j])) {
+      const double d = x[j] - mu;
+      q += d * d;
+    }
+  for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  if (lane == 0) {
+    mean[site * momStride + t] = mu;
+    var[site * momStride + t] = c > 0 ? q / c : nan("");
+  }
 }
 
-cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
-                             int64_t nsites, const double *probs, int nq, double * /*scratch*/, double *out,
-                             cudaStream_t stream) {
-  for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {
-    const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
-    dim3 grid((unsigned)nsteps, (unsigned)ns);
-    quantiles_kernel<<<grid, kRedThreads, 0, stream>>>(cols, ld, nsteps, sites + s0, probs, nq,
-                                                       out + s0 * siteStride, siteStride);
-    cudaError_t e = cudaGetLastError();
+// One column's summaries for every (site, step) row.  mean/var may be null (quantiles only), nq may be 0.
+cudaError_t launch_row_summary(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, int64_t nsites,
+                               int64_t maxMembers, const double *probs, int nq, double *mean, double *var,
+                               int64_t momStride, double *quant, int64_t qStride, cudaStream_t stream) {
+  {
+    cudaError_t e = cudaFuncSetAttribute(row_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelDynBytes);
     if (e != cudaSuccess) return e;
+  }
+  if (nq == 0 && mean != nullptr && maxMembers <= kWarpRowMax) {
+    // gridDim.y <= 65535: tile steps
+    for (int64_t t0 = 0; t0 < nsteps; t0 += 65535) {
+      const int64_t nt = (nsteps - t0) < 65535 ? (nsteps - t0) : 65535;
+      dim3 grid((unsigned)((nsites + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock), (unsigned)nt);
+      moments_warp_kernel<<<grid, kWarpRowsPerBlock * 32, 0, stream>>>(cols + t0 * ld, ld, nsteps, sites, nsites,
+                                                                       mean + t0, var + t0, momStride);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  for (int q0 = 0; q0 < (nq > 0 ? nq : 1); q0 += kSelMaxQ) {
+    const int nqq = nq - q0 < kSelMaxQ ? nq - q0 : kSelMaxQ;
+    const bool first = q0 == 0;
+    for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {  // gridDim.y <= 65535: tile sites
+      const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
+      dim3 grid((unsigned)nsteps, (unsigned)ns);
+      row_summary_kernel<<<grid, kSelThreads, kSelDynBytes, stream>>>(
+          cols, ld, nsteps, sites + s0, nq > 0 ? probs + q0 : nullptr, nq > 0 ? nqq : 0,
+          first && mean ? mean + s0 * momStride : nullptr, first && var ? var + s0 * momStride : nullptr, momStride,
+          quant ? quant + s0 * qStride + (int64_t)q0 * nsteps : nullptr, qStride);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
   }
   return cudaSuccess;
 }

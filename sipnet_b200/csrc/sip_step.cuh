@@ -69,6 +69,7 @@ struct Member {
 // extended trackers, only carried by the DEBUG instantiation (restart/debug-log rows)
 struct MemberExt {
   double yGpp, yRtot, yRa, yRh, yNpp, yNee, yLitter, tGpp, tRtot, tRa, tRh, tNpp;
+  double harvRemoved, harvTransferred;  // eventTrackers of the last step (checkpoint payload only)
 };
 
 // ---- mean-NPP ring in HBM: slot s of member m at v[s * ld + m] -----------------
@@ -969,6 +970,10 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   t.evapotranspiration = (r.transpiration + r.immedEvap + r.evaporation + r.sublimation + r.eventEvap) * len;
   mb.wetFrac = nm.divs(oldSoilWater + mb.water, prm(kTwoWhc), prm(kSeedTwoWhc));
   if (DEBUG) ext.yLitter += r.leafLitter + r.eventLeafOffLitter;
+  if (DEBUG) {
+    ext.harvRemoved = harvRemoved;
+    ext.harvTransferred = harvTransferred;
+  }
   if (fl.on(F_GDD)) {
     mb.gdd += c.gdd;
   } else {

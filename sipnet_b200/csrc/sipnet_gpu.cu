@@ -35,11 +35,9 @@ cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers
                               uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
                               cudaStream_t stream);
 }  // namespace k1
-cudaError_t launch_moments(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
-                           int64_t nsites, double *mean, double *var, cudaStream_t stream);
-cudaError_t launch_quantiles(const double *cols, int64_t ld, int64_t nsteps, int64_t siteStride, const SiteDev *sites,
-                             int64_t nsites, const double *probs, int nq, double *scratch, double *out,
-                             cudaStream_t stream);
+cudaError_t launch_row_summary(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, int64_t nsites,
+                               int64_t maxMembers, const double *probs, int nq, double *mean, double *var,
+                               int64_t momStride, double *quant, int64_t qStride, cudaStream_t stream);
 cudaError_t measure_fp64_peak(int device, double *tflops);
 cudaError_t eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n);
 }  // namespace sip
@@ -68,7 +66,7 @@ struct sipnet_gpu_handle {
   uint32_t flags = 0;
   uint32_t outputs = 0;
   int math = 0;
-  int64_t nmembers = 0, ld = 0, nsites = 0, maxSteps = 0;
+  int64_t nmembers = 0, ld = 0, nsites = 0, maxSteps = 0, maxSiteMembers = 0;
   int64_t outCap = 0;      // steps of output kept per run
   int64_t stepsDone = 0;   // next step to run
   int64_t lastBegin = 0, lastEnd = 0;
@@ -236,6 +234,9 @@ static cudaError_t dalloc(T **p, size_t count) {
 }
 
 static int run_init_state(sipnet_gpu_handle *h) {
+  // rings start zeroed so that never-written slots read the same after a reset as after init
+  CUDA_OK(cudaMemsetAsync(h->ringV, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
+  CUDA_OK(cudaMemsetAsync(h->ringW, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
   cudaError_t e = k1::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state,
                                         h->ringV, h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
   h->launches++;
@@ -261,6 +262,8 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "unknown math mode %d", cfg->math);
   if (cfg->block_threads != 0 && cfg->block_threads != 32 && cfg->block_threads != 128)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "block_threads must be 0, 32 or 128");
+  if (cfg->ring_slots != 0 && (cfg->ring_slots < 2 || cfg->ring_slots > SIPNET_GPU_RING_SLOTS_REFERENCE))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "ring_slots must be 0 or in [2, %d]", SIPNET_GPU_RING_SLOTS_REFERENCE);
   if ((cfg->outputs & SIPNET_GPU_OUT_LOGLIK) && !(cfg->nee_sigma > 0))
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "nee_sigma must be > 0");
   if ((cfg->outputs & (SIPNET_GPU_OUT_MOMENTS | SIPNET_GPU_OUT_QUANTILES)) &&
@@ -371,6 +374,9 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   {
     double bound = std::floor(kMeanNppDays / minLen) + 3.0;
     h->ringCap = (int)std::min<double>(kRingMax, std::max(2.0, bound));
+    // an explicit slot count is honoured as given: fewer slots than `bound` can overflow (status bit) where the
+    // reference would not, the reference's own count reproduces its ring layout slot for slot
+    if (cfg->ring_slots != 0) h->ringCap = cfg->ring_slots;
   }
 
   // ---- members, blocks ----
@@ -385,6 +391,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
       m = m1;
     }
   }
+  for (const SiteDev &sd : h->hostSites) h->maxSiteMembers = std::max<int64_t>(h->maxSiteMembers, sd.memberCount);
   auto count_blocks = [&](int bt) {
     int64_t n = 0;
     for (const SiteDev &sd : h->hostSites) n += (sd.memberCount + bt - 1) / bt;
@@ -534,6 +541,40 @@ extern "C" int sipnet_gpu_reset(sipnet_gpu_handle *h) {
   if (!h) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle");
   CUDA_OK(cudaSetDevice(h->device));
   return run_init_state(h);
+}
+
+extern "C" int32_t sipnet_gpu_ring_slots(const sipnet_gpu_handle *h) { return h ? h->ringCap : 0; }
+
+extern "C" int sipnet_gpu_set_state(sipnet_gpu_handle *h, const double *state, int64_t state_ld, const double *ring_values,
+                                    const double *ring_weights, int64_t ring_ld, int64_t next_step) {
+  if (!h || !state) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "NULL handle or state");
+  if (state_ld < h->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "state_ld < nmembers");
+  if ((ring_values == nullptr) != (ring_weights == nullptr))
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "ring values and weights go together");
+  if (ring_values && ring_ld < h->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "ring_ld < nmembers");
+  if (next_step < 0 || next_step > h->maxSteps) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "next_step out of range");
+  // ring cursors index the device ring: reject what restartLoadCheckpoint() rejects (restart.c:976-981)
+  for (int64_t m = 0; m < h->nmembers; ++m) {
+    const double a = state[(size_t)SIPNET_S_meanStart * (size_t)state_ld + (size_t)m];
+    const double b = state[(size_t)SIPNET_S_meanLast * (size_t)state_ld + (size_t)m];
+    if (!(a >= 0 && a < h->ringCap && b >= 0 && b < h->ringCap))
+      return fail(SIPNET_GPU_ERR_BAD_RESTART, "mean-tracker cursor out of range for member %lld", (long long)m);
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t w = (size_t)h->nmembers * sizeof(double);
+  CUDA_OK(cudaMemcpy2DAsync(h->state, (size_t)h->ld * sizeof(double), state, (size_t)state_ld * sizeof(double), w,
+                            SIPNET_GPU_NSTATE, cudaMemcpyHostToDevice, h->stream));
+  if (ring_values) {
+    CUDA_OK(cudaMemcpy2DAsync(h->ringV, (size_t)h->ld * sizeof(double), ring_values, (size_t)ring_ld * sizeof(double), w,
+                              (size_t)h->ringCap, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpy2DAsync(h->ringW, (size_t)h->ld * sizeof(double), ring_weights, (size_t)ring_ld * sizeof(double), w,
+                              (size_t)h->ringCap, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stepsDone = next_step;
+  h->lastBegin = h->lastEnd = next_step;
+  h->summariesValid = false;
+  return 0;
 }
 
 // one contiguous segment; `outbuf` = where the column outputs of this segment go (h->out or one of its halves)
@@ -695,18 +736,12 @@ static int ensure_summaries(sipnet_gpu_handle *h) {
   for (int i = 0; i < ns; ++i) {
     const int slot = h->colSlot[h->summaryCols[(size_t)i]];
     const double *cols = h->out + (size_t)slot * n * h->ld;
-    if (h->mean) {
-      cudaError_t e = launch_moments(cols, h->ld, n, (int64_t)ns * n, h->sites, h->nsites, h->mean + (size_t)i * n,
-                                     h->var + (size_t)i * n, h->stream);
-      h->launches++;
-      if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "moments launch failed: %s", cudaGetErrorString(e));
-    }
-    if (h->quant) {
-      cudaError_t e = launch_quantiles(cols, h->ld, n, (int64_t)ns * nq * n, h->sites, h->nsites, h->qprobs, (int)nq,
-                                       h->qscratch, h->quant + (size_t)i * nq * n, h->stream);
-      h->launches++;
-      if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "quantile launch failed: %s", cudaGetErrorString(e));
-    }
+    cudaError_t e = launch_row_summary(cols, h->ld, n, h->sites, h->nsites, h->maxSiteMembers, h->qprobs,
+                                       h->quant ? (int)nq : 0, h->mean ? h->mean + (size_t)i * n : nullptr,
+                                       h->var ? h->var + (size_t)i * n : nullptr, (int64_t)ns * n,
+                                       h->quant ? h->quant + (size_t)i * nq * n : nullptr, (int64_t)ns * nq * n, h->stream);
+    h->launches++;
+    if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "summary launch failed: %s", cudaGetErrorString(e));
   }
   h->summariesValid = true;
   return 0;
@@ -724,6 +759,8 @@ extern "C" size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what) 
     case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglik ? M * 8 : 0;
     case SIPNET_GPU_GATHER_STATUS: return M * 4;
     case SIPNET_GPU_GATHER_STATE: return (size_t)SIPNET_GPU_NSTATE * M * 8;
+    case SIPNET_GPU_GATHER_RING_VALUES:
+    case SIPNET_GPU_GATHER_RING_WEIGHTS: return (size_t)h->ringCap * M * 8;
     case SIPNET_GPU_GATHER_MEAN:
     case SIPNET_GPU_GATHER_VARIANCE: return h->mean ? (size_t)h->nsites * ns * n * 8 : 0;
     case SIPNET_GPU_GATHER_QUANTILES: return h->quant ? (size_t)h->nsites * ns * h->quantiles.size() * n * 8 : 0;
@@ -756,6 +793,8 @@ extern "C" int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size
     case SIPNET_GPU_GATHER_LOGLIK_N: return copy_rows(h, dst, h->loglikN, 1, 8);
     case SIPNET_GPU_GATHER_STATUS: return copy_rows(h, dst, h->status, 1, 4);
     case SIPNET_GPU_GATHER_STATE: return copy_rows(h, dst, h->state, SIPNET_GPU_NSTATE, 8);
+    case SIPNET_GPU_GATHER_RING_VALUES: return copy_rows(h, dst, h->ringV, (size_t)h->ringCap, 8);
+    case SIPNET_GPU_GATHER_RING_WEIGHTS: return copy_rows(h, dst, h->ringW, (size_t)h->ringCap, 8);
     case SIPNET_GPU_GATHER_EVENT_COUNTS: return copy_rows(h, dst, h->recCount, 1, 4);
     case SIPNET_GPU_GATHER_EVENT_RECORDS:
       CUDA_OK(cudaMemcpyAsync(dst, h->recs, need, cudaMemcpyDeviceToHost, h->stream));
@@ -860,12 +899,12 @@ extern "C" int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t
   double *dprobs = nullptr;
   CUDA_OK(cudaMalloc(&dsite, sizeof(SiteDev)));
   CUDA_OK(cudaMemcpyAsync(dsite, &host, sizeof host, cudaMemcpyHostToDevice, st));
-  if (d_mean) CUDA_OK(launch_moments(d_rows, ld, nrows, nrows, dsite, 1, d_mean, d_var, st));
   if (nq > 0) {
     CUDA_OK(cudaMalloc(&dprobs, (size_t)nq * sizeof(double)));
     CUDA_OK(cudaMemcpyAsync(dprobs, probs, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_OK(launch_quantiles(d_rows, ld, nrows, (int64_t)nq * nrows, dsite, 1, dprobs, nq, nullptr, d_quant, st));
   }
+  CUDA_OK(launch_row_summary(d_rows, ld, nrows, dsite, 1, ncols, dprobs, nq, d_mean, d_var, nrows, d_quant,
+                             (int64_t)nq * nrows, st));
   CUDA_OK(cudaStreamSynchronize(st));
   cudaFree(dsite);
   if (dprobs) cudaFree(dprobs);

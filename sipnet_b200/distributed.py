@@ -121,26 +121,32 @@ def _all_to_all_gloo(recv, send, group=None):
                 dist.recv(recv[src], src, group=group)
 
 
-def rows_summary(rows: "torch.Tensor", probs: Sequence[float]):
+def rows_summary(rows: "torch.Tensor", probs: Sequence[float], moments: bool = True):
     """mean, variance, quantiles per row of a [nrows][ncols] tensor.  CUDA tensors go through the
-    library's reducers (sipnet_gpu_rows_summary); CPU tensors (gloo tests) through numpy."""
+    library's reducers (sipnet_gpu_rows_summary); CPU tensors (gloo tests) through numpy.
+    moments=False skips mean/variance (returned as None) when only the quantiles are wanted."""
     import torch
     probs = np.ascontiguousarray(probs, dtype=np.float64)
     if rows.is_cuda:
         from . import api
         lib = api.load_library()
         nrows, ncols = rows.shape
-        mean = torch.empty(nrows, dtype=torch.float64, device=rows.device)
-        var = torch.empty_like(mean)
+        mean = torch.empty(nrows, dtype=torch.float64, device=rows.device) if moments else None
+        var = torch.empty_like(mean) if moments else None
         quant = torch.empty((max(probs.size, 1), nrows), dtype=torch.float64, device=rows.device)
         rc = lib.sipnet_gpu_rows_summary(rows.device.index or 0, C.c_void_p(rows.data_ptr()), nrows, ncols, rows.stride(0),
-                                         C.c_void_p(probs.ctypes.data), int(probs.size), C.c_void_p(mean.data_ptr()),
-                                         C.c_void_p(var.data_ptr()), C.c_void_p(quant.data_ptr()),
+                                         C.c_void_p(probs.ctypes.data), int(probs.size),
+                                         C.c_void_p(mean.data_ptr() if moments else None),
+                                         C.c_void_p(var.data_ptr() if moments else None), C.c_void_p(quant.data_ptr()),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise api.SipnetGpuError(rc, (lib.sipnet_gpu_last_error() or b"").decode())
         return mean, var, quant[: probs.size]
     a = rows.numpy()
+    if not moments:
+        with np.errstate(invalid="ignore"):
+            fin = np.where(np.isfinite(a), a, np.nan)
+            return None, None, torch.from_numpy(np.ascontiguousarray(np.nanquantile(fin, probs, axis=1)))
     with np.errstate(invalid="ignore"):
         fin = np.where(np.isfinite(a), a, np.nan)
         mean = np.nanmean(fin, axis=1)

@@ -12,6 +12,7 @@
  *   <prefix>.out    per-step text rows               src/sipnet/sipnet.c:434-473
  *   events.out      applied / computed events        src/sipnet/events.c:369-418
  *   <prefix>.config final configuration dump         src/common/context.c:225-267
+ *   restart files   --restart-in / --restart-out      src/sipnet/restart.c (sip_restart.c)
  *
  * No function here calls exit(): each returns 0 or the reference's exit code
  * (src/common/exitCodes.h:16-27) and leaves a message in sip_host_error().
@@ -90,6 +91,43 @@ const char *sip_event_type_name(int type);                                      
 void sip_write_debug_headers(FILE *envi, FILE *fluxes, FILE *trackers);
 void sip_write_debug_rows(FILE *envi, FILE *fluxes, FILE *trackers, int year, int day, double time, const double *dbg,
                           int64_t stride);
+
+/* ---- restart checkpoints (sip_restart.c; reference src/sipnet/restart.c) --------------------------- */
+#define SIP_MODEL_VERSION "2.1.0"             /* NUMERIC_VERSION, version.h:4 -- checkpoints of another version are rejected */
+#define SIP_BUILD_INFO "2.1.0_(sipnet-b200)"  /* sanitizeBuildInfo(VERSION_STRING); a mismatch is only reported */
+#define SIP_RESTART_NENVI 13
+#define SIP_RESTART_NTRACKERS 33
+#define SIP_RESTART_RING SIPNET_GPU_RING_SLOTS_REFERENCE
+
+/* one member's checkpoint: the key/value payload of the reference's file (restart.c:150-308) */
+typedef struct sip_restart {
+  char modelVersion[32], buildInfo[96];
+  long long checkpointUtcEpoch, processedSteps;
+  sipnet_gpu_flags flags;
+  int boundaryYear, boundaryDay; /* the last processed climate record */
+  double boundaryTime, boundaryLength;
+  int meanLength, meanStart, meanLast; /* MeanTracker cursors (runmean.h) */
+  double meanTotWeight, meanSum;
+  double envi[SIP_RESTART_NENVI];         /* struct Environment order */
+  double trackers[SIP_RESTART_NTRACKERS]; /* struct TrackerVars order; [26] = lastYear */
+  int didLeafGrowth, didLeafFall, phenLastYear, isAlive;
+  double dTillMod, harvestFracRemoved, harvestFracTransferred;
+  double values[SIP_RESTART_RING], weights[SIP_RESTART_RING];
+} sip_restart;
+
+int sip_write_restart(const char *path, const sip_restart *r);  /* writeRestartState(), restart.c:784-827 */
+int sip_read_restart(const char *path, sip_restart *r);         /* readRestartState(), restart.c:593-757 */
+/* the checks of restartLoadCheckpoint() (restart.c:963-983) against the run's flags and first climate record */
+int sip_check_restart(const char *path, const sip_restart *r, const sip_context *ctx, const sip_site_data *site);
+int sip_check_restart_boundary_for_write(const char *path, const sip_restart *r, int quiet);
+/* checkpoint -> one member's column of sipnet_gpu_set_state() inputs (state[k * stride], ring[i * ringStride]) */
+void sip_restart_to_state(const sip_restart *r, double *state, int64_t stride, double *ringV, double *ringW,
+                          int64_t ringStride);
+/* gathered device results of one member -> checkpoint: SIPNET_GPU_GATHER_STATE column, the LAST step's row of
+ * SIPNET_GPU_GATHER_DEBUG (dbgLast[k * dbgStride]), SIPNET_GPU_GATHER_RING_VALUES / _WEIGHTS columns */
+void sip_restart_from_device(sip_restart *r, const sip_context *ctx, const sip_site_data *site, long long processedSteps,
+                             long long utcEpoch, const double *state, int64_t stride, const double *dbgLast,
+                             int64_t dbgStride, const double *ringV, const double *ringW, int64_t ringStride);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,9 @@
  * listed .param file on the same site in one launch; member k's outputs go to
  * <prefix>.out.<k> / events.out.<k>.
  * --debug-log <prefix> writes the reference's three per-step debug logs from the device's validation dump.
- * Not supported (outside the hot-path scope): --restart-in/--restart-out, --do-single-outputs (exit 8).
+ * --restart-in / --restart-out read and write the reference's checkpoint format (sip_restart.c), so a segmented
+ * run can alternate between this binary and the reference's.
+ * Not supported (outside the hot-path scope): --do-single-outputs (exit 8).
  */
 #define _GNU_SOURCE
 #include <stdlib.h>
@@ -31,10 +33,12 @@ int main(int argc, char **argv) {
   if (ctx.helpOrVersion) return 0;
   if ((rc = sip_read_input_file(&ctx))) return die(rc, sip_host_error());
   if ((rc = sip_validate_context(&ctx))) return die(rc, sip_host_error());
-  if (ctx.restartIn[0] || ctx.restartOut[0] || ctx.doSingleOutputs)
+  if (ctx.doSingleOutputs)
     return die(SIPNET_GPU_ERR_BAD_CLI,
-               "restart checkpoints and single-variable outputs are not part of the GPU hot path; "
-               "use the reference binary for those");
+               "single-variable outputs are not part of the GPU hot path; use the reference binary for those");
+  const int useRestart = ctx.restartIn[0] || ctx.restartOut[0];
+  if (useRestart && ctx.ensembleParamList[0])
+    return die(SIPNET_GPU_ERR_BAD_CLI, "a restart checkpoint holds one member: not available with --ensemble-params");
   if (ctx.debugLogPrefix[0] && ctx.ensembleParamList[0])
     return die(SIPNET_GPU_ERR_BAD_CLI, "--debug-log is a single-member feature");
   if ((rc = sip_derive_file_names(&ctx))) return die(rc, sip_host_error());
@@ -102,12 +106,23 @@ int main(int argc, char **argv) {
   cfg.params = params;
   cfg.params_ld = M;
   cfg.outputs = (ctx.doMainOutput ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0) |
-                (ctx.debugLogPrefix[0] ? SIPNET_GPU_OUT_DEBUG : 0);
+                ((ctx.debugLogPrefix[0] || ctx.restartOut[0]) ? SIPNET_GPU_OUT_DEBUG : 0);
+  /* checkpoints carry the reference's 250-slot mean-NPP ring slot for slot (restart.c:799-806) */
+  cfg.ring_slots = useRestart ? SIPNET_GPU_RING_SLOTS_REFERENCE : 0;
   cfg.math = ctx.validationMath ? SIPNET_GPU_MATH_VALIDATION : SIPNET_GPU_MATH_FAST;
   cfg.max_event_records = ctx.flags.events ? (int32_t)(site.nevents + 4 * (site.nsteps / 300 + 8)) : 0;
   sipnet_gpu_handle *h = NULL;
   if ((rc = sipnet_gpu_init(&cfg, &h))) return die(rc, sipnet_gpu_last_error());
   const int64_t T = site.nsteps;
+  if (ctx.restartIn[0]) { /* restartLoadCheckpoint() after setupModel()+setupEvents(), sipnet.c:1963-1967 */
+    sip_restart *rs = (sip_restart *)malloc(sizeof *rs);
+    double state[SIPNET_GPU_NSTATE], ringV[SIP_RESTART_RING], ringW[SIP_RESTART_RING];
+    if ((rc = sip_read_restart(ctx.restartIn, rs))) return die(rc, sip_host_error());
+    if ((rc = sip_check_restart(ctx.restartIn, rs, &ctx, &site))) return die(rc, sip_host_error());
+    sip_restart_to_state(rs, state, 1, ringV, ringW, 1);
+    if ((rc = sipnet_gpu_set_state(h, state, 1, ringV, ringW, 1, 0))) return die(rc, sipnet_gpu_last_error());
+    free(rs);
+  }
   if ((rc = sipnet_gpu_run(h, 0, T))) return die(rc, sipnet_gpu_last_error());
 
   uint32_t *status = (uint32_t *)malloc((size_t)M * sizeof *status);
@@ -161,6 +176,24 @@ int main(int argc, char **argv) {
       sip_write_debug_rows(f[0], f[1], f[2], site.year[t], site.day[t], site.time[t], dbg + t, T);
     for (int k = 0; k < 3; ++k) fclose(f[k]);
     free(dbg);
+  }
+  if (ctx.restartOut[0]) { /* restartWriteCheckpoint(), restart.c:908-961 */
+    if (T <= 0) return die(SIPNET_GPU_ERR_BAD_RESTART, "Cannot write restart checkpoint: no timestep processed");
+    sip_restart *rs = (sip_restart *)malloc(sizeof *rs);
+    double state[SIPNET_GPU_NSTATE], ringV[SIP_RESTART_RING], ringW[SIP_RESTART_RING];
+    const size_t n = (size_t)SIPNET_GPU_NDEBUG * (size_t)T;
+    double *dbg = (double *)malloc(n * sizeof(double));
+    if (!rs || !dbg) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
+    if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_STATE, state, sizeof state)) ||
+        (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_RING_VALUES, ringV, sizeof ringV)) ||
+        (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_RING_WEIGHTS, ringW, sizeof ringW)) ||
+        (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_DEBUG, dbg, n * sizeof(double))))
+      return die(rc, sipnet_gpu_last_error());
+    sip_restart_from_device(rs, &ctx, &site, (long long)T, (long long)time(NULL), state, 1, dbg + (T - 1), T, ringV, ringW, 1);
+    if ((rc = sip_check_restart_boundary_for_write(ctx.restartOut, rs, ctx.quiet))) return die(rc, sip_host_error());
+    if ((rc = sip_write_restart(ctx.restartOut, rs))) return die(rc, sip_host_error());
+    free(dbg);
+    free(rs);
   }
   if (ctx.flags.events) {
     const size_t nrec = (size_t)M * (size_t)cfg.max_event_records;

@@ -123,9 +123,44 @@ def debug_log_md5():
     print("debug log md5:", res)
 
 
+def restart_golden():
+    """A checkpoint written by the reference binary (russell_2 cut after 2016), the reference's verdict (exit
+    code) on every tampered variant in tests/restart_cases.py, and md5s of what the reference produces when it
+    resumes from the checkpoint -> tests/golden/restart_russell_2.ckpt, restart_cases.json"""
+    import json
+    import shutil
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from host_util import split_case, strip_volatile, unpack_smoke
+    from restart_cases import CASES
+    ref = os.path.join(ROOT, "oracle", "_ref", "sipnet_ref")
+    res = {"exit_codes": {}}
+    with tempfile.TemporaryDirectory() as td:
+        smoke = unpack_smoke(os.path.join(td, "smoke"))
+        a, b = os.path.join(td, "a"), os.path.join(td, "b")
+        split_case(os.path.join(smoke, "russell_2"), a, b, 2016)
+        subprocess.check_call([ref, "-i", "sipnet.in", "--quiet", "--restart-out", "ck"], cwd=a, stdout=subprocess.DEVNULL)
+        text = open(os.path.join(a, "ck")).read()
+        shutil.copy(os.path.join(a, "ck"), os.path.join(OUT, "restart_russell_2.ckpt"))
+        for name, mutate in CASES.items():
+            with open(os.path.join(b, "ck_in"), "w") as f:
+                f.write(mutate(text))
+            r = subprocess.run([ref, "-i", "sipnet.in", "--quiet", "--restart-in", "ck_in"], cwd=b, stdout=subprocess.DEVNULL)
+            res["exit_codes"][name] = r.returncode
+        subprocess.check_call([ref, "-i", "sipnet.in", "--quiet", "--restart-in", "../a/ck", "--restart-out", "ck2"], cwd=b,
+                              stdout=subprocess.DEVNULL)
+        res["segment1_out_md5"] = hashlib.md5(open(os.path.join(a, "sipnet.out"), "rb").read()).hexdigest()
+        res["segment2_out_md5"] = hashlib.md5(open(os.path.join(b, "sipnet.out"), "rb").read()).hexdigest()
+        res["segment2_events_md5"] = hashlib.md5(open(os.path.join(b, "events.out"), "rb").read()).hexdigest()
+        res["segment2_checkpoint_md5"] = hashlib.md5(strip_volatile(open(os.path.join(b, "ck2"), "rb").read())).hexdigest()
+    json.dump(res, open(os.path.join(OUT, "restart_cases.json"), "w"), indent=1)
+    print("restart golden:", res)
+
+
 def main():
     pack_smoke_inputs()
     debug_log_md5()
+    restart_golden()
     shim = RefShim()
     for name, flags in SMOKE.items():
         d = os.path.join(REF, "tests", "smoke", name)

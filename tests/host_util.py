@@ -100,3 +100,56 @@ def read_site_c(lib, clim_path, gdd, events_path=None, flags=None, params=None):
     out["events"] = [(e.year, e.day, e.type, e.method, e.p[0], e.p[1], e.p[2], e.p[3]) for e in s.events[:s.nevents]]
     lib.sip_site_free(C.byref(s))
     return 0, out
+
+
+# ---- restart checkpoints ---------------------------------------------------------------------------
+RESTART_RING = 250
+
+
+class RestartC(C.Structure):
+    """sip_restart (sipnet_b200/host/sip_host.h)."""
+    _fields_ = [("modelVersion", C.c_char * 32), ("buildInfo", C.c_char * 96),
+                ("checkpointUtcEpoch", C.c_longlong), ("processedSteps", C.c_longlong), ("flags", A.Flags),
+                ("boundaryYear", C.c_int), ("boundaryDay", C.c_int), ("boundaryTime", C.c_double),
+                ("boundaryLength", C.c_double), ("meanLength", C.c_int), ("meanStart", C.c_int), ("meanLast", C.c_int),
+                ("meanTotWeight", C.c_double), ("meanSum", C.c_double), ("envi", C.c_double * 13),
+                ("trackers", C.c_double * 33), ("didLeafGrowth", C.c_int), ("didLeafFall", C.c_int),
+                ("phenLastYear", C.c_int), ("isAlive", C.c_int), ("dTillMod", C.c_double),
+                ("harvestFracRemoved", C.c_double), ("harvestFracTransferred", C.c_double),
+                ("values", C.c_double * RESTART_RING), ("weights", C.c_double * RESTART_RING)]
+
+
+def restart_protos(lib):
+    lib.sip_read_restart.argtypes = [C.c_char_p, C.POINTER(RestartC)]
+    lib.sip_write_restart.argtypes = [C.c_char_p, C.POINTER(RestartC)]
+    lib.sip_check_restart.argtypes = [C.c_char_p, C.POINTER(RestartC), C.POINTER(ContextC), C.POINTER(SiteDataC)]
+    return lib
+
+
+def split_case(src: str, dst1: str, dst2: str, last_year_of_first: int):
+    """Cut a smoke case into two consecutive segments at a year boundary (climate AND events, as the
+    reference's restart contract asks: docs/developer-guide/restart-checkpoint.md)."""
+    for d in (dst1, dst2):
+        os.makedirs(d, exist_ok=True)
+        for fn in ("sipnet.in", "sipnet.param"):
+            shutil.copy(os.path.join(src, fn), d)
+    clim = open(os.path.join(src, "sipnet.clim")).read().splitlines(keepends=True)
+    ycol = 1 if len(clim[0].split()) == 14 else 0          # legacy files lead with a location column
+    with open(os.path.join(dst1, "sipnet.clim"), "w") as a, open(os.path.join(dst2, "sipnet.clim"), "w") as b:
+        for ln in clim:
+            (a if int(ln.split()[ycol]) <= last_year_of_first else b).write(ln)
+    ev = os.path.join(src, "events.in")
+    if os.path.exists(ev):
+        with open(os.path.join(dst1, "events.in"), "w") as a, open(os.path.join(dst2, "events.in"), "w") as b:
+            for ln in open(ev):
+                tok = ln.split()
+                if not tok or tok[0].startswith("#"):
+                    a.write(ln); b.write(ln)
+                    continue
+                (a if int(tok[0]) <= last_year_of_first else b).write(ln)
+
+
+def strip_volatile(restart_text: bytes) -> bytes:
+    """Drop the two lines that legitimately differ between writers (wall-clock stamp, build id)."""
+    return b"\n".join(ln for ln in restart_text.split(b"\n")
+                      if not ln.startswith((b"meta_info.checkpoint_utc_epoch", b"meta_info.build_info")))

@@ -87,3 +87,87 @@ def test_debug_log_byte_identical(smoke_dir, case):
     for k in ("envi", "fluxes", "trackers"):
         got = hashlib.md5(open(os.path.join(d, f"dbg_{k}.log"), "rb").read()).hexdigest()
         assert got == want[k], f"{case}: dbg_{k}.log differs from the reference's"
+
+
+# ---- restart checkpoints: hand a segmented run back and forth with the reference -----------
+import json  # noqa: E402
+
+from conftest import GOLDEN_DIR, ROOT  # noqa: E402
+from host_util import split_case, strip_volatile  # noqa: E402
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sipnet_ref")
+RESTART_GOLD = json.load(open(os.path.join(GOLDEN_DIR, "restart_cases.json")))
+RESTART_CKPT = os.path.join(GOLDEN_DIR, "restart_russell_2.ckpt")
+
+
+def _run(binary, cwd, *extra):
+    r = subprocess.run([binary, "-i", "sipnet.in", "--quiet", *extra], cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r
+
+
+def _md5(path, strip=False):
+    data = open(path, "rb").read()
+    return hashlib.md5(strip_volatile(data) if strip else data).hexdigest()
+
+
+@pytest.mark.parametrize("math", ["fast", "validation"])
+def test_restart_against_reference_goldens(smoke_dir, tmp_path, math):
+    """russell_2 cut after 2016.  Our checkpoint equals the reference's byte for byte (bar the time stamp and
+    build id lines); resuming from the REFERENCE's checkpoint reproduces the reference's second segment --
+    sipnet.out, events.out and the next checkpoint -- byte for byte."""
+    extra = ["--validation-math"] if math == "validation" else []
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    split_case(os.path.join(smoke_dir, "russell_2"), a, b, 2016)
+    _run(DRIVER, a, "--restart-out", "ck", *extra)
+    assert _md5(os.path.join(a, "sipnet.out")) == RESTART_GOLD["segment1_out_md5"]
+    assert strip_volatile(open(os.path.join(a, "ck"), "rb").read()) == strip_volatile(open(RESTART_CKPT, "rb").read())
+    for ck in (RESTART_CKPT, os.path.join(a, "ck")):               # the reference's checkpoint, then our own
+        _run(DRIVER, b, "--restart-in", ck, "--restart-out", "ck2", *extra)
+        assert _md5(os.path.join(b, "sipnet.out")) == RESTART_GOLD["segment2_out_md5"]
+        assert _md5(os.path.join(b, "events.out")) == RESTART_GOLD["segment2_events_md5"]
+        assert _md5(os.path.join(b, "ck2"), strip=True) == RESTART_GOLD["segment2_checkpoint_md5"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/sipnet_ref not built")
+@pytest.mark.parametrize("case,year", [("niwot", 2000), ("russell_3", 2016), ("russell_1", 2016)])
+def test_restart_round_trip_with_live_reference(smoke_dir, tmp_path, case, year):
+    """ours -> reference -> ours: every hand-over through a checkpoint file, each leg compared with the reference
+    running the whole chain on its own."""
+    legs = {}
+    for who, binary in (("ref", REF_BIN), ("ours", DRIVER)):
+        a, b = str(tmp_path / who / "a"), str(tmp_path / who / "b")
+        split_case(os.path.join(smoke_dir, case), a, b, year)
+        _run(binary, a, "--restart-out", "ck")
+        legs[who] = (a, b)
+    ra, rb = legs["ref"]
+    oa, ob = legs["ours"]
+    assert strip_volatile(open(os.path.join(oa, "ck"), "rb").read()) == strip_volatile(open(os.path.join(ra, "ck"), "rb").read())
+    _run(REF_BIN, rb, "--restart-in", os.path.join(oa, "ck"), "--restart-out", "ck2")     # reference resumes from OUR file
+    _run(DRIVER, ob, "--restart-in", os.path.join(ra, "ck"), "--restart-out", "ck2")      # we resume from the REFERENCE's
+    for f in ("sipnet.out", "events.out"):
+        assert open(os.path.join(ob, f), "rb").read() == open(os.path.join(rb, f), "rb").read(), f
+    assert _md5(os.path.join(ob, "ck2"), strip=True) == _md5(os.path.join(rb, "ck2"), strip=True)
+    # and the two segments together are the unsegmented run (testRestartMVP.c:253-297)
+    whole = str(tmp_path / "whole")
+    os.makedirs(whole)
+    for fn in os.listdir(os.path.join(smoke_dir, case)):
+        if fn.endswith((".in", ".param", ".clim")):
+            import shutil
+            shutil.copy(os.path.join(smoke_dir, case, fn), whole)
+    _run(DRIVER, whole)
+    header = 1 if b"year" in open(os.path.join(whole, "sipnet.out"), "rb").readline() else 0
+    seg = open(os.path.join(oa, "sipnet.out"), "rb").read().splitlines()[header:] + \
+        open(os.path.join(ob, "sipnet.out"), "rb").read().splitlines()[header:]
+    assert open(os.path.join(whole, "sipnet.out"), "rb").read().splitlines()[header:] == seg
+
+
+def test_restart_errors_exit_like_the_reference(smoke_dir, tmp_path):
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    split_case(os.path.join(smoke_dir, "russell_2"), a, b, 2016)
+    run = lambda cwd, *extra: subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", *extra], cwd=cwd,  # noqa: E731
+                                             capture_output=True, text=True).returncode
+    assert run(b, "--restart-in", "does-not-exist") == 6
+    assert run(a, "--restart-in", RESTART_CKPT) == 9                  # the checkpoint does not precede this segment
+    assert run(b, "--restart-in", RESTART_CKPT, "--no-nitrogen-cycle") == 9
+    assert run(b, "--restart-in", RESTART_CKPT) == 0

@@ -283,3 +283,40 @@ def test_run_to_host_pipeline_equals_run_plus_gather():
     assert np.array_equal(dst, ref["out"][:, 1000:], equal_nan=True)
     assert np.array_equal(ens.state(), ref["state"], equal_nan=True)
     ens.close()
+
+
+def test_set_state_resumes_a_run_exactly():
+    """sipnet_gpu_set_state (restartLoadCheckpoint semantics): state + ring gathered after the first part of a run
+    and loaded into a FRESH handle continue bit-identically, for an ensemble with the full event schedule, in both
+    ring layouts (compact and the reference's 250 slots), debug rows (yearly/total trackers) included."""
+    site = synth.synth_site(4, 3, "unequal", with_events=True)
+    P = synth.synth_params(96, stream=9)
+    T, cut = site.nsteps, 1111
+    for slots, outputs, math in ((0, A.OUT_FULL, A.MATH_FAST), (A.RING_SLOTS_REFERENCE, A.OUT_FULL | A.OUT_DEBUG, A.MATH_VALIDATION)):
+        kw = dict(outputs=outputs | A.OUT_EVENTS, math=math, ring_slots=slots, max_event_records=400)
+        whole = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, **kw)
+        assert whole.ring_slots == (slots or whole.ring_slots) and (slots == 0 or whole.ring_slots == 250)
+        whole.run(0, T)
+        want, want_state = whole.output(), whole.state()
+        want_ring = whole.ring()
+        want_dbg = whole.debug() if outputs & A.OUT_DEBUG else None
+        first = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, **kw)
+        first.run(0, cut)
+        state, (rv, rw) = first.state(), first.ring()
+        first.close()
+        second = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, **kw)
+        second.set_state(state, rv, rw, next_step=cut)
+        second.run(cut, T)
+        assert np.array_equal(second.output(), want[:, cut:], equal_nan=True)
+        assert np.array_equal(second.state(), want_state, equal_nan=True)
+        got_ring = second.ring()
+        assert np.array_equal(got_ring[0], want_ring[0]) and np.array_equal(got_ring[1], want_ring[1])
+        if want_dbg is not None:
+            assert np.array_equal(second.debug(), want_dbg[:, cut:], equal_nan=True)
+        # a cursor outside the ring is rejected like restart.c:976-981
+        bad = state.copy()
+        bad[A.S["meanLast"], 3] = second.ring_slots
+        with pytest.raises(api.SipnetGpuError) as e:
+            second.set_state(bad, rv, rw, next_step=cut)
+        assert e.value.code == 9
+        whole.close(); second.close()

@@ -93,3 +93,55 @@ def test_rows_summary_and_zero_copy_view():
     view = D.DeviceArray(ens.device_ptr(A.GATHER_FULL), (A.NOUT, site.nsteps, 48)).tensor()
     assert np.array_equal(view.cpu().numpy(), ens.output(), equal_nan=True)
     ens.close()
+
+
+@pytest.mark.parametrize("kind", ["normal", "wide", "duplicates", "constant", "nan-heavy", "two-values"])
+def test_rows_summary_long_rows(kind):
+    """Rows longer than the in-shared-memory candidate buffer take the histogram levels of the row kernel:
+    well-spread data (two levels), values spanning many binades and both signs, heavy duplication (levels
+    until the key is complete), a constant row, mostly-NaN rows; more quantiles than one launch handles."""
+    import torch
+    from sipnet_b200 import distributed as D
+    rng = np.random.default_rng(11)
+    n, m = 6, 70001
+    if kind == "normal":
+        x = rng.normal(3.0, 2.0, size=(n, m))
+    elif kind == "wide":
+        x = rng.normal(size=(n, m)) * 10.0 ** rng.integers(-30, 30, size=(n, m))
+        x[:, ::7] = 0.0
+        x[:, 1::97] = -0.0
+    elif kind == "duplicates":
+        x = rng.integers(0, 4, size=(n, m)).astype(np.float64) * 0.1
+    elif kind == "constant":
+        x = np.full((n, m), -7.25)
+    elif kind == "nan-heavy":
+        x = rng.normal(size=(n, m))
+        x[rng.uniform(size=(n, m)) < 0.9] = np.nan
+        x[0, :] = np.nan                                      # a row with no finite value
+        x[1, 5:] = np.nan                                     # five finite values
+    else:
+        x = np.where(rng.uniform(size=(n, m)) < 0.5, 1.0, np.nextafter(1.0, 2.0))
+    qs = [0.0, 0.001, 0.05, 0.25, 0.5, 0.75, 0.999, 1.0]
+    mean, var, q = D.rows_summary(torch.from_numpy(x).cuda(), qs)
+    with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+        __import__("warnings").simplefilter("ignore")
+        want_mean, want_var = np.nanmean(x, axis=1), np.nanvar(x, axis=1)
+        want_q = np.nanquantile(x, qs, axis=1)
+    np.testing.assert_allclose(mean.cpu().numpy(), want_mean, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(var.cpu().numpy(), want_var, rtol=1e-9, atol=1e-300)
+    got = q.cpu().numpy()
+    np.testing.assert_allclose(got, want_q, rtol=4e-16, atol=0)
+    assert np.array_equal(np.isnan(got), np.isnan(want_q))
+    # the order statistics themselves are exact
+    fin = np.where(np.isnan(x), np.inf, x)
+    has = np.isfinite(fin).any(axis=1)
+    assert np.array_equal(got[0][has], fin.min(axis=1)[has])
+
+
+def test_rows_summary_is_deterministic():
+    import torch
+    from sipnet_b200 import distributed as D
+    x = torch.from_numpy(np.random.default_rng(3).normal(size=(4, 100003))).cuda()
+    a = [t.cpu().numpy() for t in D.rows_summary(x, QS)]
+    b = [t.cpu().numpy() for t in D.rows_summary(x, QS)]
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
