@@ -114,11 +114,13 @@ int main(int argc, char **argv) {
   sipnet_gpu_handle *h = NULL;
   if ((rc = sipnet_gpu_init(&cfg, &h))) return die(rc, sipnet_gpu_last_error());
   const int64_t T = site.nsteps;
+  long long processedBefore = 0; /* meta_info.processed_steps keeps counting across segments (restart.c:160, 905) */
   if (ctx.restartIn[0]) { /* restartLoadCheckpoint() after setupModel()+setupEvents(), sipnet.c:1963-1967 */
     sip_restart *rs = (sip_restart *)malloc(sizeof *rs);
     double state[SIPNET_GPU_NSTATE], ringV[SIP_RESTART_RING], ringW[SIP_RESTART_RING];
     if ((rc = sip_read_restart(ctx.restartIn, rs))) return die(rc, sip_host_error());
     if ((rc = sip_check_restart(ctx.restartIn, rs, &ctx, &site))) return die(rc, sip_host_error());
+    processedBefore = rs->processedSteps;
     sip_restart_to_state(rs, state, 1, ringV, ringW, 1);
     if ((rc = sipnet_gpu_set_state(h, state, 1, ringV, ringW, 1, 0))) return die(rc, sipnet_gpu_last_error());
     free(rs);
@@ -189,7 +191,7 @@ int main(int argc, char **argv) {
         (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_RING_WEIGHTS, ringW, sizeof ringW)) ||
         (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_DEBUG, dbg, n * sizeof(double))))
       return die(rc, sipnet_gpu_last_error());
-    sip_restart_from_device(rs, &ctx, &site, (long long)T, (long long)time(NULL), state, 1, dbg + (T - 1), T, ringV, ringW, 1);
+    sip_restart_from_device(rs, &ctx, &site, processedBefore + (long long)T, (long long)time(NULL), state, 1, dbg + (T - 1), T, ringV, ringW, 1);
     if ((rc = sip_check_restart_boundary_for_write(ctx.restartOut, rs, ctx.quiet))) return die(rc, sip_host_error());
     if ((rc = sip_write_restart(ctx.restartOut, rs))) return die(rc, sip_host_error());
     free(dbg);
