@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = the bench workload (default); c3/c4/c5 = the other BASELINE.json configs (extra lines)")
     ap.add_argument("--sites", type=int, default=0, help="c3: number of sites on this GPU (default 10000 / n_gpus)")
+    ap.add_argument("--cap", type=int, default=0, help="c4: steps per run segment kept on the device (0 = the whole run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -416,7 +417,8 @@ def run_other_config(args):
         sites = [synth.synth_site(0, args.years, "half-daily")]
         params = synth.synth_params(M, stream=100 + rank)
         ms, flags = np.zeros(M, np.int32), dict(synth.SYNTH_FLAGS)
-        kw = dict(outputs=A.OUT_MOMENTS, summary_cols=[A.O["nee"], A.O["gpp"]], out_steps_capacity=512)
+        # the two summary columns of the whole run stay on the device (15 GB at 131072 members): one launch per kernel
+        kw = dict(outputs=A.OUT_MOMENTS, summary_cols=[A.O["nee"], A.O["gpp"]], out_steps_capacity=args.cap)
         name = f"C4: {total} members x {args.years} yr on {world} GPU(s), on-device mean/variance + exact quantiles (NEE, GPP)"
     else:                          # c5: 256k draws scored by NEE log-likelihood
         total = args.members if args.members != 4096 else 1 << 18
@@ -432,7 +434,7 @@ def run_other_config(args):
     ens = api.Ensemble(sites, params, ms, flags, math=A.MATH_FAST, device=local, **kw)
     T = ens.max_steps
     M_local = params.shape[1]
-    cap = kw.get("out_steps_capacity", T)
+    cap = kw.get("out_steps_capacity", T) or T
     qs = [0.05, 0.5, 0.95]
 
     def one_pass(prof=None):

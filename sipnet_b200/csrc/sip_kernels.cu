@@ -102,48 +102,49 @@ struct Emitter {
 
 __device__ __forceinline__ void load_member(const RunArgs &a, const double *state, const uint32_t *status, int64_t m,
                                             Member &mb, MemberExt &ext, bool debug) {
+  // __ldcg: carried state may have been written by another SM earlier in this launch (dynamic scheduling)
   const double *s = state + m;
   const int64_t ld = a.ld;
-  mb.wood = s[SIPNET_S_plantWoodC * ld];
-  mb.leaf = s[SIPNET_S_plantLeafC * ld];
-  mb.soil = s[SIPNET_S_soilC * ld];
-  mb.water = s[SIPNET_S_soilWater * ld];
-  mb.litter = s[SIPNET_S_litterC * ld];
-  mb.snow = s[SIPNET_S_snow * ld];
-  mb.coarse = s[SIPNET_S_coarseRootC * ld];
-  mb.fine = s[SIPNET_S_fineRootC * ld];
-  mb.minN = s[SIPNET_S_minN * ld];
-  mb.orgN = s[SIPNET_S_soilOrgN * ld];
-  mb.litN = s[SIPNET_S_litterN * ld];
-  mb.storN = s[SIPNET_S_plantStorageN * ld];
-  mb.delta = s[SIPNET_S_plantCAccountingDelta * ld];
-  mb.gdd = s[SIPNET_S_gdd * ld];
-  mb.wetFrac = s[SIPNET_S_soilWetnessFrac * ld];
-  mb.totNee = s[SIPNET_S_totNee * ld];
-  mb.dTill = s[SIPNET_S_dTillMod * ld];
-  mb.ringSum = s[SIPNET_S_meanSum * ld];
-  mb.ringStart = (int)s[SIPNET_S_meanStart * ld];
-  mb.ringLast = (int)s[SIPNET_S_meanLast * ld];
-  mb.trkLastYear = (int)s[SIPNET_S_trackersLastYear * ld];
-  mb.phenLastYear = (int)s[SIPNET_S_phenLastYear * ld];
-  mb.didGrowth = (int)s[SIPNET_S_didLeafGrowth * ld];
-  mb.didFall = (int)s[SIPNET_S_didLeafFall * ld];
-  mb.status = status[m];
+  mb.wood = __ldcg(&s[SIPNET_S_plantWoodC * ld]);
+  mb.leaf = __ldcg(&s[SIPNET_S_plantLeafC * ld]);
+  mb.soil = __ldcg(&s[SIPNET_S_soilC * ld]);
+  mb.water = __ldcg(&s[SIPNET_S_soilWater * ld]);
+  mb.litter = __ldcg(&s[SIPNET_S_litterC * ld]);
+  mb.snow = __ldcg(&s[SIPNET_S_snow * ld]);
+  mb.coarse = __ldcg(&s[SIPNET_S_coarseRootC * ld]);
+  mb.fine = __ldcg(&s[SIPNET_S_fineRootC * ld]);
+  mb.minN = __ldcg(&s[SIPNET_S_minN * ld]);
+  mb.orgN = __ldcg(&s[SIPNET_S_soilOrgN * ld]);
+  mb.litN = __ldcg(&s[SIPNET_S_litterN * ld]);
+  mb.storN = __ldcg(&s[SIPNET_S_plantStorageN * ld]);
+  mb.delta = __ldcg(&s[SIPNET_S_plantCAccountingDelta * ld]);
+  mb.gdd = __ldcg(&s[SIPNET_S_gdd * ld]);
+  mb.wetFrac = __ldcg(&s[SIPNET_S_soilWetnessFrac * ld]);
+  mb.totNee = __ldcg(&s[SIPNET_S_totNee * ld]);
+  mb.dTill = __ldcg(&s[SIPNET_S_dTillMod * ld]);
+  mb.ringSum = __ldcg(&s[SIPNET_S_meanSum * ld]);
+  mb.ringStart = (int)__ldcg(&s[SIPNET_S_meanStart * ld]);
+  mb.ringLast = (int)__ldcg(&s[SIPNET_S_meanLast * ld]);
+  mb.trkLastYear = (int)__ldcg(&s[SIPNET_S_trackersLastYear * ld]);
+  mb.phenLastYear = (int)__ldcg(&s[SIPNET_S_phenLastYear * ld]);
+  mb.didGrowth = (int)__ldcg(&s[SIPNET_S_didLeafGrowth * ld]);
+  mb.didFall = (int)__ldcg(&s[SIPNET_S_didLeafFall * ld]);
+  mb.status = __ldcg(&status[m]);
   if (debug) {
-    ext.yGpp = s[SIPNET_S_yearlyGpp * ld];
-    ext.yRtot = s[SIPNET_S_yearlyRtot * ld];
-    ext.yRa = s[SIPNET_S_yearlyRa * ld];
-    ext.yRh = s[SIPNET_S_yearlyRh * ld];
-    ext.yNpp = s[SIPNET_S_yearlyNpp * ld];
-    ext.yNee = s[SIPNET_S_yearlyNee * ld];
-    ext.yLitter = s[SIPNET_S_yearlyLitter * ld];
-    ext.tGpp = s[SIPNET_S_totGpp * ld];
-    ext.tRtot = s[SIPNET_S_totRtot * ld];
-    ext.tRa = s[SIPNET_S_totRa * ld];
-    ext.tRh = s[SIPNET_S_totRh * ld];
-    ext.tNpp = s[SIPNET_S_totNpp * ld];
-    ext.harvRemoved = s[SIPNET_S_harvestFracRemoved * ld];
-    ext.harvTransferred = s[SIPNET_S_harvestFracTransferred * ld];
+    ext.yGpp = __ldcg(&s[SIPNET_S_yearlyGpp * ld]);
+    ext.yRtot = __ldcg(&s[SIPNET_S_yearlyRtot * ld]);
+    ext.yRa = __ldcg(&s[SIPNET_S_yearlyRa * ld]);
+    ext.yRh = __ldcg(&s[SIPNET_S_yearlyRh * ld]);
+    ext.yNpp = __ldcg(&s[SIPNET_S_yearlyNpp * ld]);
+    ext.yNee = __ldcg(&s[SIPNET_S_yearlyNee * ld]);
+    ext.yLitter = __ldcg(&s[SIPNET_S_yearlyLitter * ld]);
+    ext.tGpp = __ldcg(&s[SIPNET_S_totGpp * ld]);
+    ext.tRtot = __ldcg(&s[SIPNET_S_totRtot * ld]);
+    ext.tRa = __ldcg(&s[SIPNET_S_totRa * ld]);
+    ext.tRh = __ldcg(&s[SIPNET_S_totRh * ld]);
+    ext.tNpp = __ldcg(&s[SIPNET_S_totNpp * ld]);
+    ext.harvRemoved = __ldcg(&s[SIPNET_S_harvestFracRemoved * ld]);
+    ext.harvTransferred = __ldcg(&s[SIPNET_S_harvestFracTransferred * ld]);
   }
 }
 
@@ -205,58 +206,50 @@ __device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const 
 // segment) are integrated, starting again from the segment's start state (RunArgs::*Backup).
 constexpr int kLibmTabWords = 2 * 128 + 4 * 128;  // exp table + pow-log table, 6 KB
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 #ifndef SIP_MIN_BLOCKS_128
 #define SIP_MIN_BLOCKS_128 1
 #endif
+// One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
+// `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
-    run_kernel(const __grid_constant__ RunArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNTileRows][BLOCK]
-  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNTileRows * BLOCK);  // [2][kChunkSteps]
-  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
-  uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
-
-  const BlockDesc bd = a.blocks[blockIdx.x];
-  const SiteDev site = a.sites[bd.site];
+__device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t blk, int64_t itemBegin, int64_t itemEnd,
+                                         int &sc, double *tile, ClimRec *climBuf, uint64_t *libmTab, uint64_t *bars) {
   const int tid = threadIdx.x;
+  const BlockDesc bd = a.blocks[blk];
+  const SiteDev site = a.sites[bd.site];
   const int64_t m = (int64_t)bd.member0 + tid;
   bool active = tid < bd.count;
-  const FL fl(a.flags);
   if (REPLAY) {
     active = active && ((a.status[m] & SIPNET_GPU_ST_REPLAY) != 0) && ((a.statusBackup[m] & SIPNET_GPU_ST_REPLAY) == 0);
     if (!__syncthreads_or(active ? 1 : 0)) return;  // nothing to replay in this block (the normal case)
   }
 
-  const int64_t t0 = a.stepBegin;
-  const int64_t t1 = a.stepEnd < site.nsteps ? a.stepEnd : site.nsteps;
-  const int64_t nChunks = t1 > t0 ? (t1 - t0 + kChunkSteps - 1) / kChunkSteps : 0;
+  const int64_t t0 = itemBegin;
+  const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
 
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // parameter tile: coalesced global reads, column-per-thread shared layout
+  // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
   for (int k = 0; k < kNParamDev; ++k) {
     const int slot = tile_slot(k);
     if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
   }
-  if (NM::kFast) {  // libm tables -> shared memory (table lookups become LDS)
-    for (int i = tid; i < 2 * 128; i += BLOCK) libmTab[i] = libm::d_exp_tab[i];
-    for (int i = tid; i < 4 * 128; i += BLOCK) libmTab[2 * 128 + i] = libm::d_powlog_tab[i];
-  }
-  __syncthreads();
 
-  auto issue = [&](int64_t chunk) {
-    const int64_t cs = t0 + chunk * kChunkSteps;
+  auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, min(cs + kChunkSteps, t1)) as chunk `serial`
     const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
     const uint32_t bytes = (uint32_t)(n * sizeof(ClimRec));
-    uint64_t *bar = &bars[chunk & 1];
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(climBuf + (chunk & 1) * kChunkSteps, site.clim + cs, bytes, bar);
+    const int buf = serial & 1;
+    mbar_expect_tx(&bars[buf], bytes);
+    bulk_g2s(climBuf + buf * kChunkSteps, site.clim + cs, bytes, &bars[buf]);
   };
-  if (tid == 0 && nChunks > 0) issue(0);
+  if (tid == 0 && t1 > t0) issue(t0, sc);
 
   Member mb;
   MemberExt ext = {};
@@ -278,14 +271,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
       active = false;
       // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
       const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-      const int64_t n = (a.stepEnd < site.nsteps ? a.stepEnd : site.nsteps) - a.stepBegin;
+      const int64_t o0 = t0 - a.stepBegin, o1 = t1 - a.stepBegin;
       if (a.out != nullptr)
         for (int c = 0; c < SIPNET_GPU_NOUT; ++c)
           if (a.colSlot[c] >= 0)
-            for (int64_t t = 0; t < n; ++t) a.out[((int64_t)a.colSlot[c] * a.outSteps + t) * a.ld + m] = nanv;
+            for (int64_t t = o0; t < o1; ++t) a.out[((int64_t)a.colSlot[c] * a.outSteps + t) * a.ld + m] = nanv;
       if (a.dbg != nullptr)
         for (int k = 0; k < SIPNET_GPU_NDEBUG; ++k)
-          for (int64_t t = 0; t < n; ++t) a.dbg[((int64_t)k * a.outSteps + t) * a.ld + m] = nanv;
+          for (int64_t t = o0; t < o1; ++t) a.dbg[((int64_t)k * a.outSteps + t) * a.ld + m] = nanv;
     }
   }
   NM nm;
@@ -309,33 +302,92 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
   Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
                      site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
   if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
-    emit.ll = a.loglik[m];
-    emit.lln = a.loglikN[m];
+    emit.ll = __ldcg(&a.loglik[m]);
+    emit.lln = __ldcg(&a.loglikN[m]);
   }
 
-  for (int64_t chunk = 0; chunk < nChunks; ++chunk) {
-    if (tid == 0 && chunk + 1 < nChunks) issue(chunk + 1);  // buffer (chunk+1)&1 was released by the barrier below
-    mbar_wait(&bars[chunk & 1], (uint32_t)((chunk >> 1) & 1));
-    const ClimRec *cbuf = climBuf + (chunk & 1) * kChunkSteps;
-    const int64_t cs = t0 + chunk * kChunkSteps;
+  for (int64_t cs = t0; cs < t1; cs += kChunkSteps, ++sc) {
+    if (tid == 0 && cs + kChunkSteps < t1) issue(cs + kChunkSteps, sc + 1);  // that buffer was released by the barrier below
+    mbar_wait(&bars[sc & 1], (uint32_t)((sc >> 1) & 1));
+    const ClimRec *cbuf = climBuf + (sc & 1) * kChunkSteps;
     const int n = (int)((t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps);
     if (active) {
       for (int i = 0; i < n; ++i) {
         const int64_t t = cs + i;
-        emit.begin(t - t0, t);
+        emit.begin(t - a.stepBegin, t);
         rec.step = (int32_t)t;
         step<FL, DEBUG>(fl, nm, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, kc);
       }
     }
     __syncthreads();  // everyone is done reading this buffer before it is refilled
   }
-
   if (active) {
     if (NM::kFast && nm.bad) mb.status |= SIPNET_GPU_ST_REPLAY;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
     if (a.loglik != nullptr && site.neeObs != nullptr) {  // running sums continue across segments in step order
       a.loglik[m] = emit.ll;
       a.loglikN[m] = emit.lln;
+    }
+  }
+}
+
+// DYN = false: CTA b integrates block descriptor b over the whole step range of the launch.
+// DYN = true (persistent grid, one CTA per resident slot): work items are (block descriptor, sub-range of
+// itemSteps steps), handed out in sub-range-major order by an atomic counter, so a member count that fills a
+// fractional number of waves no longer leaves SMs idle.  Item (b, s) needs (b, s-1); items are claimed in order,
+// so the predecessor was claimed earlier by a running CTA that waits for nothing later -- no deadlock.
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
+    run_kernel(const __grid_constant__ RunArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNTileRows][BLOCK]
+  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNTileRows * BLOCK);  // [2][kChunkSteps]
+  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
+  uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
+
+  const int tid = threadIdx.x;
+  const FL fl(a.flags);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (NM::kFast) {  // libm tables -> shared memory (table lookups become LDS)
+    for (int i = tid; i < 2 * 128; i += BLOCK) libmTab[i] = libm::d_exp_tab[i];
+    for (int i = tid; i < 4 * 128; i += BLOCK) libmTab[2 * 128 + i] = libm::d_powlog_tab[i];
+  }
+  __syncthreads();
+
+  int sc = 0;
+  if constexpr (!DYN) {
+    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
+  } else {
+    __shared__ long long sItem;
+    const int64_t nsub = (a.stepEnd - a.stepBegin + a.itemSteps - 1) / a.itemSteps;
+    const int64_t nItems = (int64_t)a.nblocks * nsub;
+    for (;;) {
+      if (tid == 0) sItem = (long long)atomicAdd(a.workCounter, 1ull);
+      __syncthreads();
+      const int64_t w = sItem;
+      if (w >= nItems) break;
+      const int64_t sub = w / a.nblocks;
+      const int64_t blk = w - sub * a.nblocks;
+      if (sub > 0) {
+        if (tid == 0)
+          while (ld_acquire_u32(&a.progress[blk]) < (unsigned)sub) __nanosleep(256);
+        __syncthreads();
+        __threadfence();  // acquire side for every thread: the predecessor's state/ring/status stores are visible
+      }
+      const int64_t itemBegin = a.stepBegin + sub * (int64_t)a.itemSteps;
+      const int64_t itemEnd = itemBegin + a.itemSteps < a.stepEnd ? itemBegin + a.itemSteps : a.stepEnd;
+      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
+      __syncthreads();  // every member's state is stored ...
+      if (tid == 0) {   // ... before the sub-range is published (release)
+        const int64_t w1 = sItem;
+        const int64_t s1 = w1 / a.nblocks;
+        __threadfence();
+        st_release_u32(&a.progress[w1 - s1 * a.nblocks], (unsigned)(s1 + 1));
+      }
     }
   }
 }
@@ -471,14 +523,44 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
 
+constexpr int kItemSteps = 256;  // steps per dynamically scheduled work item (8 forcing chunks)
+constexpr int kDynamicMaxWaves = 3;  // dynamic scheduling below this many waves of block descriptors
+
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
   const size_t smem = sizeof(double) * kNTileRows * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
                       kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
-  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL>;
+  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<nblocks, BLOCK, smem, stream>>>(a);
+  RunArgs args = a;
+  args.nblocks = nblocks;
+  args.itemSteps = kItemSteps;
+  int grid = nblocks;
+  bool dynamic = false;
+  if constexpr (!REPLAY && !DEBUG && NM::kFast) {
+    if (a.workCounter != nullptr) {
+      // More block descriptors than resident CTAs, but only a few waves of them: whole waves would quantise the
+      // run time (1.4 waves cost 2), so a persistent grid pulls (block, sub-range) items instead.  With many waves
+      // the static grid's tail is small and its kernel is the (slightly) faster one.
+      auto dyn = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>;
+      int dev = 0, sms = 0, perSm = 0;
+      if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+      if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, BLOCK, smem)) != cudaSuccess) return e;
+      const int resident = sms * perSm;
+      if (resident > 0 && nblocks > resident && nblocks < kDynamicMaxWaves * resident) {
+        dynamic = true;
+        grid = resident;
+        dyn<<<grid, BLOCK, smem, stream>>>(args);
+        return cudaGetLastError();
+      }
+    }
+  }
+  (void)dynamic;
+  args.workCounter = nullptr;
+  kern<<<grid, BLOCK, smem, stream>>>(args);
   return cudaGetLastError();
 }
 

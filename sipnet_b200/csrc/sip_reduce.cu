@@ -44,6 +44,20 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
   return r;
 }
 
+// fixed-order block min / max (inputs may be +-inf, never NaN)
+__device__ __forceinline__ double block_minmax(double v, double *sh, bool wantMax) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = kSelThreads / 2; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] = wantMax ? fmax(sh[tid], sh[tid + s]) : fmin(sh[tid], sh[tid + s]);
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
 // order-preserving map double -> uint64 (ascending)
 __device__ __forceinline__ uint64_t key_of(double x) {
   const uint64_t b = (uint64_t)__double_as_longlong(x);
@@ -58,12 +72,20 @@ __device__ __forceinline__ double val_of(uint64_t k) {
 __device__ __forceinline__ int level_shift(int level) { return level < 5 ? 53 - 11 * level : 0; }
 __device__ __forceinline__ int level_bins(int level) { return level < 5 ? kSelBins : 512; }
 
-// one shared-memory atomic per distinct code in the warp (ensemble values crowd into a few bins of
-// the leading levels; unaggregated atomics would serialise 32-fold).  Executed by all 32 lanes.
+// Histogram update for all 32 lanes (code < 0: nothing to count).  Ensemble values crowd into a few bins of the
+// leading levels, where plain shared-memory atomics would serialise 32-fold: the lanes that agree with lane 0
+// are counted by one ballot and added once, the others add individually.
 __device__ __forceinline__ void hist_add(unsigned int *hist, int code) {
-  const unsigned peers = __match_any_sync(0xffffffffu, code);
-  if (code >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[code], (unsigned)__popc(peers));
+  const int lead = __shfl_sync(0xffffffffu, code, 0);
+  const unsigned same = __ballot_sync(0xffffffffu, code == lead);
+  if ((threadIdx.x & 31) == 0) {
+    if (lead >= 0) atomicAdd(&hist[lead], (unsigned)__popc(same));
+  } else if (code >= 0 && code != lead) {
+    atomicAdd(&hist[code], 1u);
+  }
 }
+
+constexpr int kSelUnroll = 4;  // independent row loads in flight per thread
 
 struct SelState {
   uint64_t prefix[kSelMaxRanks];       // resolved leading key bits of each wanted order statistic
@@ -71,6 +93,7 @@ struct SelState {
   unsigned int pop[kSelMaxRanks];      // how many keys share the prefix
   int slotOf[kSelMaxRanks];            // ranks with equal prefixes share a histogram slot
   uint64_t slotTop[kSelMaxRanks];      // prefix >> shift of the last resolved level
+  unsigned int slotTop32[kSelMaxRanks]; // the same while it still fits the key's high word (levels 0 and 1)
   unsigned int slotBase[kSelMaxRanks + 1];
   unsigned int slotFill[kSelMaxRanks];
   double frac[kSelMaxQ];
@@ -117,6 +140,7 @@ __device__ __forceinline__ void resolve_level(SelState &S, const unsigned int *h
       }
       S.slotOf[r] = ns;
       S.slotTop[ns] = S.prefix[r] >> level_shift(level);
+      S.slotTop32[ns] = (unsigned int)S.slotTop[ns];
       S.slotBase[ns] = base;
       base += S.pop[r];
       ++ns;
@@ -127,14 +151,102 @@ __device__ __forceinline__ void resolve_level(SelState &S, const unsigned int *h
   __syncthreads();
 }
 
-// which slot (if any) a key belongs to once `level` levels are resolved
-__device__ __forceinline__ int slot_of_key(const SelState &S, uint64_t key, int level, int nslots) {
+// The first two levels (22 key bits) live in the high word of the double: the passes that only need those
+// (level-0/1 histograms, compaction after level 1 -- i.e. all three passes of a typical row) classify an element
+// with 32-bit integer work.  HI32 = false is the general 64-bit path for deeper levels.
+__device__ __forceinline__ unsigned int key_hi_of(double x) {
+  const unsigned int hi = (unsigned int)__double2hiint(x);
+  return hi ^ ((unsigned int)((int)hi >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ bool finite_hi(double x) { return (((unsigned int)__double2hiint(x) >> 20) & 0x7ffu) != 0x7ffu; }
+
+template <bool HI32>
+__device__ __forceinline__ int slot_of(const SelState &S, double x, int level, int nslots) {
   if (level == 0) return 0;
-  const uint64_t top = key >> level_shift(level - 1);
   int slot = -1;
-  for (int s = 0; s < nslots; ++s)
-    if (S.slotTop[s] == top) slot = s;
+  if (HI32) {
+    const unsigned int top = key_hi_of(x) >> (level_shift(level - 1) - 32);
+    for (int s = 0; s < nslots; ++s)
+      if (S.slotTop32[s] == top) slot = s;
+  } else {
+    const uint64_t top = key_of(x) >> level_shift(level - 1);
+    for (int s = 0; s < nslots; ++s)
+      if (S.slotTop[s] == top) slot = s;
+  }
   return slot;
+}
+template <bool HI32>
+__device__ __forceinline__ int bin_of(double x, int shift, int bmask) {
+  return HI32 ? (int)((key_hi_of(x) >> (shift - 32)) & (unsigned int)bmask) : (int)((key_of(x) >> shift) & (uint64_t)bmask);
+}
+
+// one histogram pass at `level` over the row (optionally accumulating the squared deviations on the way)
+template <bool HI32>
+__device__ __forceinline__ void hist_pass(const double *row, int count, const SelState &S, unsigned int *hist, int level,
+                                          int nslots, bool needSS, double mu, double &q2) {
+  const int tid = threadIdx.x;
+  const int shift = level_shift(level), bmask = level_bins(level) - 1;
+  for (int i0 = 0; i0 < count; i0 += kSelUnroll * kSelThreads) {
+    double x[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int i = i0 + u * kSelThreads + tid;
+      x[u] = i < count ? row[i] : nan("");
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      int code = -1;
+      if (finite_hi(x[u])) {
+        if (needSS) {
+          const double d = x[u] - mu;
+          q2 += d * d;
+        }
+        const int slot = slot_of<HI32>(S, x[u], level, nslots);
+        if (slot >= 0) code = slot * kSelBins + bin_of<HI32>(x[u], shift, bmask);
+      }
+      hist_add(hist, code);
+    }
+  }
+}
+
+// keys sharing a wanted prefix (`level` levels resolved) -> shared memory, grouped by slot
+template <bool HI32>
+__device__ __forceinline__ void compact_pass(const double *row, int count, SelState &S, uint64_t *cand, int level,
+                                             int nslots, bool needSS, double mu, double &q2) {
+  const int tid = threadIdx.x, lane = threadIdx.x & 31;
+  for (int i0 = 0; i0 < count; i0 += kSelUnroll * kSelThreads) {
+    double x[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int i = i0 + u * kSelThreads + tid;
+      x[u] = i < count ? row[i] : nan("");
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      int slot = -1;
+      if (finite_hi(x[u])) {
+        if (needSS) {
+          const double d = x[u] - mu;
+          q2 += d * d;
+        }
+        slot = slot_of<HI32>(S, x[u], level, nslots);
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, slot >= 0);
+      if (any) {  // (rare on long rows) lanes of the first candidate's slot reserve their places with one atomic
+        const int lead = __shfl_sync(0xffffffffu, slot, __ffs(any) - 1);
+        const unsigned same = __ballot_sync(0xffffffffu, slot == lead);
+        const int leader = __ffs(same) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&S.slotFill[lead], (unsigned)__popc(same));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (slot == lead) {
+          cand[S.slotBase[slot] + base + __popc(same & ((1u << lane) - 1u))] = key_of(x[u]);
+        } else if (slot >= 0) {
+          cand[S.slotBase[slot] + atomicAdd(&S.slotFill[slot], 1u)] = key_of(x[u]);
+        }
+      }
+    }
+  }
 }
 
 // ---- per-row summary: moments and exact quantiles in (typically) three reads of the row ----------
@@ -168,23 +280,44 @@ __global__ void __launch_bounds__(kSelThreads, 2)
     __syncthreads();
   }
   double s = 0.0, c = 0.0;
-  for (int i0 = 0; i0 < count; i0 += kSelThreads) {
-    const int i = i0 + tid;
-    const double x = i < count ? row[i] : nan("");
-    const bool fin = isfinite(x);
-    if (fin) {
-      s += x;
-      c += 1.0;
+  double vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = -vmin;
+  for (int i0 = 0; i0 < count; i0 += kSelUnroll * kSelThreads) {
+    double x[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int i = i0 + u * kSelThreads + tid;
+      x[u] = i < count ? row[i] : nan("");
     }
-    if (big) hist_add(hist, fin ? (int)(key_of(x) >> 53) : -1);
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {  // per thread the elements are still accumulated in index order
+      const bool fin = finite_hi(x[u]);
+      if (fin) {
+        s += x[u];
+        c += 1.0;
+        if (big) {
+          vmin = fmin(vmin, x[u]);
+          vmax = fmax(vmax, x[u]);
+        }
+      }
+      if (big) hist_add(hist, fin ? (int)(key_hi_of(x[u]) >> 21) : -1);
+    }
   }
   const double total = block_sum(s, red);
   const double n = block_sum(c, red);
   const double mu = n > 0 ? total / n : nan("");
   bool needSS = mean != nullptr && n > 0;
   double q2 = 0.0;
+  // a constant row (GPP of a night step is exactly 0 for every member) would walk all six levels: settle it here
+  bool constantRow = false;
+  if (big && n > 0) {
+    vmin = block_minmax(vmin, red, false);
+    vmax = block_minmax(vmax, red, true);
+    constantRow = vmin == vmax;
+  }
 
-  if (nq > 0 && n > 0) {
+  if (constantRow) {
+    if (tid < nq) quant[(int64_t)site * qStride + (int64_t)tid * nsteps + t] = vmin;
+  } else if (nq > 0 && n > 0) {
     if (tid < nq) {
       const double pos = probs[tid] * (n - 1.0);
       const double lo = floor(pos);
@@ -209,24 +342,12 @@ __global__ void __launch_bounds__(kSelThreads, 2)
       level = 1;
       while (S.slotBase[S.nslots] > (unsigned)kCandCap && level < 6) {
         const int nslots = S.nslots;
-        const int shift = level_shift(level), bmask = level_bins(level) - 1;
         for (int i = tid; i < nslots * kSelBins; i += kSelThreads) hist[i] = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < count; i0 += kSelThreads) {
-          const int i = i0 + tid;
-          const double x = i < count ? row[i] : nan("");
-          int code = -1;
-          if (isfinite(x)) {
-            if (needSS) {
-              const double d = x - mu;
-              q2 += d * d;
-            }
-            const uint64_t key = key_of(x);
-            const int slot = slot_of_key(S, key, level, nslots);
-            if (slot >= 0) code = slot * kSelBins + (int)((key >> shift) & (uint64_t)bmask);
-          }
-          hist_add(hist, code);
-        }
+        if (level_shift(level) >= 32)
+          hist_pass<true>(row, count, S, hist, level, nslots, needSS, mu, q2);
+        else
+          hist_pass<false>(row, count, S, hist, level, nslots, needSS, mu, q2);
         needSS = false;  // accumulated (reduced below)
         __syncthreads();
         resolve_level(S, hist, nr, level);
@@ -239,26 +360,10 @@ __global__ void __launch_bounds__(kSelThreads, 2)
       const unsigned int ctot = S.slotBase[nslots];
       if (tid < nslots) S.slotFill[tid] = 0;
       __syncthreads();
-      for (int i0 = 0; i0 < count; i0 += kSelThreads) {
-        const int i = i0 + tid;
-        const double x = i < count ? row[i] : nan("");
-        int slot = -1;
-        uint64_t key = 0;
-        if (isfinite(x)) {
-          if (needSS) {
-            const double d = x - mu;
-            q2 += d * d;
-          }
-          key = key_of(x);
-          slot = slot_of_key(S, key, level, nslots);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, slot);
-        const int leader = __ffs(peers) - 1;
-        unsigned int base = 0;
-        if (slot >= 0 && (tid & 31) == leader) base = atomicAdd(&S.slotFill[slot], (unsigned)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (slot >= 0) cand[S.slotBase[slot] + base + __popc(peers & ((1u << (tid & 31)) - 1u))] = key;
-      }
+      if (level == 0 || level_shift(level - 1) >= 32)
+        compact_pass<true>(row, count, S, cand, level, nslots, needSS, mu, q2);
+      else
+        compact_pass<false>(row, count, S, cand, level, nslots, needSS, mu, q2);
       needSS = false;
       unsigned int n2 = 2;
       while (n2 < ctot) n2 <<= 1;

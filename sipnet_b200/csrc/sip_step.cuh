@@ -78,14 +78,25 @@ struct RingRef {
   double *w;
   int64_t ld;
   int cap;
-  __device__ __forceinline__ double &val(int s) const { return v[(int64_t)s * ld]; }
-  __device__ __forceinline__ double &wgt(int s) const { return w[(int64_t)s * ld]; }
+  // L2-coherent accesses: with dynamic scheduling consecutive sub-ranges of a member may run on different SMs
+  // within ONE launch, so ring slots must not be served from a stale L1 line
+#ifdef SIP_RING_L1  // measurement variant: default (L1-allocating) accesses
+  __device__ __forceinline__ double val(int s) const { return v[(int64_t)s * ld]; }
+  __device__ __forceinline__ double wgt(int s) const { return w[(int64_t)s * ld]; }
+  __device__ __forceinline__ void set_val(int s, double x) const { v[(int64_t)s * ld] = x; }
+  __device__ __forceinline__ void set_wgt(int s, double x) const { w[(int64_t)s * ld] = x; }
+#else
+  __device__ __forceinline__ double val(int s) const { return __ldcg(v + (int64_t)s * ld); }
+  __device__ __forceinline__ double wgt(int s) const { return __ldcg(w + (int64_t)s * ld); }
+  __device__ __forceinline__ void set_val(int s, double x) const { __stcg(v + (int64_t)s * ld, x); }
+  __device__ __forceinline__ void set_wgt(int s, double x) const { __stcg(w + (int64_t)s * ld, x); }
+#endif
 };
 
 __device__ __forceinline__ void ring_reset(Member &mb, const RingRef &rg, double v) {  // runmean.c:44-51
   mb.ringStart = mb.ringLast = 0;
-  rg.val(0) = v;
-  rg.wgt(0) = kMeanNppDays;
+  rg.set_val(0, v);
+  rg.set_wgt(0, kMeanNppDays);
   mb.ringSum = v * kMeanNppDays;
 }
 
@@ -102,7 +113,7 @@ __device__ __forceinline__ void ring_push(Member &mb, const RingRef &rg, double 
     const double wi = rg.wgt(i);
     const double vi = rg.val(i);
     if (wi > left) {
-      rg.wgt(i) = wi - left;
+      rg.set_wgt(i, wi - left);
       sum -= left * vi;
       left = 0;
     } else {
@@ -114,15 +125,15 @@ __device__ __forceinline__ void ring_push(Member &mb, const RingRef &rg, double 
   mb.ringStart = i;
   i = (mb.ringLast + 1 == rg.cap) ? 0 : mb.ringLast + 1;
   if (i == mb.ringStart) {  // out of space: reference restores and exits 7 (sipnet.c:1562-1569)
-    rg.wgt(i) = rg.wgt(i) + weight;
+    rg.set_wgt(i, rg.wgt(i) + weight);
     sum += weight * rg.val(i);
     mb.ringSum = sum;
     mb.status |= SIPNET_GPU_ST_RING_OVERFLOW;
     return;
   }
   mb.ringLast = i;
-  rg.val(i) = value;
-  rg.wgt(i) = weight;
+  rg.set_val(i, value);
+  rg.set_wgt(i, weight);
   sum += value * weight;
   mb.ringSum = sum;
 }
@@ -150,7 +161,7 @@ struct RecSink {
   int32_t step;
   __device__ __forceinline__ void add(Member &mb, int type, int variant, int nval, const double *v) const {
     if (count == nullptr) return;
-    const int n = *count;
+    const int n = __ldcg(count);  // L2-coherent, like the ring (see RingRef)
     if (recs != nullptr && n < maxRecs) {
       sipnet_gpu_event_record &r = recs[n];
       r.step = step;
@@ -161,7 +172,7 @@ struct RecSink {
     } else if (recs != nullptr) {
       mb.status |= SIPNET_GPU_ST_EVREC_OVERFLOW;
     }
-    *count = n + 1;
+    __stcg(count, n + 1);
   }
 };
 

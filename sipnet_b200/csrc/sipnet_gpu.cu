@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -98,6 +99,8 @@ struct sipnet_gpu_handle {
   sipnet_gpu_event_record *recs = nullptr;
   int32_t *recCount = nullptr;
   double *mean = nullptr, *var = nullptr, *quant = nullptr, *qprobs = nullptr, *qscratch = nullptr;
+  bool staticSched = false;
+  unsigned char *sched = nullptr;  // work counter (8 B, padded to 16) + per-block progress words (dynamic scheduling)
   // segment-start copies for the replay of members flagged by the optimistic kernel (MATH_FAST only)
   double *stateBk = nullptr, *ringVBk = nullptr, *ringWBk = nullptr, *loglikBk = nullptr, *loglikNBk = nullptr;
   uint32_t *statusBk = nullptr;
@@ -210,7 +213,7 @@ static void free_handle(sipnet_gpu_handle *h) {
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
                   h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant, h->qprobs,
                   h->qscratch, h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
-                  h->recCountBk};
+                  h->recCountBk, h->sched};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : h->siteAllocs)
@@ -482,6 +485,14 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     INIT_CUDA(dalloc(&h->qscratch, (size_t)h->ld * 2));
   }
 
+  {  // dynamic scheduling words: counter + one progress word per block descriptor
+    void *p = nullptr;
+    INIT_CUDA(cudaMalloc(&p, 16 + (size_t)h->nblocks * sizeof(unsigned int)));
+    h->sched = (unsigned char *)p;
+    const char *env = getenv("SIPNET_GPU_STATIC_SCHED");  // A/B switch for measurements: one CTA per block, whole range
+    h->staticSched = env && env[0] == '1';
+  }
+
   // ---- setupModel() on the device ----
   {
     int rc = derive_params(h);
@@ -654,6 +665,11 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
     a.loglikBackup = h->loglikBk;
     a.loglikNBackup = h->loglikNBk;
     a.recCountBackup = h->recCountBk;
+  }
+  if (!h->staticSched) {
+    CUDA_OK(cudaMemsetAsync(h->sched, 0, 16 + (size_t)h->nblocks * sizeof(unsigned int), h->stream));
+    a.workCounter = reinterpret_cast<unsigned long long *>(h->sched);
+    a.progress = reinterpret_cast<unsigned int *>(h->sched + 16);
   }
   CUDA_OK(cudaEventRecord(h->evStart, h->stream));
   cudaError_t e = k1::launch_run(a, h->nblocks, h->blockThreads, debug, optimistic ? 1 : 0, h->stream);

@@ -320,3 +320,61 @@ def test_set_state_resumes_a_run_exactly():
             second.set_state(bad, rv, rw, next_step=cut)
         assert e.value.code == 9
         whole.close(); second.close()
+
+
+def _run_summary(sites, P, ms, flags, static, **kw):
+    import os
+    os.environ["SIPNET_GPU_STATIC_SCHED"] = "1" if static else "0"
+    try:
+        ens = api.Ensemble(sites, P, ms, flags, math=A.MATH_FAST, **kw)
+    finally:
+        os.environ.pop("SIPNET_GPU_STATIC_SCHED", None)
+    T = ens.max_steps
+    res = []
+    for t0 in range(0, T, 600):                                  # segments that do not divide into work items evenly
+        ens.run(t0, min(T, t0 + 600))
+        res.append((ens.mean(), ens.variance()))
+    out = dict(state=ens.state(), status=ens.status(), ring=ens.ring(), moments=res,
+               loglik=ens.loglik() if kw["outputs"] & A.OUT_LOGLIK else None,
+               events=ens.event_counts() if kw["outputs"] & A.OUT_EVENTS else None)
+    ens.close()
+    return out
+
+
+def _same(a, b):
+    assert np.array_equal(a["state"], b["state"], equal_nan=True)
+    assert np.array_equal(a["status"], b["status"])
+    assert all(np.array_equal(x, y) for x, y in zip(a["ring"], b["ring"]))
+    for (m1, v1), (m2, v2) in zip(a["moments"], b["moments"]):
+        assert np.array_equal(m1, m2, equal_nan=True) and np.array_equal(v1, v2, equal_nan=True)
+    if a["loglik"] is not None:
+        assert np.array_equal(a["loglik"], b["loglik"])
+    if a["events"] is not None:
+        assert np.array_equal(a["events"], b["events"])
+
+
+def test_dynamic_scheduling_is_bit_identical(oracle):
+    """More member blocks than resident CTAs: the persistent grid hands out (block, 256-step sub-range) work items.
+    Same bits as one CTA per block over the whole range -- single site with log-likelihood, and many sites with
+    events and unequal record counts -- and the oracle on sampled members."""
+    # (1) one site, 40 000 members (313 blocks of 128 > 296 resident), NEE likelihood + moments
+    site = synth.synth_site(0, 2, "half-daily")
+    rc, done, o_out, _, _ = oracle.run(synth.SYNTH_FLAGS, synth.synth_params(1)[:, 0], site, want_debug=False)
+    site.nee_obs = synth.synth_obs(o_out[:, A.O["nee"]].copy())
+    P = synth.synth_params(40000, stream=31)
+    kw = dict(outputs=A.OUT_MOMENTS | A.OUT_LOGLIK, summary_cols=[A.O["nee"], A.O["soilWater"]], out_steps_capacity=600,
+              nee_sigma=0.7)
+    dyn = _run_summary([site], P, None, synth.SYNTH_FLAGS, False, **kw)
+    _same(dyn, _run_summary([site], P, None, synth.SYNTH_FLAGS, True, **kw))
+    for m in (0, 127, 128, 20011, 39999):                         # and the oracle for a few of them
+        rc, done, out, _, _ = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, want_debug=False)
+        assert rc == 0
+        assert dyn["state"][A.S["plantWoodC"], m] + dyn["state"][A.S["plantCAccountingDelta"], m] == out[-1, A.O["plantWoodC"]]
+        assert dyn["state"][A.S["soilC"], m] == out[-1, A.O["soilC"]] and dyn["state"][A.S["totNee"], m] == out[-1, A.O["cumNEE"]]
+    # (2) 400 sites x 100 members with the event schedule; every 7th site one year shorter
+    sites, P, ms, flags = synth.config_c3(nsites=400, members_per_site=100, nyears=2)
+    for s in range(0, 400, 7):
+        short = synth.synth_site(s, 1, "half-daily", with_events=True)
+        sites[s] = short
+    kw = dict(outputs=A.OUT_MOMENTS | A.OUT_EVENTS, summary_cols=[A.O["nee"]], out_steps_capacity=600, max_event_records=8)
+    _same(_run_summary(sites, P, ms, flags, False, **kw), _run_summary(sites, P, ms, flags, True, **kw))
