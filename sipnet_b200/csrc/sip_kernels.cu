@@ -1,396 +1,15 @@
-// sip_kernels.cu -- the fused step kernel (K1) and the setup kernels.
+// sip_kernels.cu -- setup kernels (setupModel() on the device) and the dispatcher of the fused step kernel K1.
 //
-// Compiled with -fmad=false: the model arithmetic keeps the reference's operation
-// order, and exp/pow/division are explicit operation sequences (sip_libm.cuh,
-// sip_num.cuh), so every kernel here is bit-identical to the reference binary.
-// Two numerics policies of the SAME arithmetic:
-//   FastNum  (production)  branch-free main paths + guard flag, ~2.3x fewer instructions
-//   ExactNum (validation / debug dump / replay of members the fast kernel flagged)
-//
-// K1 layout: one thread = one ensemble member; a block holds members of ONE
-// site, so forcing and the event schedule are block-uniform.  Per block:
-//   * the members' parameter rows are copied once into a shared-memory tile
-//     [kNParamDev][BLOCK] (conflict-free column access),
-//   * the site's ClimRec stream is staged chunk by chunk into a 2-deep shared
-//     memory ring with cp.async.bulk (TMA 1-D) completing on an mbarrier, so the
-//     copy of chunk i+1 overlaps the arithmetic of chunk i,
-//   * pools / trackers stay in registers for the whole run range and go back to
-//     the SoA state rows once at the end,
-//   * every requested output column is written with one coalesced streaming
-//     store per step (consecutive lanes = consecutive members = 256 B per warp).
+// K1 itself (run_item / run_kernel) is a template in sip_run.cuh, instantiated in sip_run_exact.cu and
+// sip_run_fast_*.cu.  Everything is compiled with -fmad=false: the model arithmetic keeps the reference's
+// operation order, and exp/pow/division are explicit operation sequences (sip_libm.cuh, sip_num.cuh), so every
+// kernel is bit-identical to the reference binary.
 #include <cuda_runtime.h>
 
 #include "sip_step.cuh"
 
 namespace sip {
 namespace k1 {
-
-constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 128 B = 4096 B
-
-// ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// ---- per-step output sink -----------------------------------------------------------
-// FULL = all 32 outputState() columns are kept, slot == column: the store address is one running
-// pointer bumped by a column stride (the emit calls come in column order).  Otherwise only the
-// columns with a slot (summary outputs) are stored.
-template <bool FULL>
-struct Emitter {
-  const RunArgs *a;
-  double *outp;  // a->out + m (null => no column output)
-  double *dbgp;  // a->dbg + m
-  int64_t tLocal;
-  const double *obs;  // site's observations or null
-  int64_t tSite;
-  double ll, lln;
-  char *cur;
-  int64_t colStride;  // BYTES between consecutive columns = outSteps * ld * 8
-  __device__ __forceinline__ void begin(int64_t tl, int64_t ts) {
-    tLocal = tl;
-    tSite = ts;
-    if (FULL) cur = reinterpret_cast<char *>(outp + tl * a->ld);
-  }
-  __device__ __forceinline__ void out(int col, double v) {
-    if (FULL) {
-      __stcs(reinterpret_cast<double *>(cur), v);
-      cur += colStride;
-    } else if (outp != nullptr) {
-      const int s = a->colSlot[col];
-      if (s >= 0) __stcs(outp + ((int64_t)s * a->outSteps + tLocal) * a->ld, v);
-    }
-  }
-  __device__ __forceinline__ void dbg(int k, double v) const {
-    if (dbgp != nullptr) __stcs(dbgp + ((int64_t)k * a->outSteps + tLocal) * a->ld, v);
-  }
-  __device__ __forceinline__ void nee(double v) {
-    if (obs != nullptr) {
-      const double o = __ldg(obs + tSite);
-      if (o == o) {  // NaN = no observation
-        const double d = (v - o) * a->invSigma;
-        ll += -0.5 * d * d + a->logNorm;
-        lln += 1.0;
-      }
-    }
-  }
-};
-
-__device__ __forceinline__ void load_member(const RunArgs &a, const double *state, const uint32_t *status, int64_t m,
-                                            Member &mb, MemberExt &ext, bool debug) {
-  // __ldcg: carried state may have been written by another SM earlier in this launch (dynamic scheduling)
-  const double *s = state + m;
-  const int64_t ld = a.ld;
-  mb.wood = __ldcg(&s[SIPNET_S_plantWoodC * ld]);
-  mb.leaf = __ldcg(&s[SIPNET_S_plantLeafC * ld]);
-  mb.soil = __ldcg(&s[SIPNET_S_soilC * ld]);
-  mb.water = __ldcg(&s[SIPNET_S_soilWater * ld]);
-  mb.litter = __ldcg(&s[SIPNET_S_litterC * ld]);
-  mb.snow = __ldcg(&s[SIPNET_S_snow * ld]);
-  mb.coarse = __ldcg(&s[SIPNET_S_coarseRootC * ld]);
-  mb.fine = __ldcg(&s[SIPNET_S_fineRootC * ld]);
-  mb.minN = __ldcg(&s[SIPNET_S_minN * ld]);
-  mb.orgN = __ldcg(&s[SIPNET_S_soilOrgN * ld]);
-  mb.litN = __ldcg(&s[SIPNET_S_litterN * ld]);
-  mb.storN = __ldcg(&s[SIPNET_S_plantStorageN * ld]);
-  mb.delta = __ldcg(&s[SIPNET_S_plantCAccountingDelta * ld]);
-  mb.gdd = __ldcg(&s[SIPNET_S_gdd * ld]);
-  mb.wetFrac = __ldcg(&s[SIPNET_S_soilWetnessFrac * ld]);
-  mb.totNee = __ldcg(&s[SIPNET_S_totNee * ld]);
-  mb.dTill = __ldcg(&s[SIPNET_S_dTillMod * ld]);
-  mb.ringSum = __ldcg(&s[SIPNET_S_meanSum * ld]);
-  mb.ringStart = (int)__ldcg(&s[SIPNET_S_meanStart * ld]);
-  mb.ringLast = (int)__ldcg(&s[SIPNET_S_meanLast * ld]);
-  mb.trkLastYear = (int)__ldcg(&s[SIPNET_S_trackersLastYear * ld]);
-  mb.phenLastYear = (int)__ldcg(&s[SIPNET_S_phenLastYear * ld]);
-  mb.didGrowth = (int)__ldcg(&s[SIPNET_S_didLeafGrowth * ld]);
-  mb.didFall = (int)__ldcg(&s[SIPNET_S_didLeafFall * ld]);
-  mb.status = __ldcg(&status[m]);
-  if (debug) {
-    ext.yGpp = __ldcg(&s[SIPNET_S_yearlyGpp * ld]);
-    ext.yRtot = __ldcg(&s[SIPNET_S_yearlyRtot * ld]);
-    ext.yRa = __ldcg(&s[SIPNET_S_yearlyRa * ld]);
-    ext.yRh = __ldcg(&s[SIPNET_S_yearlyRh * ld]);
-    ext.yNpp = __ldcg(&s[SIPNET_S_yearlyNpp * ld]);
-    ext.yNee = __ldcg(&s[SIPNET_S_yearlyNee * ld]);
-    ext.yLitter = __ldcg(&s[SIPNET_S_yearlyLitter * ld]);
-    ext.tGpp = __ldcg(&s[SIPNET_S_totGpp * ld]);
-    ext.tRtot = __ldcg(&s[SIPNET_S_totRtot * ld]);
-    ext.tRa = __ldcg(&s[SIPNET_S_totRa * ld]);
-    ext.tRh = __ldcg(&s[SIPNET_S_totRh * ld]);
-    ext.tNpp = __ldcg(&s[SIPNET_S_totNpp * ld]);
-    ext.harvRemoved = __ldcg(&s[SIPNET_S_harvestFracRemoved * ld]);
-    ext.harvTransferred = __ldcg(&s[SIPNET_S_harvestFracTransferred * ld]);
-  }
-}
-
-__device__ __forceinline__ void store_member(const RunArgs &a, int64_t m, const Member &mb, const MemberExt &ext,
-                                             bool debug) {
-  double *s = a.state + m;
-  const int64_t ld = a.ld;
-  s[SIPNET_S_plantWoodC * ld] = mb.wood;
-  s[SIPNET_S_plantLeafC * ld] = mb.leaf;
-  s[SIPNET_S_soilC * ld] = mb.soil;
-  s[SIPNET_S_soilWater * ld] = mb.water;
-  s[SIPNET_S_litterC * ld] = mb.litter;
-  s[SIPNET_S_snow * ld] = mb.snow;
-  s[SIPNET_S_coarseRootC * ld] = mb.coarse;
-  s[SIPNET_S_fineRootC * ld] = mb.fine;
-  s[SIPNET_S_minN * ld] = mb.minN;
-  s[SIPNET_S_soilOrgN * ld] = mb.orgN;
-  s[SIPNET_S_litterN * ld] = mb.litN;
-  s[SIPNET_S_plantStorageN * ld] = mb.storN;
-  s[SIPNET_S_plantCAccountingDelta * ld] = mb.delta;
-  s[SIPNET_S_gdd * ld] = mb.gdd;
-  s[SIPNET_S_soilWetnessFrac * ld] = mb.wetFrac;
-  s[SIPNET_S_totNee * ld] = mb.totNee;
-  s[SIPNET_S_dTillMod * ld] = mb.dTill;
-  s[SIPNET_S_meanSum * ld] = mb.ringSum;
-  s[SIPNET_S_meanStart * ld] = (double)mb.ringStart;
-  s[SIPNET_S_meanLast * ld] = (double)mb.ringLast;
-  s[SIPNET_S_trackersLastYear * ld] = (double)mb.trkLastYear;
-  s[SIPNET_S_phenLastYear * ld] = (double)mb.phenLastYear;
-  s[SIPNET_S_didLeafGrowth * ld] = (double)mb.didGrowth;
-  s[SIPNET_S_didLeafFall * ld] = (double)mb.didFall;
-  uint32_t st = mb.status;
-  if (!(isfinite(mb.wood) && isfinite(mb.leaf) && isfinite(mb.soil) && isfinite(mb.water) && isfinite(mb.litter) &&
-        isfinite(mb.snow) && isfinite(mb.coarse) && isfinite(mb.fine) && isfinite(mb.minN) && isfinite(mb.orgN) &&
-        isfinite(mb.litN) && isfinite(mb.storN) && isfinite(mb.delta))) {
-    st |= SIPNET_GPU_ST_NONFINITE;
-  }
-  a.status[m] = st;
-  if (debug) {
-    s[SIPNET_S_yearlyGpp * ld] = ext.yGpp;
-    s[SIPNET_S_yearlyRtot * ld] = ext.yRtot;
-    s[SIPNET_S_yearlyRa * ld] = ext.yRa;
-    s[SIPNET_S_yearlyRh * ld] = ext.yRh;
-    s[SIPNET_S_yearlyNpp * ld] = ext.yNpp;
-    s[SIPNET_S_yearlyNee * ld] = ext.yNee;
-    s[SIPNET_S_yearlyLitter * ld] = ext.yLitter;
-    s[SIPNET_S_totGpp * ld] = ext.tGpp;
-    s[SIPNET_S_totRtot * ld] = ext.tRtot;
-    s[SIPNET_S_totRa * ld] = ext.tRa;
-    s[SIPNET_S_totRh * ld] = ext.tRh;
-    s[SIPNET_S_totNpp * ld] = ext.tNpp;
-    s[SIPNET_S_harvestFracRemoved * ld] = ext.harvRemoved;
-    s[SIPNET_S_harvestFracTransferred * ld] = ext.harvTransferred;
-  }
-}
-
-// ---- K1: fused [events -> fluxes -> pools -> trackers -> mean tracker] over a step range ----
-// REPLAY = true: only members the optimistic kernel flagged (SIPNET_GPU_ST_REPLAY set during this
-// segment) are integrated, starting again from the segment's start state (RunArgs::*Backup).
-constexpr int kLibmTabWords = 2 * 128 + 4 * 128;  // exp table + pow-log table, 6 KB
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-#ifndef SIP_MIN_BLOCKS_128
-#define SIP_MIN_BLOCKS_128 1
-#endif
-// One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
-// `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
-__device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t blk, int64_t itemBegin, int64_t itemEnd,
-                                         int &sc, double *tile, ClimRec *climBuf, uint64_t *libmTab, uint64_t *bars) {
-  const int tid = threadIdx.x;
-  const BlockDesc bd = a.blocks[blk];
-  const SiteDev site = a.sites[bd.site];
-  const int64_t m = (int64_t)bd.member0 + tid;
-  bool active = tid < bd.count;
-  if (REPLAY) {
-    active = active && ((a.status[m] & SIPNET_GPU_ST_REPLAY) != 0) && ((a.statusBackup[m] & SIPNET_GPU_ST_REPLAY) == 0);
-    if (!__syncthreads_or(active ? 1 : 0)) return;  // nothing to replay in this block (the normal case)
-  }
-
-  const int64_t t0 = itemBegin;
-  const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
-
-  // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
-  for (int k = 0; k < kNParamDev; ++k) {
-    const int slot = tile_slot(k);
-    if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
-  }
-
-  auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, min(cs + kChunkSteps, t1)) as chunk `serial`
-    const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
-    const uint32_t bytes = (uint32_t)(n * sizeof(ClimRec));
-    const int buf = serial & 1;
-    mbar_expect_tx(&bars[buf], bytes);
-    bulk_g2s(climBuf + buf * kChunkSteps, site.clim + cs, bytes, &bars[buf]);
-  };
-  if (tid == 0 && t1 > t0) issue(t0, sc);
-
-  Member mb;
-  MemberExt ext = {};
-  if (active) {
-    if (REPLAY) {  // restore the member's segment-start state: ring columns, accumulators, status
-      for (int sl = 0; sl < a.ringCap; ++sl) {
-        a.ringV[(int64_t)sl * a.ld + m] = a.ringVBackup[(int64_t)sl * a.ld + m];
-        a.ringW[(int64_t)sl * a.ld + m] = a.ringWBackup[(int64_t)sl * a.ld + m];
-      }
-      if (a.loglik != nullptr) {
-        a.loglik[m] = a.loglikBackup[m];
-        a.loglikN[m] = a.loglikNBackup[m];
-      }
-      if (a.recCount != nullptr) a.recCount[m] = a.recCountBackup[m];
-    }
-    load_member(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
-    if (REPLAY) mb.status |= SIPNET_GPU_ST_REPLAY;
-    if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) {  // reference would have exited (sipnet.c:1117-1122)
-      active = false;
-      // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
-      const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-      const int64_t o0 = t0 - a.stepBegin, o1 = t1 - a.stepBegin;
-      if (a.out != nullptr)
-        for (int c = 0; c < SIPNET_GPU_NOUT; ++c)
-          if (a.colSlot[c] >= 0)
-            for (int64_t t = o0; t < o1; ++t) a.out[((int64_t)a.colSlot[c] * a.outSteps + t) * a.ld + m] = nanv;
-      if (a.dbg != nullptr)
-        for (int k = 0; k < SIPNET_GPU_NDEBUG; ++k)
-          for (int64_t t = o0; t < o1; ++t) a.dbg[((int64_t)k * a.outSteps + t) * a.ld + m] = nanv;
-    }
-  }
-  NM nm;
-  if constexpr (NM::kFast) {
-    nm.expTab = libmTab;
-    nm.powlogTab = libmTab + 2 * 128;
-    // the member-constant divisors must be ordinary numbers (sip_num.cuh divisor_check)
-    const int divisors[] = {SIPNET_P_leafCSpWt, kPsnTRangeSqSlot, SIPNET_P_halfSatPar, SIPNET_P_soilWHC, kTwoWhc,
-                            SIPNET_P_leafCN,    SIPNET_P_woodCN,  SIPNET_P_fineRootCN, SIPNET_P_fAnoxia, kOneMinusFa};
-    for (int k : divisors) nm.divisor_check(tile[tile_slot(k) * BLOCK + tid]);
-    if (fl.on(F_CSAT)) nm.divisor_check(tile[tile_slot(SIPNET_P_soilCSaturation) * BLOCK + tid]);
-  }
-  const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
-  const ParamTile prm{tile + tid, BLOCK};
-  const RingRef rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
-  RecSink rec{nullptr, nullptr, a.maxRecs, 0};
-  if (a.recCount != nullptr && active) {
-    rec.count = a.recCount + m;
-    rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
-  }
-  Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
-                     site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
-  if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
-    emit.ll = __ldcg(&a.loglik[m]);
-    emit.lln = __ldcg(&a.loglikN[m]);
-  }
-
-  for (int64_t cs = t0; cs < t1; cs += kChunkSteps, ++sc) {
-    if (tid == 0 && cs + kChunkSteps < t1) issue(cs + kChunkSteps, sc + 1);  // that buffer was released by the barrier below
-    mbar_wait(&bars[sc & 1], (uint32_t)((sc >> 1) & 1));
-    const ClimRec *cbuf = climBuf + (sc & 1) * kChunkSteps;
-    const int n = (int)((t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps);
-    if (active) {
-      for (int i = 0; i < n; ++i) {
-        const int64_t t = cs + i;
-        emit.begin(t - a.stepBegin, t);
-        rec.step = (int32_t)t;
-        step<FL, DEBUG>(fl, nm, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, kc);
-      }
-    }
-    __syncthreads();  // everyone is done reading this buffer before it is refilled
-  }
-  if (active) {
-    if (NM::kFast && nm.bad) mb.status |= SIPNET_GPU_ST_REPLAY;  // outside the optimistic guards: general kernel re-runs it
-    store_member(a, m, mb, ext, DEBUG);
-    if (a.loglik != nullptr && site.neeObs != nullptr) {  // running sums continue across segments in step order
-      a.loglik[m] = emit.ll;
-      a.loglikN[m] = emit.lln;
-    }
-  }
-}
-
-// DYN = false: CTA b integrates block descriptor b over the whole step range of the launch.
-// DYN = true (persistent grid, one CTA per resident slot): work items are (block descriptor, sub-range of
-// itemSteps steps), handed out in sub-range-major order by an atomic counter, so a member count that fills a
-// fractional number of waves no longer leaves SMs idle.  Item (b, s) needs (b, s-1); items are claimed in order,
-// so the predecessor was claimed earlier by a running CTA that waits for nothing later -- no deadlock.
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
-    run_kernel(const __grid_constant__ RunArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNTileRows][BLOCK]
-  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNTileRows * BLOCK);  // [2][kChunkSteps]
-  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
-  uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
-
-  const int tid = threadIdx.x;
-  const FL fl(a.flags);
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (NM::kFast) {  // libm tables -> shared memory (table lookups become LDS)
-    for (int i = tid; i < 2 * 128; i += BLOCK) libmTab[i] = libm::d_exp_tab[i];
-    for (int i = tid; i < 4 * 128; i += BLOCK) libmTab[2 * 128 + i] = libm::d_powlog_tab[i];
-  }
-  __syncthreads();
-
-  int sc = 0;
-  if constexpr (!DYN) {
-    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
-  } else {
-    __shared__ long long sItem;
-    const int64_t nsub = (a.stepEnd - a.stepBegin + a.itemSteps - 1) / a.itemSteps;
-    const int64_t nItems = (int64_t)a.nblocks * nsub;
-    for (;;) {
-      if (tid == 0) sItem = (long long)atomicAdd(a.workCounter, 1ull);
-      __syncthreads();
-      const int64_t w = sItem;
-      if (w >= nItems) break;
-      const int64_t sub = w / a.nblocks;
-      const int64_t blk = w - sub * a.nblocks;
-      if (sub > 0) {
-        if (tid == 0)
-          while (ld_acquire_u32(&a.progress[blk]) < (unsigned)sub) __nanosleep(256);
-        __syncthreads();
-        __threadfence();  // acquire side for every thread: the predecessor's state/ring/status stores are visible
-      }
-      const int64_t itemBegin = a.stepBegin + sub * (int64_t)a.itemSteps;
-      const int64_t itemEnd = itemBegin + a.itemSteps < a.stepEnd ? itemBegin + a.itemSteps : a.stepEnd;
-      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
-      __syncthreads();  // every member's state is stored ...
-      if (tid == 0) {   // ... before the sub-range is published (release)
-        const int64_t w1 = sItem;
-        const int64_t s1 = w1 / a.nblocks;
-        __threadfence();
-        st_release_u32(&a.progress[w1 - s1 * a.nblocks], (unsigned)(s1 + 1));
-      }
-    }
-  }
-}
 
 // ---- setup kernels: setupModel(), sipnet.c:1858-1951 ----------------------------------------
 // (1) parameter derivation, in place on the uploaded raw rows
@@ -523,73 +142,28 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
 
-constexpr int kItemSteps = 256;  // steps per dynamically scheduled work item (8 forcing chunks)
-constexpr int kDynamicMaxWaves = 3;  // dynamic scheduling below this many waves of block descriptors
-
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
-static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * kNTileRows * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
-                      kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
-  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  RunArgs args = a;
-  args.nblocks = nblocks;
-  args.itemSteps = kItemSteps;
-  int grid = nblocks;
-  bool dynamic = false;
-  if constexpr (!REPLAY && !DEBUG && NM::kFast) {
-    if (a.workCounter != nullptr) {
-      // More block descriptors than resident CTAs, but only a few waves of them: whole waves would quantise the
-      // run time (1.4 waves cost 2), so a persistent grid pulls (block, sub-range) items instead.  With many waves
-      // the static grid's tail is small and its kernel is the (slightly) faster one.
-      auto dyn = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>;
-      int dev = 0, sms = 0, perSm = 0;
-      if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-      if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, BLOCK, smem)) != cudaSuccess) return e;
-      const int resident = sms * perSm;
-      if (resident > 0 && nblocks > resident && nblocks < kDynamicMaxWaves * resident) {
-        dynamic = true;
-        grid = resident;
-        dyn<<<grid, BLOCK, smem, stream>>>(args);
-        return cudaGetLastError();
-      }
-    }
-  }
-  (void)dynamic;
-  args.workCounter = nullptr;
-  kern<<<grid, BLOCK, smem, stream>>>(args);
-  return cudaGetLastError();
-}
-
-template <class FL, int BLOCK>
-static cudaError_t launch_fast(const RunArgs &a, int nblocks, bool full, cudaStream_t stream) {
-  return full ? launch_one<FL, false, FastNum, BLOCK, false, true>(a, nblocks, stream)
-              : launch_one<FL, false, FastNum, BLOCK, false, false>(a, nblocks, stream);
-}
+// K1 instantiations live in sip_run_exact.cu / sip_run_fast_*.cu
+cudaError_t launch_exact(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream);
+cudaError_t launch_fast_default_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_fast_default_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_fast_cropn_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_fast_cropn_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_fast_generic_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_fast_generic_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
 
 // mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members (exact)
-template <int BLOCK>
-static cudaError_t launch_block(const RunArgs &a, int nblocks, bool debug, int mode, cudaStream_t stream) {
+cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream) {
+  if (blockThreads != 32 && blockThreads != 128) return cudaErrorInvalidValue;
+  if (mode != 1 || debug) return launch_exact(a, nblocks, blockThreads, debug, mode, stream);
   const uint32_t arith = a.flags & ~(uint32_t)F_SNOW;  // ctx.snow has no arithmetic effect (SURVEY 8a trap 6)
   bool full = a.out != nullptr;
   for (int c = 0; c < SIPNET_GPU_NOUT; ++c) full = full && a.colSlot[c] == c;
-  if (mode == 2) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, true, false>(a, nblocks, stream);
-  if (debug) return launch_one<RuntimeFlags, true, ExactNum, BLOCK, false, false>(a, nblocks, stream);
-  if (mode == 0) return launch_one<RuntimeFlags, false, ExactNum, BLOCK, false, false>(a, nblocks, stream);
-  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW)) return launch_fast<StaticFlags<kMaskDefault>, BLOCK>(a, nblocks, full, stream);
-  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW)) return launch_fast<StaticFlags<kMaskCropN>, BLOCK>(a, nblocks, full, stream);
-  return launch_fast<RuntimeFlags, BLOCK>(a, nblocks, full, stream);
-}
-
-cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream) {
-  switch (blockThreads) {
-    case 32: return launch_block<32>(a, nblocks, debug, mode, stream);
-    case 128: return launch_block<128>(a, nblocks, debug, mode, stream);
-    default: return cudaErrorInvalidValue;
-  }
+  const bool wide = blockThreads == 128;
+  if (arith == (kMaskDefault & ~(uint32_t)F_SNOW))
+    return wide ? launch_fast_default_128(a, nblocks, full, stream) : launch_fast_default_32(a, nblocks, full, stream);
+  if (arith == (kMaskCropN & ~(uint32_t)F_SNOW))
+    return wide ? launch_fast_cropn_128(a, nblocks, full, stream) : launch_fast_cropn_32(a, nblocks, full, stream);
+  return wide ? launch_fast_generic_128(a, nblocks, full, stream) : launch_fast_generic_32(a, nblocks, full, stream);
 }
 
 cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream) {
