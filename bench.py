@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--cap", type=int, default=0, help="c4: steps per run segment kept on the device (0 = the whole run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-filled", action="store_true", help="skip the filled-GPU (C4 per-GPU share) roofline measurement")
     return ap.parse_args()
 
 
@@ -229,6 +230,48 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_filled(local: int, years: int, fp64_peak_tflops: float):
+    """Roofline of the same kernel when the GPU is FILLED: BASELINE.json's target configuration (C4: 1M members on
+    8 GPUs) per-GPU share, 131072 members x 10 yr, with the on-device reductions the config asks for (mean, variance
+    and exact 5/50/95 % quantiles of NEE and GPP per step).  C2's 4096 members are 128 warps on 592 warp schedulers:
+    its roofline fraction measures the model's sequential time loop, not the kernel."""
+    from sipnet_b200 import _abi as A, api, synth
+    M = 131072
+    site = synth.synth_site(0, years, "half-daily")
+    params = synth.synth_params(M, stream=100)
+    ens = api.Ensemble([site], params, None, dict(synth.SYNTH_FLAGS), math=A.MATH_FAST, device=local,
+                       outputs=A.OUT_MOMENTS | A.OUT_QUANTILES, summary_cols=[A.O["nee"], A.O["gpp"]],
+                       quantiles=[0.05, 0.5, 0.95])
+    T = ens.max_steps
+
+    def one_pass():
+        ens.reset()
+        ens.run(0, T)
+        ens.device_ptr(A.GATHER_QUANTILES)      # launches the row-summary kernels (results stay on the device)
+        ens.sync()
+
+    one_pass()
+    kern, total = [], []
+    for _ in range(3):
+        ens.sync()
+        ens.timer_start()
+        one_pass()
+        total.append(ens.timer_stop_ms())
+        kern.append(ens.last_run_ms())
+    q = ens.quantiles()
+    assert np.isfinite(q).all()
+    ens.close()
+    kern_ms, total_ms = float(np.mean(kern)), float(np.mean(total))
+    ach = M * T / (kern_ms * 1e-3) * FLOP_PER_MEMBER_STEP / 1e12
+    whole = M * T / (total_ms * 1e-3)
+    return {"workload": f"C4 per-GPU share: {M} members x {T} steps, on-device mean/variance + exact 5/50/95% quantiles "
+                        "of NEE and GPP",
+            "bound": "fp64", "kernel": "sip::run_kernel", "kernel_ms": kern_ms, "achieved": ach, "peak": fp64_peak_tflops,
+            "unit": "TFLOP/s", "frac": ach / fp64_peak_tflops if fp64_peak_tflops > 0 else None,
+            "whole_job_ms": total_ms, "whole_job_value": whole,
+            "whole_job_frac": whole * FLOP_PER_MEMBER_STEP / 1e12 / fp64_peak_tflops if fp64_peak_tflops > 0 else None}
+
+
 # ---------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -331,6 +374,9 @@ def run_ours(args):
         lib.sipnet_gpu_host_free(hout)
         lib.sipnet_gpu_host_free(hpar)
     ens.close()
+    filled = None
+    if world == 1 and not args.no_filled and args.members == 4096:
+        filled = measure_filled(local, args.years, fp64_peak_tflops)
 
     if rank == 0:
         peaks = {}
@@ -368,6 +414,8 @@ def run_ours(args):
                        "l2": "each step writes 7.66 GB of output (>> 126 MB L2), inputs are re-read from HBM"},
             "roofline": primary, "roofline_alt": alt, "clocks": clocks, "gpu_launches": int(launches),
         }
+        if filled is not None:
+            line["roofline_filled_gpu"] = filled
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
@@ -437,6 +485,8 @@ def run_other_config(args):
     cap = kw.get("out_steps_capacity", T) or T
     qs = [0.05, 0.5, 0.95]
 
+    checks = []
+
     def one_pass(prof=None):
         """prof: dict of phase -> seconds, filled with a device synchronize after every phase (an extra,
         untimed pass; the timed passes run without those synchronizes)."""
@@ -462,6 +512,12 @@ def run_other_config(args):
             ens.run(t0, t1)
             tp = lap("run_kernel", tp)
             n = t1 - t0
+            if args.workload == "c3":                           # per-site moments stay on the device (1.2 GB at full size)
+                mom = D.DeviceArray(ens.device_ptr(A.GATHER_MEAN), (ens.nsites, n)).tensor(local)
+                var = D.DeviceArray(ens.device_ptr(A.GATHER_VARIANCE), (ens.nsites, n)).tensor(local)
+                checks.append(float(mom[0, -1].item()) + float(var[-1, 0].item()))   # a result really is read back
+                tp = lap("moments", tp)
+                continue
             mean, var = ens.mean(), ens.variance()              # local shard's per-step moments
             tp = lap("moments", tp)
             if args.workload == "c4":

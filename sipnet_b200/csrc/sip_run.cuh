@@ -81,13 +81,21 @@ struct Emitter {
     tSite = ts;
     if (FULL) cur = reinterpret_cast<char *>(outp + tl * a->ld);
   }
-  __device__ __forceinline__ void out(int col, double v) {
+  // value(col) is the step's column -> value switch (sip_step.cuh)
+  template <class F>
+  __device__ __forceinline__ void outputs(const F &value) {
     if (FULL) {
-      __stcs(reinterpret_cast<double *>(cur), v);
-      cur += colStride;
+#pragma unroll
+      for (int c = 0; c < SIPNET_GPU_NOUT; ++c) {
+        __stcs(reinterpret_cast<double *>(cur), value(c));
+        cur += colStride;
+      }
     } else if (outp != nullptr) {
-      const int s = a->colSlot[col];
-      if (s >= 0) __stcs(outp + ((int64_t)s * a->outSteps + tLocal) * a->ld, v);
+      double *p = outp + tLocal * a->ld;
+      for (int s = 0; s < a->nOutCols; ++s) {
+        __stcs(p, value((int)a->slotCol[s]));
+        p += a->outSteps * a->ld;
+      }
     }
   }
   __device__ __forceinline__ void dbg(int k, double v) const {

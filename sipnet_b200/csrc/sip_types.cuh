@@ -165,6 +165,8 @@ struct RunArgs {
   double invSigma;         // 1 / nee_sigma
   double logNorm;          // -log(sigma) - 0.5*log(2*pi)
   int8_t colSlot[SIPNET_GPU_NOUT];  // output column -> slot in `out`, or -1
+  int8_t slotCol[SIPNET_GPU_NOUT];  // slot -> output column (first nOutCols entries)
+  int32_t nOutCols;
   // dynamic scheduling of (block descriptor, sub-range of steps) work items over a persistent grid; a null
   // workCounter means one CTA per block descriptor over the whole range (sip_kernels.cu: run_kernel)
   unsigned long long *workCounter;  // next work item

@@ -638,6 +638,11 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
   a.invSigma = 1.0 / h->sigma;
   a.logNorm = -std::log(h->sigma) - 0.5 * std::log(2.0 * M_PI);
   memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);
+  for (int c = 0; c < SIPNET_GPU_NOUT; ++c)
+    if (h->colSlot[c] >= 0) {
+      a.slotCol[h->colSlot[c]] = (int8_t)c;
+      a.nOutCols = std::max<int32_t>(a.nOutCols, h->colSlot[c] + 1);
+    }
 
   if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
     if (outbuf) CUDA_OK(cudaMemsetAsync(outbuf, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
