@@ -61,6 +61,8 @@ def parse_args():
                     help="c2 = the bench workload (default); c3/c4/c5 = the other BASELINE.json configs (extra lines)")
     ap.add_argument("--sites", type=int, default=0, help="c3: number of sites on this GPU (default 10000 / n_gpus)")
     ap.add_argument("--cap", type=int, default=0, help="c4: steps per run segment kept on the device (0 = the whole run)")
+    ap.add_argument("--verify", action="store_true", help="c4 pipelined: compare its quantiles with the sequential pass")
+    ap.add_argument("--no-pipeline", action="store_true", help="c4 on several GPUs: run kernel, exchange and select one after the other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-filled", action="store_true", help="skip the filled-GPU (C4 per-GPU share) roofline measurement")
@@ -479,6 +481,12 @@ def run_other_config(args):
         kw = dict(outputs=A.OUT_LOGLIK, nee_sigma=0.5)
         name = f"C5: {total} parameter draws x {args.years} yr, on-device NEE log-likelihood, NCCL all_gather"
     t_build = time.perf_counter() - t_build
+    pipelined = args.workload == "c4" and world > 1 and not args.no_pipeline
+    s_run = s_sum = None
+    if pipelined:                                        # library work on a torch-visible stream, summaries on another
+        s_run, s_sum = torch.cuda.Stream(device=local), torch.cuda.Stream(device=local, priority=-1)
+        kw["stream"] = s_run.cuda_stream
+        kw["out_steps_capacity"] = args.cap or 1024
     ens = api.Ensemble(sites, params, ms, flags, math=A.MATH_FAST, device=local, **kw)
     T = ens.max_steps
     M_local = params.shape[1]
@@ -486,6 +494,44 @@ def run_other_config(args):
     qs = [0.05, 0.5, 0.95]
 
     checks = []
+    collected = []                                       # quantile tensors of the last pass (--verify)
+
+    def c4_pipelined_pass():
+        """C4 on several GPUs, segment-pipelined: while the step kernel integrates segment i+1 on the library's
+        stream, the summary stream packs, exchanges (all-to-all over NVLink) and selects the quantiles of
+        segment i.  The only host synchronisation is at the end of the pass."""
+        ens.reset()
+        packed = None
+        keep = []
+        ld = (M_local + 15) // 16 * 16
+        for t0 in range(0, T, cap):
+            t1 = min(T, t0 + cap)
+            n = t1 - t0
+            if packed is not None:
+                s_run.wait_event(packed)                 # the previous segment's columns have been copied out
+            ens.run(t0, t1)                              # asynchronous, on s_run
+            mean_ptr, var_ptr = ens.device_ptr(A.GATHER_MEAN), ens.device_ptr(A.GATHER_VARIANCE)   # moments kernel, s_run
+            ready = torch.cuda.Event()
+            ready.record(s_run)
+            with torch.cuda.stream(s_sum):
+                s_sum.wait_event(ready)
+                colbuf = D.DeviceArray(ens.device_ptr(A.GATHER_FULL), (2, n, M_local), (n * ld, ld, 1)).tensor(local)
+                mom = torch.stack([D.DeviceArray(mean_ptr, (2, n)).tensor(local), D.DeviceArray(var_ptr, (2, n)).tensor(local)])
+                sends = [D.pack_time_slices(colbuf[i], world, copy=True) for i in range(2)]
+                packed = torch.cuda.Event()
+                packed.record(s_sum)
+                gathered = [torch.empty_like(mom) for _ in range(world)]
+                dist.all_gather(gathered, mom)           # per-rank (mean, variance); combined in rank order below
+                for i in range(2):
+                    rows, _, _ = D.exchange_time_slices(sends[i], n, [M_local] * world)
+                    keep.append(D.rows_summary(rows, qs, moments=False)[2])
+                keep.append(gathered)
+        s_sum.synchronize()
+        s_run.synchronize()
+        collected[:] = [k for k in keep if torch.is_tensor(k)]
+        g = keep[-1]                                     # ordered (Chan) combination of the last segment's moments
+        cnt = [np.full(g[0][0][0].shape, float(M_local))] * world
+        D.combine_moments(cnt, [x[0][0].cpu().numpy() for x in g], [x[1][0].cpu().numpy() for x in g])
 
     def one_pass(prof=None):
         """prof: dict of phase -> seconds, filled with a device synchronize after every phase (an extra,
@@ -498,6 +544,7 @@ def run_other_config(args):
             prof[name] = prof.get(name, 0.0) + now - t_prev
             return now
         tp = lap("_", time.perf_counter())
+        collected.clear()
         ens.reset()
         if args.workload == "c5":
             ens.run(0, T)
@@ -533,26 +580,38 @@ def run_other_config(args):
                     if world > 1:
                         rows, _, _ = D.time_transpose(rows, [M_local] * world)
                         tp = lap("time_transpose", tp)
-                    D.rows_summary(rows, qs, moments=False)
+                    collected.append(D.rows_summary(rows, qs, moments=False)[2])
                     tp = lap("quantile_select", tp)
 
-    one_pass()
+    timed_pass = c4_pipelined_pass if pipelined else one_pass
+    timed_pass()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_pass()
+        timed_pass()
     barrier()
     dt = (time.perf_counter() - t0) / args.steps
     tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     prof = {}
-    one_pass(prof)
+    if pipelined and args.verify:                        # same quantiles, bit for bit, as the one-after-the-other pass
+        got = [t.clone() for t in collected]
+        one_pass()
+        torch.cuda.synchronize()
+        same = len(got) == len(collected) and all(torch.equal(a, b) for a, b in zip(got, collected))
+        prof["verified_against_sequential_pass"] = bool(same)
+        if not same:
+            raise SystemExit("bench.py: pipelined C4 pass differs from the sequential pass")
+    if pipelined:
+        prof["pipelined"] = "segments of %d steps: all-to-all + select of segment i overlap the kernel of segment i+1" % cap
+    else:
+        one_pass(prof)
     prof.pop("_", None)
     status = ens.status()
     ens.close()
     if rank == 0:
-        print(json.dumps({"metric": METRIC, "workload": name, "phases_s": {k: round(v, 5) for k, v in prof.items()}, "value": world * M_local * T / float(tmax.item()),
+        print(json.dumps({"metric": METRIC, "workload": name, "phases_s": {k: (round(v, 5) if isinstance(v, float) else v) for k, v in prof.items()}, "value": world * M_local * T / float(tmax.item()),
                           "unit": UNIT, "n_gpus": world, "steps": args.steps, "s_per_pass": float(tmax.item()),
                           "members_per_gpu": M_local, "model_steps": T, "input_build_s": t_build,
                           "replayed_members": int((status & A.ST_REPLAY).astype(bool).sum()),

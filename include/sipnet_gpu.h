@@ -405,6 +405,8 @@ int sipnet_gpu_measure_fp64_peak(int device, double *tflops);
  * Used for exact cross-GPU quantiles: after an all-to-all time-transpose each rank holds complete
  * ensembles for its share of the steps and summarises them locally.  d_mean/d_var are [nrows],
  * d_quant is [nq][nrows] (any of them may be NULL); `probs` is a host array; `stream` a cudaStream_t or NULL.
+ * On a non-NULL stream the call only enqueues work (results are ordered on that stream); on the NULL stream it
+ * returns when the results are complete.
  */
 int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t nrows, int64_t ncols, int64_t ld,
                             const double *probs, int32_t nq, double *d_mean, double *d_var, double *d_quant,

@@ -87,6 +87,14 @@ __device__ __forceinline__ void hist_add(unsigned int *hist, int code) {
 
 constexpr int kSelUnroll = 4;  // independent row loads in flight per thread
 
+// kernel parameters passed by value, so a caller needs no device scratch (and no synchronising allocation)
+struct RowSpan {
+  int member0, memberCount;
+};
+struct QuantileProbs {
+  double p[kSelMaxQ];
+};
+
 struct SelState {
   uint64_t prefix[kSelMaxRanks];       // resolved leading key bits of each wanted order statistic
   unsigned long long k[kSelMaxRanks];  // its rank among the keys that share the prefix
@@ -258,7 +266,8 @@ __device__ __forceinline__ void compact_pass(const double *row, int count, SelSt
 // wanted prefixes still hold more than kCandCap keys (heavily duplicated data).  Last pass: the few keys
 // sharing a wanted prefix are compacted to shared memory, sorted (bitonic) and indexed.
 __global__ void __launch_bounds__(kSelThreads, 2)
-    row_summary_kernel(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, const double *probs, int nq,
+    row_summary_kernel(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, const RowSpan oneRow,
+                       const QuantileProbs probs, int nq,
                        double *mean, double *var, int64_t momStride, double *quant, int64_t qStride) {
   extern __shared__ __align__(16) unsigned char dyn[];
   unsigned int *hist = reinterpret_cast<unsigned int *>(dyn);
@@ -268,9 +277,10 @@ __global__ void __launch_bounds__(kSelThreads, 2)
   const int tid = threadIdx.x;
   const int64_t t = blockIdx.x;
   const int site = blockIdx.y;
-  const SiteDev sd = sites[site];
-  const int count = sd.memberCount;
-  const double *row = cols + t * ld + sd.member0;
+  // the members of the row: a site of the handle, or (sites == nullptr) the one span passed by value
+  const int member0 = sites != nullptr ? sites[site].member0 : oneRow.member0;
+  const int count = sites != nullptr ? sites[site].memberCount : oneRow.memberCount;
+  const double *row = cols + t * ld + member0;
   const int nr = 2 * nq;
   const bool big = nq > 0 && count > kCandCap;
 
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(kSelThreads, 2)
     if (tid < nq) quant[(int64_t)site * qStride + (int64_t)tid * nsteps + t] = vmin;
   } else if (nq > 0 && n > 0) {
     if (tid < nq) {
-      const double pos = probs[tid] * (n - 1.0);
+      const double pos = probs.p[tid] * (n - 1.0);
       const double lo = floor(pos);
       const double fr = pos - lo;
       S.frac[tid] = fr;
@@ -466,6 +476,8 @@ __global__ void __launch_bounds__(kWarpRowsPerBlock * 32)
 }
 
 // One column's summaries for every (site, step) row.  mean/var may be null (quantiles only), nq may be 0.
+// `sites` = the handle's device site table, or null: then every row is columns [0, maxMembers) (nsites must be 1).
+// `probs` is a HOST array.
 cudaError_t launch_row_summary(const double *cols, int64_t ld, int64_t nsteps, const SiteDev *sites, int64_t nsites,
                                int64_t maxMembers, const double *probs, int nq, double *mean, double *var,
                                int64_t momStride, double *quant, int64_t qStride, cudaStream_t stream) {
@@ -473,7 +485,8 @@ cudaError_t launch_row_summary(const double *cols, int64_t ld, int64_t nsteps, c
     cudaError_t e = cudaFuncSetAttribute(row_summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelDynBytes);
     if (e != cudaSuccess) return e;
   }
-  if (nq == 0 && mean != nullptr && maxMembers <= kWarpRowMax) {
+  const RowSpan one{0, (int)maxMembers};
+  if (sites != nullptr && nq == 0 && mean != nullptr && maxMembers <= kWarpRowMax) {
     // gridDim.y <= 65535: tile steps
     for (int64_t t0 = 0; t0 < nsteps; t0 += 65535) {
       const int64_t nt = (nsteps - t0) < 65535 ? (nsteps - t0) : 65535;
@@ -488,11 +501,13 @@ cudaError_t launch_row_summary(const double *cols, int64_t ld, int64_t nsteps, c
   for (int q0 = 0; q0 < (nq > 0 ? nq : 1); q0 += kSelMaxQ) {
     const int nqq = nq - q0 < kSelMaxQ ? nq - q0 : kSelMaxQ;
     const bool first = q0 == 0;
+    QuantileProbs qp{};
+    for (int i = 0; i < nqq && nq > 0; ++i) qp.p[i] = probs[q0 + i];
     for (int64_t s0 = 0; s0 < nsites; s0 += 65535) {  // gridDim.y <= 65535: tile sites
       const int ns = (int)((nsites - s0) < 65535 ? (nsites - s0) : 65535);
       dim3 grid((unsigned)nsteps, (unsigned)ns);
       row_summary_kernel<<<grid, kSelThreads, kSelDynBytes, stream>>>(
-          cols, ld, nsteps, sites + s0, nq > 0 ? probs + q0 : nullptr, nq > 0 ? nqq : 0,
+          cols, ld, nsteps, sites != nullptr ? sites + s0 : nullptr, one, qp, nq > 0 ? nqq : 0,
           first && mean ? mean + s0 * momStride : nullptr, first && var ? var + s0 * momStride : nullptr, momStride,
           quant ? quant + s0 * qStride + (int64_t)q0 * nsteps : nullptr, qStride);
       cudaError_t e = cudaGetLastError();

@@ -757,7 +757,7 @@ static int ensure_summaries(sipnet_gpu_handle *h) {
   for (int i = 0; i < ns; ++i) {
     const int slot = h->colSlot[h->summaryCols[(size_t)i]];
     const double *cols = h->out + (size_t)slot * n * h->ld;
-    cudaError_t e = launch_row_summary(cols, h->ld, n, h->sites, h->nsites, h->maxSiteMembers, h->qprobs,
+    cudaError_t e = launch_row_summary(cols, h->ld, n, h->sites, h->nsites, h->maxSiteMembers, h->quantiles.data(),
                                        h->quant ? (int)nq : 0, h->mean ? h->mean + (size_t)i * n : nullptr,
                                        h->var ? h->var + (size_t)i * n : nullptr, (int64_t)ns * n,
                                        h->quant ? h->quant + (size_t)i * nq * n : nullptr, (int64_t)ns * nq * n, h->stream);
@@ -911,23 +911,9 @@ extern "C" int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t
     return fail(SIPNET_GPU_ERR_NO_DEVICE, "device %d not present", device);
   CUDA_OK(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
-  // one pseudo-site covering all columns: the reducers take (rows = steps) x (members of a site)
-  SiteDev host{};
-  host.member0 = 0;
-  host.memberCount = (int32_t)ncols;
-  host.nsteps = nrows;
-  SiteDev *dsite = nullptr;
-  double *dprobs = nullptr;
-  CUDA_OK(cudaMalloc(&dsite, sizeof(SiteDev)));
-  CUDA_OK(cudaMemcpyAsync(dsite, &host, sizeof host, cudaMemcpyHostToDevice, st));
-  if (nq > 0) {
-    CUDA_OK(cudaMalloc(&dprobs, (size_t)nq * sizeof(double)));
-    CUDA_OK(cudaMemcpyAsync(dprobs, probs, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
-  }
-  CUDA_OK(launch_row_summary(d_rows, ld, nrows, dsite, 1, ncols, dprobs, nq, d_mean, d_var, nrows, d_quant,
+  // row span and probabilities travel as kernel parameters: no device scratch, nothing that synchronises
+  CUDA_OK(launch_row_summary(d_rows, ld, nrows, nullptr, 1, ncols, probs, nq, d_mean, d_var, nrows, d_quant,
                              (int64_t)nq * nrows, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  cudaFree(dsite);
-  if (dprobs) cudaFree(dprobs);
+  if (st == nullptr) CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }

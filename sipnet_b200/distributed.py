@@ -85,22 +85,38 @@ def all_gather_moments(count: "torch.Tensor", mean: "torch.Tensor", var: "torch.
     return combine_moments([h[0] for h in host], [h[1] for h in host], [h[2] for h in host])
 
 
+def pack_time_slices(cols: "torch.Tensor", world: int, copy: bool = False) -> List["torch.Tensor"]:
+    """cols [nsteps][m_local] (a view of the library's column buffer) -> contiguous per-destination blocks of steps.
+    copy=True always copies (a slice of an unpadded buffer is already contiguous and would otherwise alias it), so
+    that the column buffer may be overwritten while the exchange is still in flight."""
+    nsteps = cols.shape[0]
+    tb = [(nsteps * r) // world for r in range(world + 1)]
+    if copy:
+        return [cols[tb[r]:tb[r + 1], :].clone(memory_format=__import__("torch").contiguous_format) for r in range(world)]
+    return [cols[tb[r]:tb[r + 1], :].contiguous() for r in range(world)]
+
+
+def exchange_time_slices(send: List["torch.Tensor"], nsteps: int, local_counts: List[int], group=None):
+    """all-to-all of packed blocks -> ([t1 - t0][M_total] rows of this rank's share of the steps, t0, t1)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    tb = [(nsteps * r) // world for r in range(world + 1)]
+    recv = [torch.empty((tb[rank + 1] - tb[rank], local_counts[r]), dtype=send[0].dtype, device=send[0].device)
+            for r in range(world)]
+    dist.all_to_all(recv, send, group=group) if dist.get_backend(group) != "gloo" else _all_to_all_gloo(recv, send, group)
+    return torch.cat(recv, dim=1), tb[rank], tb[rank + 1]
+
+
 def time_transpose(cols: "torch.Tensor", local_counts: List[int], group=None) -> Tuple["torch.Tensor", int, int]:
     """The one exchange step for exact cross-rank quantiles.
 
     cols: [nsteps][m_local] (this rank's members of ONE output column).  Returns ([t1 - t0][M_total],
     t0, t1): all members for this rank's contiguous share of the steps, members in rank-major order."""
-    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    nsteps = cols.shape[0]
-    tb = [(nsteps * r) // world for r in range(world + 1)]
-    send = [cols[tb[r]:tb[r + 1], :].contiguous() for r in range(world)]
-    recv = [torch.empty((tb[rank + 1] - tb[rank], local_counts[r]), dtype=cols.dtype, device=cols.device)
-            for r in range(world)]
-    dist.all_to_all(recv, send, group=group) if dist.get_backend(group) != "gloo" else _all_to_all_gloo(recv, send, group)
-    return torch.cat(recv, dim=1).contiguous(), tb[rank], tb[rank + 1]
+    return exchange_time_slices(pack_time_slices(cols, world), cols.shape[0], local_counts, group)
 
 
 def _all_to_all_gloo(recv, send, group=None):
