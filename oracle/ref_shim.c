@@ -205,6 +205,16 @@ static void dump_out(double *o) {
   o[31] = envi.plantCAccountingDelta;
 }
 
+/* the reference's context (flag defaults) is initialised once for all entry points: a per-function guard would let a
+ * later first call of another entry point reset flags the caller has just set through sipref_read_params() */
+static void ensure_context(void) {
+  static int ready = 0;
+  if (!ready) {
+    initContext();
+    ready = 1;
+  }
+}
+
 /*
  * Run one member through the reference.  Arrays are per step, already in the
  * units readClimData() leaves them in.  out32 is [T][32], dbg is [T][106]
@@ -221,11 +231,7 @@ int sipref_run(const int32_t *flags, const double *params_in, int64_t T,
                const char *events_out_path, const char *main_out_path,
                int print_header, double *out32, double *dbg,
                int64_t *steps_done) {
-  static int context_ready = 0;
-  if (!context_ready) {
-    initContext();
-    context_ready = 1;
-  }
+  ensure_context();
   ctx.events = flags[0];
   ctx.gdd = flags[1];
   ctx.growthResp = flags[2];
@@ -332,11 +338,7 @@ int sipref_run(const int32_t *flags, const double *params_in, int64_t T,
  * -exitcode. */
 int64_t sipref_read_clim(const char *path, int gddFlag, int64_t cap,
                          int32_t *year, int32_t *day, double *cols /*[11][cap]*/) {
-  static int context_ready2 = 0;
-  if (!context_ready2) {
-    initContext();
-    context_ready2 = 1;
-  }
+  ensure_context();
   ctx.gdd = gddFlag;
   ctx.quiet = 1;
   sipref_code = 0;
@@ -368,11 +370,7 @@ int64_t sipref_read_clim(const char *path, int gddFlag, int64_t cap,
 
 /* The reference's parameter reader (sipnet.c:290-427) into a flat vector. */
 int sipref_read_params(const char *path, const int32_t *flags, double *out80) {
-  static int context_ready3 = 0;
-  if (!context_ready3) {
-    initContext();
-    context_ready3 = 1;
-  }
+  ensure_context();
   ctx.events = flags[0];
   ctx.gdd = flags[1];
   ctx.growthResp = flags[2];
@@ -401,11 +399,7 @@ int sipref_read_params(const char *path, const int32_t *flags, double *out80) {
 
 /* The reference's event reader (events.c:263-367). Returns count or -exitcode. */
 int64_t sipref_read_events(const char *path, int64_t cap, sipnet_gpu_event *out) {
-  static int context_ready4 = 0;
-  if (!context_ready4) {
-    initContext();
-    context_ready4 = 1;
-  }
+  ensure_context();
   ctx.quiet = 1;
   sipref_code = 0;
   sipref_jmp_armed = 1;

@@ -98,7 +98,7 @@ struct sipnet_gpu_handle {
   double *out = nullptr, *dbg = nullptr, *loglik = nullptr, *loglikN = nullptr;
   sipnet_gpu_event_record *recs = nullptr;
   int32_t *recCount = nullptr;
-  double *mean = nullptr, *var = nullptr, *quant = nullptr, *qprobs = nullptr, *qscratch = nullptr;
+  double *mean = nullptr, *var = nullptr, *quant = nullptr;
   bool staticSched = false;
   unsigned char *sched = nullptr;  // work counter (8 B, padded to 16) + per-block progress words (dynamic scheduling)
   // segment-start copies for the replay of members flagged by the optimistic kernel (MATH_FAST only)
@@ -211,8 +211,8 @@ static void free_handle(sipnet_gpu_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
-                  h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant, h->qprobs,
-                  h->qscratch, h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
+                  h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant,
+                  h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
                   h->recCountBk, h->sched};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -480,9 +480,6 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   }
   if (cfg->outputs & SIPNET_GPU_OUT_QUANTILES) {
     INIT_CUDA(dalloc(&h->quant, nsum * h->quantiles.size()));
-    INIT_CUDA(dalloc(&h->qprobs, h->quantiles.size()));
-    INIT_CUDA(cudaMemcpy(h->qprobs, h->quantiles.data(), h->quantiles.size() * sizeof(double), cudaMemcpyHostToDevice));
-    INIT_CUDA(dalloc(&h->qscratch, (size_t)h->ld * 2));
   }
 
   {  // dynamic scheduling words: counter + one progress word per block descriptor

@@ -157,6 +157,31 @@ def restart_golden():
     print("restart golden:", res)
 
 
+def balance_fixtures(shim):
+    """The fixture of the reference's mass-balance regression test (tests/sipnet/test_modeling/testBalance.c:
+    balance.param + balance.clim, 40 steps of 0.125 d; litter + nitrogen + anaerobic, GDD phenology off): as is
+    (model-computed leaf-on/off on days 47 and 49), without the litter pool, and with the test's leaf-on/leaf-off
+    EVENT file -- for which leafOnDay/leafOffDay are set to 0 in a copy of the parameter file, because the reference's
+    reader rejects leaf events next to day-based phenology (events.c:251-261)."""
+    import re
+    d = os.path.join(REF, "tests", "sipnet", "test_modeling")
+    on = dict(litterPool=1, nitrogenCycle=1, gdd=0, waterHResp=1, anaerobic=1)
+    with tempfile.TemporaryDirectory() as td:
+        text = open(os.path.join(d, "balance.param")).read()
+        text0 = re.sub(r"^(leafOnDay|leafOffDay)\s+\S+", r"\1 0", text, flags=re.M)
+        pfile0 = os.path.join(td, "balance_events.param")
+        open(pfile0, "w").write(text0)
+        for name, flags, pfile, evfile in (("balance_plain", on, os.path.join(d, "balance.param"), None),
+                                           ("balance_no_litter_pool", dict(gdd=0, waterHResp=1), os.path.join(d, "balance.param"), None),
+                                           ("balance_leaf_events", on, pfile0, "events_leaf.in")):
+            full = dict(A.DEFAULT_FLAGS)
+            full.update(flags)
+            site = shim.read_clim(os.path.join(d, "balance.clim"), full["gdd"])
+            params = shim.read_params(pfile, full)
+            site.events = shim.read_events(os.path.join(d, evfile)) if evfile else []
+            run_case(shim, name, full, params, site)
+
+
 def main():
     pack_smoke_inputs()
     debug_log_md5()
@@ -170,6 +195,7 @@ def main():
         site.events = shim.read_events(os.path.join(d, "events.in"))
         params = shim.read_params(os.path.join(d, "sipnet.param"), full)
         run_case(shim, "smoke_" + name, full, params, site, print_header=0 if name == "niwot" else 1)
+    balance_fixtures(shim)
     # synthetic: C3-style event schedule, two members of the wide prior + the anchor, 3 years
     for variant in ("half-daily", "unequal"):
         site = synth.synth_site(3, 3, variant, with_events=True)

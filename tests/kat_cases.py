@@ -138,6 +138,27 @@ CASES["leafoff_nitrogen_resorption"] = (NFLAGS, dict(_npools, wood=5.0, leaf=10.
                                         dict(plantLeafC=10.0 - _off, litterC=1.0 + _off, litterN=(_off / 30.0) * (1 - 0.3),
                                              plantStorageN=(_off / 30.0) * 0.3))
 
+# ---- testPlantMortality.c (tests/sipnet/test_modeling): pools wood 5, leaf 2, fine 3, coarse 4, soil 10.  The unit
+# test zeroes a pool by hand and calls checkForMortality(); in a whole step the plant has to be alive when the step
+# starts (sipnet.c:1828), so death is reached through a total harvest in the same step and the routing of what is
+# left follows sipnet.c:1733-1748: roots -> soil C, wood + leaf (+ delta) -> litter C (or soil C), N equivalents ----
+_m = dict(wood=5.0, leaf=2.0, fine=3.0, coarse=4.0, soilC=10.0)
+_dead = dict(plantWoodC=0.0, plantLeafC=0.0, fineRootC=0.0, coarseRootC=0.0, nppStorage=0.0)
+CASES["mortality_roots_harvested_no_litter"] = (FLAGS0, _m, {}, [ev(70, HARV, 0.0, 1.0, 0.0, 0.0)],
+                                                dict(_dead, soilC=10.0 + 0.0 + 5.0 + 2.0))
+CASES["mortality_shoots_harvested_no_litter"] = (FLAGS0, _m, {}, [ev(70, HARV, 1.0, 0.0, 0.0, 0.0)],
+                                                 dict(_dead, soilC=10.0 + 3.0 + 4.0))
+CASES["mortality_shoots_harvested_with_litter"] = (LFLAGS, dict(_m, litterC=5.0), {}, [ev(70, HARV, 1.0, 0.0, 0.0, 0.0)],
+                                                   dict(_dead, soilC=10.0 + 3.0 + 4.0, litterC=5.0))
+_mn = dict(_m, litterC=5.0, soilOrgN=2.0, litterN=3.0, storageN=0.5)
+_mcn = dict(woodCN=100.0, leafCN=20.0, fineRootCN=40.0)
+CASES["mortality_shoots_harvested_with_nitrogen"] = (NFLAGS, _mn, _mcn, [ev(70, HARV, 1.0, 0.0, 0.0, 0.0)],
+                                                     dict(_dead, soilC=17.0, litterC=5.0, soilOrgN=2.0 + 3.0 / 40.0 + 4.0 / 100.0,
+                                                          litterN=3.0 + 0.5, plantStorageN=0.0))
+CASES["mortality_roots_harvested_with_nitrogen"] = (NFLAGS, _mn, _mcn, [ev(70, HARV, 0.0, 1.0, 0.0, 0.0)],
+                                                    dict(_dead, soilC=10.0, litterC=5.0 + 5.0 + 2.0, soilOrgN=2.0,
+                                                         litterN=3.0 + 5.0 / 100.0 + 2.0 / 20.0 + 0.5, plantStorageN=0.0))
+
 # no event at all: the quiet parameters really leave every pool where it was
 CASES["quiet_step_moves_nothing"] = (NFLAGS, dict(leaf=2.0, wood=3.0, fine=4.0, coarse=5.0, soilC=10.0, litterC=15.0,
                                                   soilOrgN=2.0, litterN=3.0, minN=10.0, storageN=1.0, water=7.0), {}, [],
