@@ -24,6 +24,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "sip_step.cuh"
 
 namespace sip {
@@ -410,7 +412,17 @@ constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;    
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
 
 constexpr int kItemSteps = 256;  // steps per dynamically scheduled work item (8 forcing chunks)
-constexpr int kDynamicMaxWaves = 3;  // dynamic scheduling below this many waves of block descriptors
+constexpr int kDynamicMaxWaves = 1 << 20;  // dynamic scheduling below this many waves of block descriptors (= always)
+
+// A/B switch for measurements: SIPNET_GPU_DYNAMIC_MAX_WAVES overrides the wave threshold of dynamic scheduling
+inline int dynamic_max_waves() {
+  static const int v = [] {
+    const char *e = getenv("SIPNET_GPU_DYNAMIC_MAX_WAVES");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 ? n : kDynamicMaxWaves;
+  }();
+  return v;
+}
 
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
@@ -426,9 +438,9 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
   bool dynamic = false;
   if constexpr (!REPLAY && !DEBUG && NM::kFast) {
     if (a.workCounter != nullptr) {
-      // More block descriptors than resident CTAs, but only a few waves of them: whole waves would quantise the
-      // run time (1.4 waves cost 2), so a persistent grid pulls (block, sub-range) items instead.  With many waves
-      // the static grid's tail is small and its kernel is the (slightly) faster one.
+      // More block descriptors than resident CTAs: whole waves would quantise the run time (1.4 waves cost 2,
+      // 3.46 cost ~3.6), so a persistent grid pulls (block, sub-range) items instead.  Measured: 32 768 members
+      // 57.6 -> 42.3 ms, 131 072 members 122.6 -> 108.3 ms, 262 144 members (6.9 waves) 219.4 -> 216.8 ms.
       auto dyn = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>;
       int dev = 0, sms = 0, perSm = 0;
       if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -436,7 +448,7 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
       if ((e = cudaFuncSetAttribute(dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, BLOCK, smem)) != cudaSuccess) return e;
       const int resident = sms * perSm;
-      if (resident > 0 && nblocks > resident && nblocks < kDynamicMaxWaves * resident) {
+      if (resident > 0 && nblocks > resident && nblocks < dynamic_max_waves() * resident) {
         dynamic = true;
         grid = resident;
         dyn<<<grid, BLOCK, smem, stream>>>(args);
