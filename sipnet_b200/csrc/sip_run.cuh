@@ -115,51 +115,52 @@ struct Emitter {
   }
 };
 
+template <bool COHERENT>
 __device__ __forceinline__ void load_member(const RunArgs &a, const double *state, const uint32_t *status, int64_t m,
                                             Member &mb, MemberExt &ext, bool debug) {
-  // __ldcg: carried state may have been written by another SM earlier in this launch (dynamic scheduling)
+  // COHERENT: carried state may have been written by another SM earlier in this launch (dynamic scheduling)
   const double *s = state + m;
   const int64_t ld = a.ld;
-  mb.wood = __ldcg(&s[SIPNET_S_plantWoodC * ld]);
-  mb.leaf = __ldcg(&s[SIPNET_S_plantLeafC * ld]);
-  mb.soil = __ldcg(&s[SIPNET_S_soilC * ld]);
-  mb.water = __ldcg(&s[SIPNET_S_soilWater * ld]);
-  mb.litter = __ldcg(&s[SIPNET_S_litterC * ld]);
-  mb.snow = __ldcg(&s[SIPNET_S_snow * ld]);
-  mb.coarse = __ldcg(&s[SIPNET_S_coarseRootC * ld]);
-  mb.fine = __ldcg(&s[SIPNET_S_fineRootC * ld]);
-  mb.minN = __ldcg(&s[SIPNET_S_minN * ld]);
-  mb.orgN = __ldcg(&s[SIPNET_S_soilOrgN * ld]);
-  mb.litN = __ldcg(&s[SIPNET_S_litterN * ld]);
-  mb.storN = __ldcg(&s[SIPNET_S_plantStorageN * ld]);
-  mb.delta = __ldcg(&s[SIPNET_S_plantCAccountingDelta * ld]);
-  mb.gdd = __ldcg(&s[SIPNET_S_gdd * ld]);
-  mb.wetFrac = __ldcg(&s[SIPNET_S_soilWetnessFrac * ld]);
-  mb.totNee = __ldcg(&s[SIPNET_S_totNee * ld]);
-  mb.dTill = __ldcg(&s[SIPNET_S_dTillMod * ld]);
-  mb.ringSum = __ldcg(&s[SIPNET_S_meanSum * ld]);
-  mb.ringStart = (int)__ldcg(&s[SIPNET_S_meanStart * ld]);
-  mb.ringLast = (int)__ldcg(&s[SIPNET_S_meanLast * ld]);
-  mb.trkLastYear = (int)__ldcg(&s[SIPNET_S_trackersLastYear * ld]);
-  mb.phenLastYear = (int)__ldcg(&s[SIPNET_S_phenLastYear * ld]);
-  mb.didGrowth = (int)__ldcg(&s[SIPNET_S_didLeafGrowth * ld]);
-  mb.didFall = (int)__ldcg(&s[SIPNET_S_didLeafFall * ld]);
-  mb.status = __ldcg(&status[m]);
+  mb.wood = carried_load<COHERENT>(&s[SIPNET_S_plantWoodC * ld]);
+  mb.leaf = carried_load<COHERENT>(&s[SIPNET_S_plantLeafC * ld]);
+  mb.soil = carried_load<COHERENT>(&s[SIPNET_S_soilC * ld]);
+  mb.water = carried_load<COHERENT>(&s[SIPNET_S_soilWater * ld]);
+  mb.litter = carried_load<COHERENT>(&s[SIPNET_S_litterC * ld]);
+  mb.snow = carried_load<COHERENT>(&s[SIPNET_S_snow * ld]);
+  mb.coarse = carried_load<COHERENT>(&s[SIPNET_S_coarseRootC * ld]);
+  mb.fine = carried_load<COHERENT>(&s[SIPNET_S_fineRootC * ld]);
+  mb.minN = carried_load<COHERENT>(&s[SIPNET_S_minN * ld]);
+  mb.orgN = carried_load<COHERENT>(&s[SIPNET_S_soilOrgN * ld]);
+  mb.litN = carried_load<COHERENT>(&s[SIPNET_S_litterN * ld]);
+  mb.storN = carried_load<COHERENT>(&s[SIPNET_S_plantStorageN * ld]);
+  mb.delta = carried_load<COHERENT>(&s[SIPNET_S_plantCAccountingDelta * ld]);
+  mb.gdd = carried_load<COHERENT>(&s[SIPNET_S_gdd * ld]);
+  mb.wetFrac = carried_load<COHERENT>(&s[SIPNET_S_soilWetnessFrac * ld]);
+  mb.totNee = carried_load<COHERENT>(&s[SIPNET_S_totNee * ld]);
+  mb.dTill = carried_load<COHERENT>(&s[SIPNET_S_dTillMod * ld]);
+  mb.ringSum = carried_load<COHERENT>(&s[SIPNET_S_meanSum * ld]);
+  mb.ringStart = (int)carried_load<COHERENT>(&s[SIPNET_S_meanStart * ld]);
+  mb.ringLast = (int)carried_load<COHERENT>(&s[SIPNET_S_meanLast * ld]);
+  mb.trkLastYear = (int)carried_load<COHERENT>(&s[SIPNET_S_trackersLastYear * ld]);
+  mb.phenLastYear = (int)carried_load<COHERENT>(&s[SIPNET_S_phenLastYear * ld]);
+  mb.didGrowth = (int)carried_load<COHERENT>(&s[SIPNET_S_didLeafGrowth * ld]);
+  mb.didFall = (int)carried_load<COHERENT>(&s[SIPNET_S_didLeafFall * ld]);
+  mb.status = carried_load<COHERENT>(&status[m]);
   if (debug) {
-    ext.yGpp = __ldcg(&s[SIPNET_S_yearlyGpp * ld]);
-    ext.yRtot = __ldcg(&s[SIPNET_S_yearlyRtot * ld]);
-    ext.yRa = __ldcg(&s[SIPNET_S_yearlyRa * ld]);
-    ext.yRh = __ldcg(&s[SIPNET_S_yearlyRh * ld]);
-    ext.yNpp = __ldcg(&s[SIPNET_S_yearlyNpp * ld]);
-    ext.yNee = __ldcg(&s[SIPNET_S_yearlyNee * ld]);
-    ext.yLitter = __ldcg(&s[SIPNET_S_yearlyLitter * ld]);
-    ext.tGpp = __ldcg(&s[SIPNET_S_totGpp * ld]);
-    ext.tRtot = __ldcg(&s[SIPNET_S_totRtot * ld]);
-    ext.tRa = __ldcg(&s[SIPNET_S_totRa * ld]);
-    ext.tRh = __ldcg(&s[SIPNET_S_totRh * ld]);
-    ext.tNpp = __ldcg(&s[SIPNET_S_totNpp * ld]);
-    ext.harvRemoved = __ldcg(&s[SIPNET_S_harvestFracRemoved * ld]);
-    ext.harvTransferred = __ldcg(&s[SIPNET_S_harvestFracTransferred * ld]);
+    ext.yGpp = carried_load<COHERENT>(&s[SIPNET_S_yearlyGpp * ld]);
+    ext.yRtot = carried_load<COHERENT>(&s[SIPNET_S_yearlyRtot * ld]);
+    ext.yRa = carried_load<COHERENT>(&s[SIPNET_S_yearlyRa * ld]);
+    ext.yRh = carried_load<COHERENT>(&s[SIPNET_S_yearlyRh * ld]);
+    ext.yNpp = carried_load<COHERENT>(&s[SIPNET_S_yearlyNpp * ld]);
+    ext.yNee = carried_load<COHERENT>(&s[SIPNET_S_yearlyNee * ld]);
+    ext.yLitter = carried_load<COHERENT>(&s[SIPNET_S_yearlyLitter * ld]);
+    ext.tGpp = carried_load<COHERENT>(&s[SIPNET_S_totGpp * ld]);
+    ext.tRtot = carried_load<COHERENT>(&s[SIPNET_S_totRtot * ld]);
+    ext.tRa = carried_load<COHERENT>(&s[SIPNET_S_totRa * ld]);
+    ext.tRh = carried_load<COHERENT>(&s[SIPNET_S_totRh * ld]);
+    ext.tNpp = carried_load<COHERENT>(&s[SIPNET_S_totNpp * ld]);
+    ext.harvRemoved = carried_load<COHERENT>(&s[SIPNET_S_harvestFracRemoved * ld]);
+    ext.harvTransferred = carried_load<COHERENT>(&s[SIPNET_S_harvestFracTransferred * ld]);
   }
 }
 
@@ -235,7 +236,7 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 #endif
 // One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
 // `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN>
 __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t blk, int64_t itemBegin, int64_t itemEnd,
                                          int &sc, double *tile, ClimRec *climBuf, uint64_t *libmTab, uint64_t *bars) {
   const int tid = threadIdx.x;
@@ -280,7 +281,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
       }
       if (a.recCount != nullptr) a.recCount[m] = a.recCountBackup[m];
     }
-    load_member(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
+    load_member<DYN>(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
     if (REPLAY) mb.status |= SIPNET_GPU_ST_REPLAY;
     if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) {  // reference would have exited (sipnet.c:1117-1122)
       active = false;
@@ -308,8 +309,8 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   }
   const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
   const ParamTile prm{tile + tid, BLOCK};
-  const RingRef rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
-  RecSink rec{nullptr, nullptr, a.maxRecs, 0};
+  const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
+  RecSinkT<DYN> rec{nullptr, nullptr, a.maxRecs, 0};
   if (a.recCount != nullptr && active) {
     rec.count = a.recCount + m;
     rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
@@ -317,8 +318,8 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
                      site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
   if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
-    emit.ll = __ldcg(&a.loglik[m]);
-    emit.lln = __ldcg(&a.loglikN[m]);
+    emit.ll = carried_load<DYN>(&a.loglik[m]);
+    emit.lln = carried_load<DYN>(&a.loglikN[m]);
   }
 
   for (int64_t cs = t0; cs < t1; cs += kChunkSteps, ++sc) {
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
 
   int sc = 0;
   if constexpr (!DYN) {
-    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
+    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
   } else {
     __shared__ long long sItem;
     const int64_t nsub = (a.stepEnd - a.stepBegin + a.itemSteps - 1) / a.itemSteps;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
       }
       const int64_t itemBegin = a.stepBegin + sub * (int64_t)a.itemSteps;
       const int64_t itemEnd = itemBegin + a.itemSteps < a.stepEnd ? itemBegin + a.itemSteps : a.stepEnd;
-      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
+      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
       __syncthreads();  // every member's state is stored ...
       if (tid == 0) {   // ... before the sub-range is published (release)
         const int64_t w1 = sItem;

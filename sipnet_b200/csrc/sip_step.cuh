@@ -51,6 +51,21 @@ struct ParamTile {
 };
 #define SIP_P(name) prm(SIPNET_P_##name)
 
+// Loads / stores of carried per-member data (ring slots, event counters, state rows).  COHERENT = true goes
+// through L2 (ld.cg / st.cg): with dynamic scheduling consecutive sub-ranges of a member may run on different SMs
+// within ONE launch, so a stale L1 line must not be served.  The static schedule keeps a member on one SM for the
+// whole launch and uses ordinary accesses (the ring load sits on the step's critical path: 0.5 ms of 31 on C2).
+template <bool COHERENT, class T>
+__device__ __forceinline__ T carried_load(const T *p) {
+  if constexpr (COHERENT) return __ldcg(p);
+  else return *p;
+}
+template <bool COHERENT, class T>
+__device__ __forceinline__ void carried_store(T *p, T v) {
+  if constexpr (COHERENT) __stcg(p, v);
+  else *p = v;
+}
+
 // ---- per-member register state -------------------------------------------------
 struct Member {
   // Envi, state.h:416-463
@@ -73,7 +88,8 @@ struct MemberExt {
 };
 
 // ---- mean-NPP ring in HBM: slot s of member m at v[s * ld + m] -----------------
-struct RingRef {
+template <bool COHERENT>
+struct RingRefT {
   double *v;
   double *w;
   int64_t ld;
@@ -86,21 +102,23 @@ struct RingRef {
   __device__ __forceinline__ void set_val(int s, double x) const { v[(int64_t)s * ld] = x; }
   __device__ __forceinline__ void set_wgt(int s, double x) const { w[(int64_t)s * ld] = x; }
 #else
-  __device__ __forceinline__ double val(int s) const { return __ldcg(v + (int64_t)s * ld); }
-  __device__ __forceinline__ double wgt(int s) const { return __ldcg(w + (int64_t)s * ld); }
-  __device__ __forceinline__ void set_val(int s, double x) const { __stcg(v + (int64_t)s * ld, x); }
-  __device__ __forceinline__ void set_wgt(int s, double x) const { __stcg(w + (int64_t)s * ld, x); }
+  __device__ __forceinline__ double val(int s) const { return carried_load<COHERENT>(v + (int64_t)s * ld); }
+  __device__ __forceinline__ double wgt(int s) const { return carried_load<COHERENT>(w + (int64_t)s * ld); }
+  __device__ __forceinline__ void set_val(int s, double x) const { carried_store<COHERENT>(v + (int64_t)s * ld, x); }
+  __device__ __forceinline__ void set_wgt(int s, double x) const { carried_store<COHERENT>(w + (int64_t)s * ld, x); }
 #endif
 };
 
-__device__ __forceinline__ void ring_reset(Member &mb, const RingRef &rg, double v) {  // runmean.c:44-51
+template <class RG>
+__device__ __forceinline__ void ring_reset(Member &mb, const RG &rg, double v) {  // runmean.c:44-51
   mb.ringStart = mb.ringLast = 0;
   rg.set_val(0, v);
   rg.set_wgt(0, kMeanNppDays);
   mb.ringSum = v * kMeanNppDays;
 }
 
-__device__ __forceinline__ void ring_push(Member &mb, const RingRef &rg, double value, double weight) {
+template <class RG>
+__device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value, double weight) {
   // addValueToMeanTracker, runmean.c:61-115 (weight <= 0 is rejected at init: events.c:460)
   if (weight >= kMeanNppDays) {
     ring_reset(mb, rg, value);
@@ -154,14 +172,15 @@ __device__ __forceinline__ void clamp_stock(double &v, double floorv, uint32_t &
 }
 
 // record sink for events.out rows (events.c:379-402)
-struct RecSink {
+template <bool COHERENT>
+struct RecSinkT {
   sipnet_gpu_event_record *recs;  // this member's slots, or null
   int32_t *count;                 // this member's counter, or null
   int32_t maxRecs;
   int32_t step;
   __device__ __forceinline__ void add(Member &mb, int type, int variant, int nval, const double *v) const {
     if (count == nullptr) return;
-    const int n = __ldcg(count);  // L2-coherent, like the ring (see RingRef)
+    const int n = carried_load<COHERENT>(count);
     if (recs != nullptr && n < maxRecs) {
       sipnet_gpu_event_record &r = recs[n];
       r.step = step;
@@ -172,7 +191,7 @@ struct RecSink {
     } else if (recs != nullptr) {
       mb.status |= SIPNET_GPU_ST_EVREC_OVERFLOW;
     }
-    __stcg(count, n + 1);
+    carried_store<COHERENT>(count, n + 1);
   }
 };
 
@@ -310,10 +329,10 @@ __device__ __forceinline__ double ratio(NM &nm, double num, double den) {
 // Emit is a functor: emit.outputs(column) stores the outputState() columns it keeps and, in the
 // DEBUG instantiation, emit.dbg(index, value) for the debug-log fields.
 // NM is the numerics policy (sip_num.cuh): ExactNum or FastNum -- same bits.
-template <class FL, bool DEBUG, class NM, class PT, class Emit>
+template <class FL, bool DEBUG, class NM, class PT, class RG, class RS, class Emit>
 __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const ClimRec &c, const EventDev *events,
-                                     Member &mb, MemberExt &ext, const RingRef &rg, const RecSink &rec,
-                                     Emit &emit, const StepConsts &kc) {
+                                     Member &mb, MemberExt &ext, const RG &rg, const RS &rec, Emit &emit,
+                                     const StepConsts &kc) {
   const double len = c.length;
   double seedLen = 0.0;
   if constexpr (NM::kFast) {
