@@ -1,6 +1,7 @@
-"""Known-answer tests taken from the reference's own unit tests for the events.in handler
+"""Known-answer tests taken from the reference's own unit tests: the events.in handler
 (reference tests/sipnet/test_events_types/testEvent{Harvest,Fertilization,Irrigation,Planting,LeafOnOff,Tillage}.c
-and their events_*.in fixtures).
+and their events_*.in fixtures) and, further down, plant mortality, carbon saturation, methane and drainage
+(tests/sipnet/test_modeling/test{PlantMortality,CarbonSaturation,Methane,SoilMoisture,NitrogenCycle}.c).
 
 Those tests call processEvents() + updatePoolsForEvents() on hand-set pools (helpers.c: climate 2024-070,
 time 0, length 0.125) and compare the pools with closed-form numbers, tolerance 1e-6.  Our boundary is the
@@ -35,7 +36,7 @@ FLAGS0 = dict(events=1, gdd=0, growthResp=0, leafWater=0, litterPool=0, snow=1, 
 NFLAGS = dict(FLAGS0, litterPool=1, nitrogenCycle=1, anaerobic=1)
 
 
-def one_step_site(events, nsteps=1, length=0.125):
+def one_step_site(events, nsteps=1, length=0.125, tsoil=9.0):
     """helpers.c:prepTypesTest(): 2024, day 70, time 0, length 0.125 -- plus benign forcing (no rain, no soil VPD)."""
     year = np.full(nsteps, 2024, np.int32)
     t = np.arange(nsteps) * length
@@ -44,10 +45,10 @@ def one_step_site(events, nsteps=1, length=0.125):
     clim["time"] = np.round((t - np.floor(t + 1e-9)) * 24.0, 6)
     clim["length"][:] = length
     clim["tair"][:] = 10.0
-    clim["tsoil"][:] = 9.0
+    clim["tsoil"][:] = tsoil
     clim["vpd"][:] = 0.7          # kPa-scale, as left by readClimData
     clim["vpdSoil"][:] = 0.0      # no soil evaporation
-    clim["vPress"][:] = 0.5
+    clim["vPress"][:] = 0.7       # above 0.6 kPa: no snow sublimation (sipnet.c:915)
     clim["wspd"][:] = 1.5
     site = SiteData(year, day, clim)
     site.events = [(2024, d, typ, method, p[0], p[1], p[2], p[3]) for (d, typ, method, p) in events]
@@ -62,7 +63,8 @@ def params_for(pools, **over):
     tot = wood + fine + coarse
     p.update(plantWoodInit=tot, fineRootFrac=fine / tot, coarseRootFrac=coarse / tot, laiInit=leaf / p["leafCSpWt"],
              soilInit=pools.get("soilC", 0.0), litterInit=pools.get("litterC", 0.0),
-             soilWFracInit=pools.get("water", 1.0) / p["soilWHC"], minNInit=pools.get("minN", 0.0),
+             soilWFracInit=pools.get("water", 1.0) / over.get("soilWHC", p["soilWHC"]), minNInit=pools.get("minN", 0.0),
+             snowInit=pools.get("snow", 0.0),
              soilOrgNInit=pools.get("soilOrgN", 0.0), litterOrgNInit=pools.get("litterN", 0.0),
              plantStorageNInit=pools.get("storageN", 0.0))
     p.update(over)
@@ -159,6 +161,66 @@ CASES["mortality_roots_harvested_with_nitrogen"] = (NFLAGS, _mn, _mcn, [ev(70, H
                                                     dict(_dead, soilC=10.0, litterC=5.0 + 5.0 + 2.0, soilOrgN=2.0,
                                                          litterN=3.0 + 5.0 / 100.0 + 2.0 / 20.0 + 0.5, plantStorageN=0.0))
 
+# ---- testCarbonSaturation.c: soilCSaturation 10, litter 10, a coarse-root loss of 100 or 200 g C m-2 d-1 (here:
+# 50 g of coarse roots turning over at 2 or 4 d-1) is split between soil and litter by unitClip(soilC / saturation);
+# the 125 % case also respires 50 g C m-2 d-1 from the soil (sipnet.c:1634-1680) ----
+CFLAGS = dict(FLAGS0, litterPool=1, carbonSaturation=1)
+
+
+def _csat(soil, loss, rsoil=0.0):
+    sat = min(max(soil / 10.0, 0.0), 1.0)
+    return dict(soilC=soil + (loss * (1 - sat) - rsoil) * 0.125, litterC=10.0 + loss * sat * 0.125,
+                coarseRootC=50.0 - loss * 0.125)
+
+
+_cs = dict(soilCSaturation=10.0, soilRespQ10=1.0, soilRespMoistEffect=0.0)
+CASES["csat_25pct_loss_100"] = (CFLAGS, dict(coarse=50.0, soilC=2.5, litterC=10.0), dict(_cs, coarseRootTurnoverRate=2.0 * 365.0),
+                                [], _csat(2.5, 100.0))
+CASES["csat_25pct_loss_200"] = (CFLAGS, dict(coarse=50.0, soilC=2.5, litterC=10.0), dict(_cs, coarseRootTurnoverRate=4.0 * 365.0),
+                                [], _csat(2.5, 200.0))
+CASES["csat_75pct_loss_100"] = (CFLAGS, dict(coarse=50.0, soilC=7.5, litterC=10.0), dict(_cs, coarseRootTurnoverRate=2.0 * 365.0),
+                                [], _csat(7.5, 100.0))
+CASES["csat_125pct_loss_200_rsoil_50"] = (CFLAGS, dict(coarse=50.0, soilC=12.5, litterC=10.0),
+                                          dict(_cs, coarseRootTurnoverRate=4.0 * 365.0, baseSoilResp=4.0 * 365.0), [],
+                                          _csat(12.5, 200.0, 50.0))
+
+# ---- testMethane.c: water 7.5 of WHC 10, fAnoxia 0.6, transition exponent 2, Q10 3 at tsoil 20: temperature effect 9,
+# moisture effect ((0.75 - 0.6) / 0.4)^2; rates 0.05 (soil) and 0.1 (litter) ----
+_mm = ((0.75 - 0.6) / (1 - 0.6)) ** 2
+_mp = dict(soilWHC=10.0, soilRespQ10=3.0, fAnoxia=0.6, anaerobicDecompRate=0.5, anaerobicTransExp=2.0,
+           soilMethaneRate=0.05, litterMethaneRate=0.1)
+MFLAGS = dict(FLAGS0, litterPool=1, anaerobic=1)
+CASES["methane_litter_pool"] = (MFLAGS, dict(water=7.5, soilC=15.0, litterC=7.5), _mp, [], dict(
+    soilC=15 - 0.75 * 9.0 * _mm * 0.125, litterC=7.5 - 0.75 * 9.0 * _mm * 0.125, ch4=2 * 0.75 * 9.0 * _mm * 0.125), 20.0)
+CASES["methane_no_litter_pool"] = (dict(FLAGS0, anaerobic=1), dict(water=7.5, soilC=20.0), _mp, [], dict(
+    soilC=20 - 1.0 * 9.0 * _mm * 0.125, ch4=1.0 * 9.0 * _mm * 0.125), 20.0)
+
+# ---- testSoilMoisture.c: drainage of 2 cm above WHC = 10 with flooding on is min(excess * waterDrainFrac,
+# excess / length); snow on the ground switches soil evaporation off (sipnet.c:986, 1016-1027) ----
+DFLAGS = dict(FLAGS0, flooding=1)
+for _frac, _drain in ((2.0, 4.0), (0.5, 1.0), (0.0, 0.0), (20.0, 16.0)):
+    CASES["drainage_frac_%g" % _frac] = (DFLAGS, dict(water=12.0, snow=1.0), dict(soilWHC=10.0, waterDrainFrac=_frac, snowMelt=0.0),
+                                         [], dict(soilWater=12.0 - _drain * 0.125, snow=1.0))
+CASES["drainage_none_at_whc"] = (DFLAGS, dict(water=10.0, snow=1.0), dict(soilWHC=10.0, waterDrainFrac=1.0, snowMelt=0.0), [],
+                                 dict(soilWater=10.0, snow=1.0))
+
+# ---- testNitrogenCycle.c: water 5 of WHC 10, soil C 1.5, litter C 1, Q10 2.9 at tsoil 20 (temperature effect 8.41);
+# volatilisation = frac * minN * tEffect * (0.05 + 3.8 A (1 - A)) with A = 0 below fAnoxia; leaching = minN *
+# min(drainage / WHC, 1) * frac, drainage being the excess over WHC per day (sipnet.c:1022-1027, nitrogen.c:15-40) ----
+_np = dict(soilWHC=10.0, soilRespQ10=2.9, soilRespMoistEffect=1.0, leafCN=20.0, woodCN=100.0, fineRootCN=40.0)
+_nq = dict(water=5.0, soilC=1.5, litterC=1.0)
+_vol = lambda n: 0.1 * n * 2.9 ** 2 * 0.05                                              # noqa: E731
+CASES["nitrogen_volatilisation"] = (NFLAGS, dict(_nq, minN=4.0), dict(_np, nVolatilizationFrac=0.1), [],
+                                    dict(minN=4.0 - _vol(4.0) * 0.125, n2o=_vol(4.0) * 0.125), 20.0)
+CASES["nitrogen_fertilisation_and_volatilisation"] = (NFLAGS, dict(_nq, minN=2.0), dict(_np, nVolatilizationFrac=0.1),
+                                                      [ev(70, FERT, 15, 5, 10)],
+                                                      dict(minN=2.0 + (10 / 0.125 - _vol(2.0)) * 0.125, litterN=15.0, litterC=1.0 + 5.0), 20.0)
+CASES["nitrogen_leaching_partial"] = (NFLAGS, dict(_nq, water=10.0 + 5 * 0.125, minN=1.0), dict(_np, nLeachingFrac=0.5), [],
+                                      dict(minN=1.0 - 1.0 * (5 / 10.0) * 0.5 * 0.125, nLeaching=1.0 * 0.5 * 0.5 * 0.125,
+                                           soilWater=10.0), 20.0)
+CASES["nitrogen_leaching_capped"] = (NFLAGS, dict(_nq, water=10.0 + 20 * 0.125, minN=1.0), dict(_np, nLeachingFrac=0.5), [],
+                                     dict(minN=1.0 - 1.0 * 1.0 * 0.5 * 0.125, nLeaching=0.5 * 0.125, soilWater=10.0), 20.0)
+
 # no event at all: the quiet parameters really leave every pool where it was
 CASES["quiet_step_moves_nothing"] = (NFLAGS, dict(leaf=2.0, wood=3.0, fine=4.0, coarse=5.0, soilC=10.0, litterC=15.0,
                                                   soilOrgN=2.0, litterN=3.0, minN=10.0, storageN=1.0, water=7.0), {}, [],
@@ -167,8 +229,8 @@ CASES["quiet_step_moves_nothing"] = (NFLAGS, dict(leaf=2.0, wood=3.0, fine=4.0, 
 
 
 def build(name):
-    flags, pools, over, events, want = CASES[name]
-    return dict(flags), params_for(pools, **over), one_step_site(events), want
+    flags, pools, over, events, want, *rest = CASES[name]
+    return dict(flags), params_for(pools, **over), one_step_site(events, tsoil=rest[0] if rest else 9.0), want
 
 
 def tillage_case():

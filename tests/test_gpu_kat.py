@@ -1,4 +1,4 @@
-"""GPU: the reference's event-handler unit tests as known-answer tests through the CUDA kernel (tests/kat_cases.py)."""
+"""GPU: the reference's own unit tests re-stated as known-answer tests, through the CUDA kernel (tests/kat_cases.py)."""
 import numpy as np
 import pytest
 

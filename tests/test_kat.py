@@ -1,4 +1,4 @@
-"""The reference's event-handler unit tests as known-answer tests (tests/kat_cases.py) -- oracle and, when built,
+"""The reference's own unit tests re-stated as known-answer tests over one complete step (tests/kat_cases.py) -- oracle and, when built,
 the live reference on the CPU; the CUDA kernel in tests/test_gpu_kat.py."""
 import numpy as np
 import pytest
