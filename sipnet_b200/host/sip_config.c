@@ -133,6 +133,9 @@ static void usage(const char *prog) {
          "  -e, --events-prefix <name>   prefix of events .in / .out ('events')\n"
          "      --ensemble-params <file> one .param path per line: run them as one ensemble; member k writes\n"
          "                               <prefix>.out.<k> (this implementation's extension)\n"
+         "      --site-list <file>       several sites in one launch (extension).  One site per line:\n"
+         "                               <file-prefix> [<events-prefix> [<member-list>]]; defaults: events next to the\n"
+         "                               site's files, one member from <file-prefix>.param; all sites share this run's flags\n"
          "      --validation-math        run the general (reference-shaped) kernel instead of the optimistic one\n"
          "  model flags (prefix with no- to turn off): --events --gdd --growth-resp --leaf-water --litter-pool --snow\n"
          "      --soil-phenol --water-hresp --nitrogen-cycle --anaerobic --flooding --carbon-saturation\n"
@@ -141,7 +144,7 @@ static void usage(const char *prog) {
 }
 
 int sip_parse_cli(sip_context *c, int argc, char **argv) {
-  enum { OPT_RESTART_IN = 1001, OPT_RESTART_OUT, OPT_DEBUG_LOG, OPT_ENSEMBLE, OPT_VALIDATION };
+  enum { OPT_RESTART_IN = 1001, OPT_RESTART_OUT, OPT_DEBUG_LOG, OPT_ENSEMBLE, OPT_VALIDATION, OPT_SITE_LIST };
   struct option opts[2 * kNumFlagSettings + 16];
   char names[kNumFlagSettings][40];
   int flagValue = 0, n = 0;
@@ -158,6 +161,7 @@ int sip_parse_cli(sip_context *c, int argc, char **argv) {
   opts[n++] = (struct option){"restart-out", required_argument, 0, OPT_RESTART_OUT};
   opts[n++] = (struct option){"debug-log", required_argument, 0, OPT_DEBUG_LOG};
   opts[n++] = (struct option){"ensemble-params", required_argument, 0, OPT_ENSEMBLE};
+  opts[n++] = (struct option){"site-list", required_argument, 0, OPT_SITE_LIST};
   opts[n++] = (struct option){"validation-math", no_argument, 0, OPT_VALIDATION};
   opts[n++] = (struct option){"help", no_argument, 0, 'h'};
   opts[n++] = (struct option){"version", no_argument, 0, 'v'};
@@ -194,6 +198,9 @@ int sip_parse_cli(sip_context *c, int argc, char **argv) {
         break;
       case OPT_ENSEMBLE:
         strncpy(c->ensembleParamList, optarg, SIP_NAME_MAX - 1);
+        break;
+      case OPT_SITE_LIST:
+        strncpy(c->siteList, optarg, SIP_NAME_MAX - 1);
         break;
       case OPT_VALIDATION:
         c->validationMath = 1;

@@ -50,6 +50,7 @@ typedef struct sip_context {
   char ensembleParamList[SIP_NAME_MAX]; /* --ensemble-params FILE: one .param path per line => one member each */
   int32_t validationMath;               /* --validation-math: run the general kernel */
   int32_t helpOrVersion;                /* 1 = --help printed, 2 = --version printed (caller exits 0) */
+  char siteList[SIP_NAME_MAX];          /* --site-list FILE: one site per line, all sites in one launch (see usage) */
 } sip_context;
 
 const char *sip_host_error(void);

@@ -5,15 +5,20 @@
  * <prefix>.out / events.out / <prefix>.config outputs and exit codes as
  * reference src/sipnet/frontend.c:130-253 -- but the body of runModelOutput()
  * (reference src/sipnet/sipnet.c:1954-1990) runs on a B200 through the C ABI
- * include/sipnet_gpu.h.  Extension: --ensemble-params FILE runs one member per
- * listed .param file on the same site in one launch; member k's outputs go to
- * <prefix>.out.<k> / events.out.<k>.
+ * include/sipnet_gpu.h.
+ * Extensions (one launch for many members / sites):
+ *   --ensemble-params FILE  one member per listed .param file on the same site; member k's outputs go to
+ *                           <prefix>.out.<k> / <events-prefix>.out.<k>
+ *   --site-list FILE        one site per line: <file-prefix> [<events-prefix> [<member-list>]] -- each site has its
+ *                           own .clim / .param (or member list) / events files and gets its own output files; all
+ *                           sites run under this invocation's flags
  * --debug-log <prefix> writes the reference's three per-step debug logs from the device's validation dump.
  * --restart-in / --restart-out read and write the reference's checkpoint format (sip_restart.c), so a segmented
  * run can alternate between this binary and the reference's.
  * Not supported (outside the hot-path scope): --do-single-outputs (exit 8).
  */
 #define _GNU_SOURCE
+#include <libgen.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -23,6 +28,68 @@
 static int die(int code, const char *what) {
   printf("[ERROR  ] %s\n", what);
   return code;
+}
+
+/* one site of the launch: its files, its members, its parsed inputs */
+typedef struct {
+  char prefix[SIP_NAME_MAX];       /* <prefix>.clim / .param / .out */
+  char eventsPrefix[SIP_NAME_MAX]; /* <eventsPrefix>.in / .out */
+  char memberList[SIP_NAME_MAX];   /* "" => one member from <prefix>.param */
+  char **paramFiles;
+  int64_t nmembers, member0;
+  sip_site_data data;
+} site_job;
+
+static int read_member_list(site_job *job) {
+  if (!job->memberList[0]) {
+    job->paramFiles = (char **)malloc(sizeof *job->paramFiles);
+    char name[SIP_NAME_MAX + 16];
+    snprintf(name, sizeof name, "%s.param", job->prefix);
+    job->paramFiles[0] = strdup(name);
+    job->nmembers = 1;
+    return 0;
+  }
+  FILE *lf = fopen(job->memberList, "r");
+  if (!lf) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open the member (.param) list");
+  char line[1024];
+  while (fgets(line, sizeof line, lf)) {
+    line[strcspn(line, "\r\n")] = '\0';
+    if (!line[0]) continue;
+    job->paramFiles = (char **)realloc(job->paramFiles, (size_t)(job->nmembers + 1) * sizeof *job->paramFiles);
+    job->paramFiles[job->nmembers++] = strdup(line);
+  }
+  fclose(lf);
+  if (job->nmembers == 0) return die(SIPNET_GPU_ERR_INPUT_FILE, "the member (.param) list is empty");
+  return 0;
+}
+
+/* --site-list: "<file-prefix> [<events-prefix> [<member-list>]]" per line, '#' comments */
+static int read_site_list(const char *path, site_job **jobs, int64_t *njobs) {
+  FILE *f = fopen(path, "r");
+  if (!f) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open the --site-list file");
+  char line[3 * SIP_NAME_MAX + 16];
+  while (fgets(line, sizeof line, f)) {
+    char a[SIP_NAME_MAX] = "", b[SIP_NAME_MAX] = "", c[SIP_NAME_MAX] = "";
+    char *hash = strchr(line, '#');
+    if (hash) *hash = '\0';
+    const int n = sscanf(line, " %255s %255s %255s", a, b, c);
+    if (n <= 0) continue;
+    *jobs = (site_job *)realloc(*jobs, (size_t)(*njobs + 1) * sizeof **jobs);
+    site_job *job = &(*jobs)[(*njobs)++];
+    memset(job, 0, sizeof *job);
+    snprintf(job->prefix, sizeof job->prefix, "%s", a);
+    if (n >= 2) {
+      snprintf(job->eventsPrefix, sizeof job->eventsPrefix, "%s", b);
+    } else { /* events.in / events.out next to the site's files */
+      char tmp[SIP_NAME_MAX];
+      snprintf(tmp, sizeof tmp, "%s", a);
+      snprintf(job->eventsPrefix, sizeof job->eventsPrefix, "%.240s/events", dirname(tmp));
+    }
+    if (n >= 3) snprintf(job->memberList, sizeof job->memberList, "%s", c);
+  }
+  fclose(f);
+  if (*njobs == 0) return die(SIPNET_GPU_ERR_INPUT_FILE, "the --site-list file names no site");
+  return 0;
 }
 
 int main(int argc, char **argv) {
@@ -37,14 +104,18 @@ int main(int argc, char **argv) {
     return die(SIPNET_GPU_ERR_BAD_CLI,
                "single-variable outputs are not part of the GPU hot path; use the reference binary for those");
   const int useRestart = ctx.restartIn[0] || ctx.restartOut[0];
-  if (useRestart && ctx.ensembleParamList[0])
-    return die(SIPNET_GPU_ERR_BAD_CLI, "a restart checkpoint holds one member: not available with --ensemble-params");
-  if (ctx.debugLogPrefix[0] && ctx.ensembleParamList[0])
-    return die(SIPNET_GPU_ERR_BAD_CLI, "--debug-log is a single-member feature");
+  const int many = ctx.ensembleParamList[0] || ctx.siteList[0];
+  if (useRestart && many)
+    return die(SIPNET_GPU_ERR_BAD_CLI,
+               "a restart checkpoint holds one member: not available with --ensemble-params / --site-list");
+  if (ctx.debugLogPrefix[0] && many) return die(SIPNET_GPU_ERR_BAD_CLI, "--debug-log is a single-member feature");
+  if (ctx.ensembleParamList[0] && ctx.siteList[0])
+    return die(SIPNET_GPU_ERR_BAD_CLI, "--ensemble-params and --site-list exclude each other (a site list names member lists)");
   if ((rc = sip_derive_file_names(&ctx))) return die(rc, sip_host_error());
 
+  /* the reference opens its main output before reading anything (frontend.c:211-215) */
   FILE *out = NULL;
-  if (ctx.doMainOutput && !ctx.ensembleParamList[0]) {
+  if (ctx.doMainOutput && !many) {
     out = fopen(ctx.outFile, "w");
     if (!out) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open main output file");
   }
@@ -58,51 +129,62 @@ int main(int argc, char **argv) {
     fclose(cf);
   }
 
-  /* ---- inputs: initModel() + initEvents(), sipnet.c:2001-2009, events.c:427-433 ---- */
-  char **paramFiles = NULL;
-  int64_t M = 0;
-  if (ctx.ensembleParamList[0]) {
-    FILE *lf = fopen(ctx.ensembleParamList, "r");
-    if (!lf) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open the --ensemble-params list");
-    char line[1024];
-    while (fgets(line, sizeof line, lf)) {
-      line[strcspn(line, "\r\n")] = '\0';
-      if (!line[0]) continue;
-      paramFiles = (char **)realloc(paramFiles, (size_t)(M + 1) * sizeof *paramFiles);
-      paramFiles[M++] = strdup(line);
-    }
-    fclose(lf);
-    if (M == 0) return die(SIPNET_GPU_ERR_INPUT_FILE, "the --ensemble-params list is empty");
+  /* ---- the sites of this launch ---- */
+  site_job *jobs = NULL;
+  int64_t njobs = 0;
+  if (ctx.siteList[0]) {
+    if ((rc = read_site_list(ctx.siteList, &jobs, &njobs))) return rc;
   } else {
-    paramFiles = (char **)malloc(sizeof *paramFiles);
-    paramFiles[0] = strdup(ctx.paramFile);
-    M = 1;
+    jobs = (site_job *)calloc(1, sizeof *jobs);
+    njobs = 1;
+    snprintf(jobs[0].prefix, sizeof jobs[0].prefix, "%s", ctx.filePrefix);
+    snprintf(jobs[0].eventsPrefix, sizeof jobs[0].eventsPrefix, "%s", ctx.eventsPrefix);
+    snprintf(jobs[0].memberList, sizeof jobs[0].memberList, "%s", ctx.ensembleParamList);
+  }
+
+  /* ---- inputs: initModel() + initEvents() per site, sipnet.c:2001-2009, events.c:427-433 ---- */
+  int64_t M = 0, Tmax = 0, maxEvents = 0;
+  for (int64_t s = 0; s < njobs; ++s) {
+    if ((rc = read_member_list(&jobs[s]))) return rc;
+    jobs[s].member0 = M;
+    M += jobs[s].nmembers;
   }
   double *params = (double *)calloc((size_t)SIPNET_GPU_NPARAMS * (size_t)M, sizeof(double)); /* [80][M] */
-  for (int64_t m = 0; m < M; ++m) {
-    double one[SIPNET_GPU_NPARAMS];
-    if ((rc = sip_read_params(paramFiles[m], &ctx.flags, ctx.quiet || m > 0, one))) return die(rc, sip_host_error());
-    for (int k = 0; k < SIPNET_GPU_NPARAMS; ++k) params[(size_t)k * (size_t)M + (size_t)m] = one[k];
-  }
-  sip_site_data site;
-  if ((rc = sip_read_clim(ctx.climFile, ctx.flags.gdd, ctx.quiet, &site))) return die(rc, sip_host_error());
-  if (ctx.flags.events) {
-    double first[SIPNET_GPU_NPARAMS];
-    for (int k = 0; k < SIPNET_GPU_NPARAMS; ++k) first[k] = params[(size_t)k * (size_t)M];
-    if ((rc = sip_read_events(ctx.eventsInFile, &ctx.flags, first, ctx.quiet, &site))) return die(rc, sip_host_error());
+  int32_t *memberSite = (int32_t *)malloc((size_t)M * sizeof *memberSite);
+  sipnet_gpu_site *views = (sipnet_gpu_site *)calloc((size_t)njobs, sizeof *views);
+  for (int64_t s = 0; s < njobs; ++s) {
+    site_job *job = &jobs[s];
+    char name[SIP_NAME_MAX + 16];
+    for (int64_t k = 0; k < job->nmembers; ++k) {
+      double one[SIPNET_GPU_NPARAMS];
+      const int64_t m = job->member0 + k;
+      if ((rc = sip_read_params(job->paramFiles[k], &ctx.flags, ctx.quiet || m > 0, one))) return die(rc, sip_host_error());
+      for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) params[(size_t)p * (size_t)M + (size_t)m] = one[p];
+      memberSite[m] = (int32_t)s;
+    }
+    snprintf(name, sizeof name, "%s.clim", job->prefix);
+    if ((rc = sip_read_clim(name, ctx.flags.gdd, ctx.quiet || s > 0, &job->data))) return die(rc, sip_host_error());
+    if (ctx.flags.events) {
+      double first[SIPNET_GPU_NPARAMS];
+      for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) first[p] = params[(size_t)p * (size_t)M + (size_t)job->member0];
+      snprintf(name, sizeof name, "%s.in", job->eventsPrefix);
+      if ((rc = sip_read_events(name, &ctx.flags, first, ctx.quiet || s > 0, &job->data))) return die(rc, sip_host_error());
+    }
+    sip_site_view(&job->data, &views[s]);
+    if (job->data.nsteps > Tmax) Tmax = job->data.nsteps;
+    if (job->data.nevents > maxEvents) maxEvents = job->data.nevents;
   }
 
   /* ---- the run: setupModel() + the updateState() loop, on the device ---- */
-  sipnet_gpu_site view;
-  sip_site_view(&site, &view);
   sipnet_gpu_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.abi_version = SIPNET_GPU_ABI_VERSION;
   cfg.device = 0;
   cfg.flags = ctx.flags;
-  cfg.nsites = 1;
-  cfg.sites = &view;
+  cfg.nsites = njobs;
+  cfg.sites = views;
   cfg.nmembers = M;
+  cfg.member_site = memberSite;
   cfg.params = params;
   cfg.params_ld = M;
   cfg.outputs = (ctx.doMainOutput ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0) |
@@ -110,16 +192,17 @@ int main(int argc, char **argv) {
   /* checkpoints carry the reference's 250-slot mean-NPP ring slot for slot (restart.c:799-806) */
   cfg.ring_slots = useRestart ? SIPNET_GPU_RING_SLOTS_REFERENCE : 0;
   cfg.math = ctx.validationMath ? SIPNET_GPU_MATH_VALIDATION : SIPNET_GPU_MATH_FAST;
-  cfg.max_event_records = ctx.flags.events ? (int32_t)(site.nevents + 4 * (site.nsteps / 300 + 8)) : 0;
+  cfg.max_event_records = ctx.flags.events ? (int32_t)(maxEvents + 4 * (Tmax / 300 + 8)) : 0;
   sipnet_gpu_handle *h = NULL;
   if ((rc = sipnet_gpu_init(&cfg, &h))) return die(rc, sipnet_gpu_last_error());
-  const int64_t T = site.nsteps;
+  const int64_t T = Tmax;
+  const sip_site_data *site0 = &jobs[0].data; /* the single-member features below have exactly one site */
   long long processedBefore = 0; /* meta_info.processed_steps keeps counting across segments (restart.c:160, 905) */
   if (ctx.restartIn[0]) { /* restartLoadCheckpoint() after setupModel()+setupEvents(), sipnet.c:1963-1967 */
     sip_restart *rs = (sip_restart *)malloc(sizeof *rs);
     double state[SIPNET_GPU_NSTATE], ringV[SIP_RESTART_RING], ringW[SIP_RESTART_RING];
     if ((rc = sip_read_restart(ctx.restartIn, rs))) return die(rc, sip_host_error());
-    if ((rc = sip_check_restart(ctx.restartIn, rs, &ctx, &site))) return die(rc, sip_host_error());
+    if ((rc = sip_check_restart(ctx.restartIn, rs, &ctx, site0))) return die(rc, sip_host_error());
     processedBefore = rs->processedSteps;
     sip_restart_to_state(rs, state, 1, ringV, ringW, 1);
     if ((rc = sipnet_gpu_set_state(h, state, 1, ringV, ringW, 1, 0))) return die(rc, sipnet_gpu_last_error());
@@ -144,19 +227,26 @@ int main(int argc, char **argv) {
     double *buf = (double *)malloc(n * sizeof(double));
     if (!buf) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
     if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_FULL, buf, n * sizeof(double)))) return die(rc, sipnet_gpu_last_error());
-    for (int64_t m = 0; m < M; ++m) {
-      FILE *o = out;
-      if (!o) {
-        char name[SIP_NAME_MAX + 32];
-        snprintf(name, sizeof name, "%s.%lld", ctx.outFile, (long long)m);
-        o = fopen(name, "w");
-        if (!o) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open ensemble output file");
+    for (int64_t s = 0; s < njobs; ++s) {
+      const site_job *job = &jobs[s];
+      for (int64_t k = 0; k < job->nmembers; ++k) {
+        const int64_t m = job->member0 + k;
+        FILE *o = out;
+        if (!o) {
+          char name[SIP_NAME_MAX + 32];
+          if (job->memberList[0])
+            snprintf(name, sizeof name, "%s.out.%lld", job->prefix, (long long)k);
+          else
+            snprintf(name, sizeof name, "%s.out", job->prefix);
+          o = fopen(name, "w");
+          if (!o) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open a main output file");
+        }
+        if (ctx.printHeader) sip_write_header(o);
+        for (int64_t t = 0; t < job->data.nsteps; ++t)
+          sip_write_state_row(o, job->data.year[t], job->data.day[t], job->data.time[t],
+                              buf + (size_t)t * (size_t)M + (size_t)m, (int64_t)T * M);
+        fclose(o);
       }
-      if (ctx.printHeader) sip_write_header(o);
-      for (int64_t t = 0; t < T; ++t)
-        sip_write_state_row(o, site.year[t], site.day[t], site.time[t], buf + (size_t)t * (size_t)M + (size_t)m,
-                            (int64_t)T * M);
-      fclose(o);
     }
     free(buf);
   }
@@ -175,7 +265,7 @@ int main(int argc, char **argv) {
     }
     if (ctx.printHeader) sip_write_debug_headers(f[0], f[1], f[2]);
     for (int64_t t = 0; t < T; ++t)
-      sip_write_debug_rows(f[0], f[1], f[2], site.year[t], site.day[t], site.time[t], dbg + t, T);
+      sip_write_debug_rows(f[0], f[1], f[2], site0->year[t], site0->day[t], site0->time[t], dbg + t, T);
     for (int k = 0; k < 3; ++k) fclose(f[k]);
     free(dbg);
   }
@@ -191,7 +281,8 @@ int main(int argc, char **argv) {
         (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_RING_WEIGHTS, ringW, sizeof ringW)) ||
         (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_DEBUG, dbg, n * sizeof(double))))
       return die(rc, sipnet_gpu_last_error());
-    sip_restart_from_device(rs, &ctx, &site, processedBefore + (long long)T, (long long)time(NULL), state, 1, dbg + (T - 1), T, ringV, ringW, 1);
+    sip_restart_from_device(rs, &ctx, site0, processedBefore + (long long)T, (long long)time(NULL), state, 1, dbg + (T - 1), T,
+                            ringV, ringW, 1);
     if ((rc = sip_check_restart_boundary_for_write(ctx.restartOut, rs, ctx.quiet))) return die(rc, sip_host_error());
     if ((rc = sip_write_restart(ctx.restartOut, rs))) return die(rc, sip_host_error());
     free(dbg);
@@ -205,30 +296,40 @@ int main(int argc, char **argv) {
       return die(rc, sipnet_gpu_last_error());
     if (nrec && (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_EVENT_RECORDS, recs, nrec * sizeof *recs)))
       return die(rc, sipnet_gpu_last_error());
-    for (int64_t m = 0; m < M; ++m) {
-      char name[SIP_NAME_MAX + 32];
-      if (ctx.ensembleParamList[0])
-        snprintf(name, sizeof name, "%s.%lld", ctx.eventsOutFile, (long long)m);
-      else
-        snprintf(name, sizeof name, "%s", ctx.eventsOutFile);
-      FILE *eo = fopen(name, "w");
-      if (!eo) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open events output file");
-      if (ctx.printHeader) sip_write_events_header(eo);
-      if (counts[m] > cfg.max_event_records) return die(SIPNET_GPU_ERR_INTERNAL, "event record buffer too small");
-      for (int32_t k = 0; k < counts[m]; ++k) {
-        const sipnet_gpu_event_record *r = &recs[(size_t)m * (size_t)cfg.max_event_records + (size_t)k];
-        if ((rc = sip_write_event_row(eo, site.year[r->step], site.day[r->step], r))) return die(rc, sip_host_error());
+    for (int64_t s = 0; s < njobs; ++s) {
+      const site_job *job = &jobs[s];
+      for (int64_t k = 0; k < job->nmembers; ++k) {
+        const int64_t m = job->member0 + k;
+        char name[SIP_NAME_MAX + 32];
+        if (job->memberList[0])
+          snprintf(name, sizeof name, "%s.out.%lld", job->eventsPrefix, (long long)k);
+        else
+          snprintf(name, sizeof name, "%s.out", job->eventsPrefix);
+        FILE *eo = fopen(name, "w");
+        if (!eo) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open events output file");
+        if (ctx.printHeader) sip_write_events_header(eo);
+        if (counts[m] > cfg.max_event_records) return die(SIPNET_GPU_ERR_INTERNAL, "event record buffer too small");
+        for (int32_t r = 0; r < counts[m]; ++r) {
+          const sipnet_gpu_event_record *rec = &recs[(size_t)m * (size_t)cfg.max_event_records + (size_t)r];
+          if ((rc = sip_write_event_row(eo, job->data.year[rec->step], job->data.day[rec->step], rec)))
+            return die(rc, sip_host_error());
+        }
+        fclose(eo);
       }
-      fclose(eo);
     }
     free(recs);
     free(counts);
   }
   sipnet_gpu_destroy(h);
-  sip_site_free(&site);
+  for (int64_t s = 0; s < njobs; ++s) {
+    sip_site_free(&jobs[s].data);
+    for (int64_t k = 0; k < jobs[s].nmembers; ++k) free(jobs[s].paramFiles[k]);
+    free(jobs[s].paramFiles);
+  }
+  free(jobs);
+  free(views);
+  free(memberSite);
   free(params);
   free(status);
-  for (int64_t m = 0; m < M; ++m) free(paramFiles[m]);
-  free(paramFiles);
   return 0;
 }

@@ -28,7 +28,7 @@ class ContextC(C.Structure):
                                                       "eventsInFile", "eventsOutFile", "inputFile", "restartIn",
                                                       "restartOut", "debugLogPrefix", "filePrefix")]
                 + [("source", C.c_int32 * 32), ("ensembleParamList", C.c_char * NAME_MAX),
-                   ("validationMath", C.c_int32), ("helpOrVersion", C.c_int32)])
+                   ("validationMath", C.c_int32), ("helpOrVersion", C.c_int32), ("siteList", C.c_char * NAME_MAX)])
 
 
 def host_lib():

@@ -171,3 +171,55 @@ def test_restart_errors_exit_like_the_reference(smoke_dir, tmp_path):
     assert run(a, "--restart-in", RESTART_CKPT) == 9                  # the checkpoint does not precede this segment
     assert run(b, "--restart-in", RESTART_CKPT, "--no-nitrogen-cycle") == 9
     assert run(b, "--restart-in", RESTART_CKPT) == 0
+
+
+def test_site_list_runs_many_sites_in_one_launch(smoke_dir, tmp_path):
+    """--site-list: several sites (own forcing, events, members; different record counts) in ONE launch.  Every
+    output file equals the one a separate single-site run of the driver writes."""
+    import shutil
+    src = os.path.join(smoke_dir, "russell_2")
+    work = str(tmp_path / "multi")
+    os.makedirs(work)
+    shutil.copy(os.path.join(src, "sipnet.in"), work)
+    # site A: the whole smoke case; site B: its first year only; site C: whole case, two members with changed parameters
+    a, b, c = (os.path.join(work, n) for n in ("siteA", "siteB", "siteC"))
+    split_case(src, b, str(tmp_path / "unused"), 2016)
+    for d in (a, c):
+        os.makedirs(d)
+        for fn in ("sipnet.param", "sipnet.clim", "events.in"):
+            shutil.copy(os.path.join(src, fn), d)
+    base = open(os.path.join(src, "sipnet.param")).read()
+    members = []
+    for k, txt in enumerate((base.replace("aMax 53.2895432752984", "aMax 44.0"), base.replace("soilWHC 12", "soilWHC 10.5"))):
+        p = os.path.join(c, f"m{k}.param")
+        open(p, "w").write(txt)
+        members.append(p)
+    open(os.path.join(c, "members.txt"), "w").write("\n".join(members) + "\n")
+    with open(os.path.join(work, "sites.txt"), "w") as f:
+        f.write("# file-prefix [events-prefix [member-list]]\n")
+        f.write(f"{a}/sipnet\n")
+        f.write(f"{b}/sipnet {b}/events   # explicit events prefix\n")
+        f.write(f"{c}/sipnet {c}/events {c}/members.txt\n")
+    r = subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "sites.txt"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = {n: open(n, "rb").read() for n in (f"{a}/sipnet.out", f"{a}/events.out", f"{b}/sipnet.out", f"{b}/events.out",
+                                             f"{c}/sipnet.out.0", f"{c}/events.out.0", f"{c}/sipnet.out.1", f"{c}/events.out.1")}
+    # the same sites one at a time
+    def single(d, param=None):
+        if param:
+            shutil.copy(param, os.path.join(d, "sipnet.param"))
+        shutil.copy(os.path.join(work, "sipnet.in"), d)
+        r = subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet"], cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return open(os.path.join(d, "sipnet.out"), "rb").read(), open(os.path.join(d, "events.out"), "rb").read()
+    assert single(a) == (got[f"{a}/sipnet.out"], got[f"{a}/events.out"])
+    assert hashlib.md5(got[f"{a}/sipnet.out"]).hexdigest() == Golden("smoke_russell_2").main_out_md5     # = the reference's file
+    assert single(b) == (got[f"{b}/sipnet.out"], got[f"{b}/events.out"])
+    assert hashlib.md5(got[f"{b}/sipnet.out"]).hexdigest() == RESTART_GOLD["segment1_out_md5"]
+    for k in range(2):
+        assert single(c, members[k]) == (got[f"{c}/sipnet.out.{k}"], got[f"{c}/events.out.{k}"])
+    # bad lists
+    open(os.path.join(work, "empty.txt"), "w").write("# nothing\n")
+    assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "empty.txt"], cwd=work).returncode == 5
+    assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "missing.txt"], cwd=work).returncode == 6
+    assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "sites.txt", "--restart-out", "x"], cwd=work).returncode == 8
