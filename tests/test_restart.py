@@ -125,3 +125,35 @@ def test_checkpoint_maps_onto_device_state_rows(lib):
                                 dp(state), 1, dp(dbg), 1, dp(rv), dp(rw), 1)
     back.buildInfo = r.buildInfo
     assert bytes(back) == bytes(r)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/sipnet_ref not built")
+def test_random_checkpoint_mutants_get_the_references_verdict(lib, segments, tmp_path):
+    """Seeded random edits of the reference's checkpoint (tests/test_reader_fuzz.py: mutate) -- the reference binary's
+    exit code on `--restart-in mutant` must be what our reader + load-time checks return."""
+    import random
+
+    from test_reader_fuzz import mutate
+    src = open(CKPT).readlines()
+    rng = random.Random(505)
+    site = load_site(lib, os.path.join(segments[1], "sipnet.clim"))
+    path = str(tmp_path / "ck_mut")
+    seen = set()
+    for n in range(150):
+        lines = src
+        for _ in range(rng.choice([1, 1, 2])):
+            lines = mutate(lines, rng, keep_first=0)
+        open(path, "w").writelines(lines)
+        r = subprocess.run([REF_BIN, "-i", "sipnet.in", "--quiet", "--restart-in", path], cwd=segments[1],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        got = verdict(lib, path, site)
+        if r.returncode < 0:
+            assert got != 0, n
+            continue
+        if r.returncode not in (0, 5, 6, 9):      # accepted by the loader, then the RUN failed on the edited state
+            assert got == 0, (n, r.returncode)    # (e.g. a huge ring weight: exit 7 from the mean tracker)
+            continue
+        assert got == r.returncode, (n, [ln for ln in lines if ln not in src][:3], lib.sip_host_error())
+        seen.add(got)
+    assert seen == {0, 9}
+    lib.sip_site_free(C.byref(site))
