@@ -51,3 +51,30 @@ def assert_close(a, b, scale, names, rtol=RTOL, what=""):
     bad = np.argwhere(~(e <= rtol)).ravel()
     assert bad.size == 0, what + " " + ", ".join(f"{names[i]}={e[i]:.3e}" for i in bad[:8])
     return float(np.nanmax(e)) if e.size else 0.0
+
+
+def random_flag_cases(ntrials=30, members=6, seed=2026):
+    """Seeded random combinations of the 12 model flags that pass validateContext() (context.c:195-223), each with a
+    synthetic two-year site (alternating step patterns, event schedule when EVENTS is on) and a few wide-prior members."""
+    import numpy as np
+
+    from sipnet_b200 import _abi as A, synth
+    rng = np.random.default_rng(seed)
+    for trial in range(ntrials):
+        f = dict(A.DEFAULT_FLAGS)
+        f.update(events=int(rng.integers(0, 2)), gdd=int(rng.integers(0, 2)), growthResp=int(rng.integers(0, 2)),
+                 leafWater=int(rng.integers(0, 2)), litterPool=int(rng.integers(0, 2)), snow=int(rng.integers(0, 2)),
+                 waterHResp=int(rng.integers(0, 2)), flooding=int(rng.integers(0, 2)))
+        if not f["gdd"]:
+            f["soilPhenol"] = int(rng.integers(0, 2))
+        f["anaerobic"] = int(rng.integers(0, 2))
+        if f["litterPool"]:
+            f["carbonSaturation"] = int(rng.integers(0, 2))
+            if f["anaerobic"]:
+                f["nitrogenCycle"] = int(rng.integers(0, 2))
+        site = synth.synth_site(100 + trial, 2, ["half-daily", "unequal"][trial % 2], with_events=bool(f["events"]),
+                                gdd_flag=f["gdd"])
+        P = synth.synth_params(members, stream=1000 + trial)
+        P[A.P["soilCSaturation"], :] = rng.uniform(500, 5000)
+        P[A.P["waterDrainFrac"], :] = rng.uniform(0.1, 2.0)
+        yield trial, f, site, P

@@ -378,3 +378,21 @@ def test_dynamic_scheduling_is_bit_identical(oracle):
         sites[s] = short
     kw = dict(outputs=A.OUT_MOMENTS | A.OUT_EVENTS, summary_cols=[A.O["nee"]], out_steps_capacity=600, max_event_records=8)
     _same(_run_summary(sites, P, ms, flags, False, **kw), _run_summary(sites, P, ms, flags, True, **kw))
+
+
+def test_random_flag_combinations_are_bit_identical(oracle):
+    """The same 30 random flag combinations as tests/test_oracle_vs_reference.py, optimistic kernel vs oracle: all 32
+    output columns of every step and the final state, bit for bit."""
+    from gpu_util import random_flag_cases
+    for trial, f, site, P in random_flag_cases():
+        with api.Ensemble([site], P, None, f, outputs=A.OUT_FULL, math=A.MATH_FAST) as ens:
+            ens.run()
+            out = ens.output()
+            status = ens.status()
+        for m in range(P.shape[1]):
+            rc, done, o_out, _, _ = oracle.run(f, P[:, m], site, want_debug=False)
+            if status[m] & A.ST_BAD_ALLOCATION:
+                assert rc == 3
+                continue
+            assert rc == 0 and done == site.nsteps, (trial, m)
+            assert np.array_equal(out[:, :, m].T, o_out, equal_nan=True), (trial, m, f)

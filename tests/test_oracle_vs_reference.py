@@ -81,3 +81,15 @@ def test_error_codes_match_reference(oracle, refshim):
     # allocation parameters must sum below one -> 3 (sipnet.c:1117-1122)
     pb = p.copy(); pb[A.P["leafAllocation"]] = 0.7
     assert refshim.run(fl, pb, base)[0] == oracle.run(fl, pb, base)[0] == 3
+
+
+def test_oracle_vs_reference_random_flag_combinations(oracle, refshim):
+    """30 random valid flag combinations x 6 wide-prior members x 2 years: every debug field of every step, bit for bit."""
+    from gpu_util import random_flag_cases
+    for trial, f, site, P in random_flag_cases():
+        for m in range(P.shape[1]):
+            rc, done, out, dbg = refshim.run(f, P[:, m], site)
+            rc2, done2, out2, dbg2, _ = oracle.run(f, P[:, m], site)
+            assert (rc, done) == (rc2, done2), (trial, m, f)
+            assert np.array_equal(dbg[:done], dbg2[:done], equal_nan=True), (trial, m, f)
+            assert np.array_equal(out[:done], out2[:done], equal_nan=True), (trial, m, f)
