@@ -10,7 +10,7 @@ import numpy as np
 from conftest import GOLDEN_DIR, ROOT
 from sipnet_b200 import _abi as A
 
-HOST_LIB = os.path.join(ROOT, "sipnet_b200", "libsipnet_host.so")
+HOST_LIB = os.environ.get("SIPNET_HOST_LIB") or os.path.join(ROOT, "sipnet_b200", "libsipnet_host.so")   # override: sanitizer builds
 DRIVER = os.path.join(ROOT, "sipnet_b200", "sipnet_gpu")
 NAME_MAX = 256
 
