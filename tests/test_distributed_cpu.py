@@ -75,3 +75,18 @@ def test_gloo_gather_paths(world, tmp_path):
     port = 29650 + world
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_pack_time_slices_copy_does_not_alias_the_column_buffer():
+    """An unpadded column buffer's time slices are already contiguous, so .contiguous() would alias them; the
+    pipelined C4 pass overwrites the buffer while the exchange is in flight and needs real copies."""
+    import torch
+    cols = torch.arange(12 * 16, dtype=torch.float64).reshape(12, 16)
+    views = D.pack_time_slices(cols, 3)
+    copies = D.pack_time_slices(cols, 3, copy=True)
+    assert [v.shape for v in views] == [c.shape for c in copies] == [(4, 16)] * 3
+    assert all(torch.equal(v, c) for v, c in zip(views, copies))
+    assert views[1].data_ptr() == cols[4:8].data_ptr()                  # alias
+    assert all(c.data_ptr() != cols[4 * i:4 * i + 4].data_ptr() for i, c in enumerate(copies))
+    cols.zero_()
+    assert float(copies[2].sum()) > 0 and float(views[2].sum()) == 0
