@@ -145,3 +145,19 @@ def test_rows_summary_is_deterministic():
     a = [t.cpu().numpy() for t in D.rows_summary(x, QS)]
     b = [t.cpu().numpy() for t in D.rows_summary(x, QS)]
     assert all(np.array_equal(u, v) for u, v in zip(a, b))
+
+
+def test_rows_summary_is_stream_ordered_on_a_side_stream():
+    """On a non-default stream the call only enqueues work (no allocation, no synchronisation): the result is
+    ordered on that stream and equals the synchronous call's."""
+    import torch
+    from sipnet_b200 import distributed as D
+    x = torch.from_numpy(np.random.default_rng(8).normal(size=(64, 50001))).cuda()
+    want = [t.cpu().numpy() for t in D.rows_summary(x, QS)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        y = x * 1.0                                          # work queued ahead of the summary on the same stream
+        got = D.rows_summary(y, QS)
+    side.synchronize()
+    assert all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(want, got))
