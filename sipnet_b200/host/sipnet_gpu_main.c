@@ -15,7 +15,7 @@
  * --debug-log <prefix> writes the reference's three per-step debug logs from the device's validation dump.
  * --restart-in / --restart-out read and write the reference's checkpoint format (sip_restart.c), so a segmented
  * run can alternate between this binary and the reference's.
- * Not supported (outside the hot-path scope): --do-single-outputs (exit 8).
+ * --do-single-outputs writes <prefix>.NEE / .NEE_cum / .GPP / .GPP_cum like outputItems.c (one "%f " per step).
  */
 #define _GNU_SOURCE
 #include <libgen.h>
@@ -100,9 +100,6 @@ int main(int argc, char **argv) {
   if (ctx.helpOrVersion) return 0;
   if ((rc = sip_read_input_file(&ctx))) return die(rc, sip_host_error());
   if ((rc = sip_validate_context(&ctx))) return die(rc, sip_host_error());
-  if (ctx.doSingleOutputs)
-    return die(SIPNET_GPU_ERR_BAD_CLI,
-               "single-variable outputs are not part of the GPU hot path; use the reference binary for those");
   const int useRestart = ctx.restartIn[0] || ctx.restartOut[0];
   const int many = ctx.ensembleParamList[0] || ctx.siteList[0];
   if (useRestart && many)
@@ -187,7 +184,7 @@ int main(int argc, char **argv) {
   cfg.member_site = memberSite;
   cfg.params = params;
   cfg.params_ld = M;
-  cfg.outputs = (ctx.doMainOutput ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0) |
+  cfg.outputs = ((ctx.doMainOutput || ctx.doSingleOutputs) ? SIPNET_GPU_OUT_FULL : 0) | (ctx.flags.events ? SIPNET_GPU_OUT_EVENTS : 0) |
                 ((ctx.debugLogPrefix[0] || ctx.restartOut[0]) ? SIPNET_GPU_OUT_DEBUG : 0);
   /* checkpoints carry the reference's 250-slot mean-NPP ring slot for slot (restart.c:799-806) */
   cfg.ring_slots = useRestart ? SIPNET_GPU_RING_SLOTS_REFERENCE : 0;
@@ -198,12 +195,14 @@ int main(int argc, char **argv) {
   const int64_t T = Tmax;
   const sip_site_data *site0 = &jobs[0].data; /* the single-member features below have exactly one site */
   long long processedBefore = 0; /* meta_info.processed_steps keeps counting across segments (restart.c:160, 905) */
+  double totGppBefore = 0.0;     /* trackers.totGpp carried in from a checkpoint (GPP_cum single output) */
   if (ctx.restartIn[0]) { /* restartLoadCheckpoint() after setupModel()+setupEvents(), sipnet.c:1963-1967 */
     sip_restart *rs = (sip_restart *)malloc(sizeof *rs);
     double state[SIPNET_GPU_NSTATE], ringV[SIP_RESTART_RING], ringW[SIP_RESTART_RING];
     if ((rc = sip_read_restart(ctx.restartIn, rs))) return die(rc, sip_host_error());
     if ((rc = sip_check_restart(ctx.restartIn, rs, &ctx, site0))) return die(rc, sip_host_error());
     processedBefore = rs->processedSteps;
+    totGppBefore = rs->trackers[20]; /* trackers.totGpp */
     sip_restart_to_state(rs, state, 1, ringV, ringW, 1);
     if ((rc = sipnet_gpu_set_state(h, state, 1, ringV, ringW, 1, 0))) return die(rc, sipnet_gpu_last_error());
     free(rs);
@@ -222,7 +221,7 @@ int main(int argc, char **argv) {
   }
 
   /* ---- writers: outputState() per step, events.out rows ---- */
-  if (ctx.doMainOutput) {
+  if (ctx.doMainOutput || ctx.doSingleOutputs) {
     const size_t n = (size_t)SIPNET_GPU_NOUT * (size_t)T * (size_t)M;
     double *buf = (double *)malloc(n * sizeof(double));
     if (!buf) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
@@ -231,6 +230,33 @@ int main(int argc, char **argv) {
       const site_job *job = &jobs[s];
       for (int64_t k = 0; k < job->nmembers; ++k) {
         const int64_t m = job->member0 + k;
+        if (ctx.doSingleOutputs) { /* setupOutputItems() + writeOutputItemValues(), sipnet.c:1993-1998, outputItems.c:126-148 */
+          static const char *const kItems[4] = {"NEE", "NEE_cum", "GPP", "GPP_cum"};
+          static const int kCols[4] = {SIPNET_O_nee, SIPNET_O_cumNEE, SIPNET_O_gpp, -1};
+          for (int it = 0; it < 4; ++it) {
+            char name[SIP_NAME_MAX + 48];
+            if (job->memberList[0])
+              snprintf(name, sizeof name, "%s.%s.%lld", job->prefix, kItems[it], (long long)k);
+            else
+              snprintf(name, sizeof name, "%s.%s", job->prefix, kItems[it]);
+            FILE *sf = fopen(name, "w");
+            if (!sf) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open a single-variable output file");
+            double totGpp = totGppBefore; /* trackers.totGpp += trackers.gpp, the reference's own accumulation order */
+            for (int64_t t = 0; t < job->data.nsteps; ++t) {
+              double v;
+              if (kCols[it] >= 0) {
+                v = buf[((size_t)kCols[it] * (size_t)T + (size_t)t) * (size_t)M + (size_t)m];
+              } else {
+                totGpp += buf[((size_t)SIPNET_O_gpp * (size_t)T + (size_t)t) * (size_t)M + (size_t)m];
+                v = totGpp;
+              }
+              fprintf(sf, "%f ", v);
+            }
+            fprintf(sf, "\n");
+            fclose(sf);
+          }
+        }
+        if (!ctx.doMainOutput) continue;
         FILE *o = out;
         if (!o) {
           char name[SIP_NAME_MAX + 32];

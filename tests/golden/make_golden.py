@@ -123,6 +123,25 @@ def debug_log_md5():
     print("debug log md5:", res)
 
 
+def single_outputs_md5():
+    """md5 of the reference binary's --do-single-outputs files (<prefix>.NEE, .NEE_cum, .GPP, .GPP_cum) for the smoke
+    cases -> tests/golden/single_outputs_md5.json"""
+    import json
+    import shutil
+    import subprocess
+    res = {}
+    for name in SMOKE:
+        with tempfile.TemporaryDirectory() as td:
+            for fn in ("sipnet.in", "sipnet.param", "sipnet.clim", "events.in"):
+                shutil.copy(os.path.join(REF, "tests", "smoke", name, fn), td)
+            subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "sipnet_ref"), "-i", "sipnet.in", "--quiet",
+                                   "--do-single-outputs"], cwd=td, stdout=subprocess.DEVNULL)
+            res[name] = {k: hashlib.md5(open(os.path.join(td, "sipnet." + k), "rb").read()).hexdigest()
+                         for k in ("NEE", "NEE_cum", "GPP", "GPP_cum")}
+    json.dump(res, open(os.path.join(OUT, "single_outputs_md5.json"), "w"), indent=1)
+    print("single outputs md5:", res)
+
+
 def restart_golden():
     """A checkpoint written by the reference binary (russell_2 cut after 2016), the reference's verdict (exit
     code) on every tampered variant in tests/restart_cases.py, and md5s of what the reference produces when it
@@ -185,6 +204,7 @@ def balance_fixtures(shim):
 def main():
     pack_smoke_inputs()
     debug_log_md5()
+    single_outputs_md5()
     restart_golden()
     shim = RefShim()
     for name, flags in SMOKE.items():

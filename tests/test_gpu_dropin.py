@@ -223,3 +223,16 @@ def test_site_list_runs_many_sites_in_one_launch(smoke_dir, tmp_path):
     assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "empty.txt"], cwd=work).returncode == 5
     assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "missing.txt"], cwd=work).returncode == 6
     assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "sites.txt", "--restart-out", "x"], cwd=work).returncode == 8
+
+
+@pytest.mark.parametrize("case", SMOKE)
+def test_single_variable_outputs_byte_identical(smoke_dir, case):
+    """--do-single-outputs: <prefix>.NEE / .NEE_cum / .GPP / .GPP_cum equal the reference's files (md5 from
+    tests/golden/make_golden.py); GPP_cum is accumulated on the host in the reference's own addition order."""
+    want = json.load(open(os.path.join(GOLDEN_DIR, "single_outputs_md5.json")))[case]
+    d = os.path.join(smoke_dir, case)
+    r = subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--do-single-outputs", "--no-do-main-output"], cwd=d,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for k, md5 in want.items():
+        assert hashlib.md5(open(os.path.join(d, "sipnet." + k), "rb").read()).hexdigest() == md5, k

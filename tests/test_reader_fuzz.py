@@ -239,10 +239,6 @@ def test_config_parser_agrees_with_reference_on_mutants(smoke_dir, tmp_path):
             assert codes["ours"] not in (0, 100), (n, lines)
             continue
         if codes["ref"] == 0:
-            single = [ln.split()[-1] for ln in dumps["ref"] or [] if ln.split() and ln.split()[0].startswith("DO_SINGLE_OUTPUT")]
-            if single and single[0] != "0":
-                assert codes["ours"] == 8          # single-variable outputs are deliberately not offered
-                continue
             accepted += 1
             assert codes["ours"] in (0, 100), (n, codes, lines, extra)
             assert dumps["ours"] == dumps["ref"], (n, lines, extra)
