@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SIPNET_GPU_ABI_VERSION 2
+#define SIPNET_GPU_ABI_VERSION 3
 
 /* ---- return codes: reference src/common/exitCodes.h:16-27 ---------------- */
 #define SIPNET_GPU_OK 0
@@ -416,6 +416,51 @@ int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t nrows, int
  * on host arrays of n doubles, so the device libm can be compared bit for bit with the
  * reference's host libm (glibc) -- see sipnet_b200/csrc/sip_libm.cuh. */
 int sipnet_gpu_eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------------------
+ * Members are independent (no cross-member term anywhere in updateState(), sipnet.c:1818-1855), so the loop
+ * `while (climate) { updateState(); ... }` (sipnet.c:1969-1982) shards trivially: every GPU integrates its share
+ * and `run` needs no communication.  NCCL appears only in the final gather of log-likelihoods and of the summaries
+ * of a site whose members are spread over GPUs.  NCCL is loaded at run time (libnccl.so.2) by these entry points
+ * only.
+ *
+ * (a) one process per GPU (torchrun, mpirun, ...): each rank creates its handle with ITS members of every site
+ *     (all ranks list the same sites; rank order = member order) and joins a team: rank 0 makes the id, the
+ *     caller's launcher broadcasts its SIPNET_GPU_COMM_ID_BYTES bytes, every rank calls init_rank (collective).
+ */
+#define SIPNET_GPU_COMM_ID_BYTES 128
+typedef struct sipnet_gpu_comm sipnet_gpu_comm;
+int sipnet_gpu_comm_unique_id(void *id);
+int sipnet_gpu_comm_init_rank(sipnet_gpu_handle *h, int32_t nranks, int32_t rank, const void *id, sipnet_gpu_comm **out);
+void sipnet_gpu_comm_destroy(sipnet_gpu_comm *c); /* before sipnet_gpu_destroy() of the handle */
+int32_t sipnet_gpu_comm_nranks(const sipnet_gpu_comm *c);
+/* Collective.  Ensemble mean / variance / exact quantiles of the last run range over the members of ALL ranks,
+ * into the handle's summary buffers: gather(MEAN / VARIANCE / QUANTILES) and device_ptr() then return the team's
+ * result on every rank.  No member value leaves its GPU: per key-bit level the ranks all-reduce 8 KB of histogram
+ * per (site, column, step) row (sip_gsum.cuh).  With nranks == 1 the same kernels run without any exchange. */
+int sipnet_gpu_comm_summaries(sipnet_gpu_comm *c);
+/* Histogram levels the last sipnet_gpu_comm_summaries() needed (diagnostic). */
+int32_t sipnet_gpu_comm_last_levels(const sipnet_gpu_comm *c);
+/* Collective.  Log-likelihoods of the members of all ranks, rank-major: double [sum of member counts]. */
+int sipnet_gpu_comm_gather_loglik(sipnet_gpu_comm *c, double *dst, size_t bytes);
+int sipnet_gpu_comm_member_counts(const sipnet_gpu_comm *c, int64_t *counts /* [nranks] */);
+
+/* (b) one process, one host thread, several GPUs: the single-GPU configuration, partitioned by the library --
+ *     whole sites per device when there are at least as many sites as devices, otherwise an even contiguous share
+ *     of every site's members per device.  ndevices <= 0: all visible devices; devices == NULL: 0..ndevices-1.
+ *     cfg->device and cfg->stream are ignored (a caller stream cannot span devices: rejected if set).
+ *     gather() delivers exactly what one GPU would: per-member data in the configuration's member order, summaries
+ *     per site (through the team select when a site is split).  This is what `sipnet_gpu --site-list` uses. */
+typedef struct sipnet_gpu_multi sipnet_gpu_multi;
+int sipnet_gpu_multi_init(const sipnet_gpu_config *cfg, int32_t ndevices, const int32_t *devices, sipnet_gpu_multi **out);
+int sipnet_gpu_multi_run(sipnet_gpu_multi *m, int64_t step_begin, int64_t step_end); /* clamped per device to its longest site */
+int sipnet_gpu_multi_gather(sipnet_gpu_multi *m, int what, void *dst, size_t bytes);
+size_t sipnet_gpu_multi_gather_bytes(const sipnet_gpu_multi *m, int what);
+int sipnet_gpu_multi_reset(sipnet_gpu_multi *m);
+int sipnet_gpu_multi_sync(sipnet_gpu_multi *m);
+int32_t sipnet_gpu_multi_ndevices(const sipnet_gpu_multi *m);
+sipnet_gpu_handle *sipnet_gpu_multi_handle(sipnet_gpu_multi *m, int32_t i); /* device i's handle (owned by m) */
+void sipnet_gpu_multi_destroy(sipnet_gpu_multi *m);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+COMM_ID_BYTES = 128
 
 # reference src/common/context.h:45-56
 FLAG_NAMES = (

@@ -88,6 +88,41 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sipnet_gpu_rows_summary.restype = C.c_int
     lib.sipnet_gpu_rows_summary.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    # multi-GPU entry points
+    lib.sipnet_gpu_comm_unique_id.restype = C.c_int
+    lib.sipnet_gpu_comm_unique_id.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_comm_init_rank.restype = C.c_int
+    lib.sipnet_gpu_comm_init_rank.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.sipnet_gpu_comm_destroy.restype = None
+    lib.sipnet_gpu_comm_destroy.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_comm_nranks.restype = C.c_int32
+    lib.sipnet_gpu_comm_nranks.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_comm_summaries.restype = C.c_int
+    lib.sipnet_gpu_comm_summaries.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_comm_last_levels.restype = C.c_int32
+    lib.sipnet_gpu_comm_last_levels.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_comm_gather_loglik.restype = C.c_int
+    lib.sipnet_gpu_comm_gather_loglik.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.sipnet_gpu_comm_member_counts.restype = C.c_int
+    lib.sipnet_gpu_comm_member_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sipnet_gpu_multi_init.restype = C.c_int
+    lib.sipnet_gpu_multi_init.argtypes = [C.POINTER(A.Config), C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.sipnet_gpu_multi_run.restype = C.c_int
+    lib.sipnet_gpu_multi_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.sipnet_gpu_multi_gather.restype = C.c_int
+    lib.sipnet_gpu_multi_gather.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.sipnet_gpu_multi_gather_bytes.restype = C.c_size_t
+    lib.sipnet_gpu_multi_gather_bytes.argtypes = [C.c_void_p, C.c_int]
+    lib.sipnet_gpu_multi_reset.restype = C.c_int
+    lib.sipnet_gpu_multi_reset.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_multi_sync.restype = C.c_int
+    lib.sipnet_gpu_multi_sync.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_multi_ndevices.restype = C.c_int32
+    lib.sipnet_gpu_multi_ndevices.argtypes = [C.c_void_p]
+    lib.sipnet_gpu_multi_handle.restype = C.c_void_p
+    lib.sipnet_gpu_multi_handle.argtypes = [C.c_void_p, C.c_int32]
+    lib.sipnet_gpu_multi_destroy.restype = None
+    lib.sipnet_gpu_multi_destroy.argtypes = [C.c_void_p]
     lib.sipnet_gpu_eval_libm.restype = C.c_int
     lib.sipnet_gpu_eval_libm.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     if path is None:
@@ -192,6 +227,18 @@ class Ensemble:
                  nee_sigma: float = 1.0, max_event_records: int = 0,
                  block_threads: int = 0, stream: int = 0, ring_slots: int = 0, lib: Optional[C.CDLL] = None):
         self.lib = lib or load_library()
+        cfg = self._configure(sites, params, member_site, flags, outputs, math, device, out_steps_capacity, summary_cols,
+                              quantiles, nee_sigma, max_event_records, block_threads, stream, ring_slots)
+        self.handle = C.c_void_p()
+        rc = self.lib.sipnet_gpu_init(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            self.handle = None
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (0, 0)
+
+    def _configure(self, sites, params, member_site, flags, outputs, math, device, out_steps_capacity, summary_cols,
+                   quantiles, nee_sigma, max_event_records, block_threads, stream, ring_slots) -> "A.Config":
+        """sipnet_gpu_config from numpy inputs (the arrays it points into are kept alive in self._keep)."""
         params = np.ascontiguousarray(params, dtype=np.float64)
         if params.ndim != 2 or params.shape[0] != A.NPARAMS:
             raise ValueError("params must be float64 [80][M] (struct Parameters order)")
@@ -238,12 +285,7 @@ class Ensemble:
         self.n_quantiles = int(q.size)
         self.max_event_records = max_event_records
         self.max_steps = max(s.nsteps for s in self.sites)
-        self.handle = C.c_void_p()
-        rc = self.lib.sipnet_gpu_init(C.byref(cfg), C.byref(self.handle))
-        if rc != 0:
-            self.handle = None
-            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
-        self.last_range = (0, 0)
+        return cfg
 
     # -- reference: the while(climate) loop, sipnet.c:1969-1982
     def run(self, step_begin: int = 0, step_end: Optional[int] = None) -> None:
@@ -400,7 +442,41 @@ class Ensemble:
     def device_ptr(self, what: int) -> int:
         return int(self.lib.sipnet_gpu_device_ptr(self.handle, what) or 0)
 
+    # -- multi-GPU, one process per GPU (sipnet_gpu_comm_*): this handle holds ITS members of every site
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+
+    def join_team(self, nranks: int = 1, rank: int = 0, comm_id: Optional[bytes] = None) -> None:
+        """Collective.  comm_id: the 128 bytes of unique_comm_id() made on rank 0 and broadcast by the launcher."""
+        self.comm = C.c_void_p()
+        buf = C.create_string_buffer(comm_id, A.COMM_ID_BYTES) if comm_id is not None else None
+        self._check(self.lib.sipnet_gpu_comm_init_rank(self.handle, nranks, rank, buf, C.byref(self.comm)))
+        self.team_size = nranks
+
+    def team_summaries(self) -> None:
+        """Collective.  Afterwards mean() / variance() / quantiles() return the whole team's result."""
+        self._check(self.lib.sipnet_gpu_comm_summaries(self.comm))
+
+    def team_last_levels(self) -> int:
+        return int(self.lib.sipnet_gpu_comm_last_levels(self.comm))
+
+    def team_member_counts(self) -> np.ndarray:
+        counts = np.zeros(self.team_size, np.int64)
+        self._check(self.lib.sipnet_gpu_comm_member_counts(self.comm, counts.ctypes.data))
+        return counts
+
+    def team_loglik(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Collective.  Log-likelihoods of all ranks' members, rank-major."""
+        if out is None:
+            out = np.empty(int(self.team_member_counts().sum()), np.float64)
+        self._check(self.lib.sipnet_gpu_comm_gather_loglik(self.comm, out.ctypes.data, out.nbytes))
+        return out
+
     def close(self) -> None:
+        if getattr(self, "comm", None):
+            self.lib.sipnet_gpu_comm_destroy(self.comm)
+            self.comm = None
         if self.handle:
             self.lib.sipnet_gpu_destroy(self.handle)
             self.handle = None
@@ -416,3 +492,74 @@ class Ensemble:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def unique_comm_id(lib: Optional[C.CDLL] = None) -> bytes:
+    """sipnet_gpu_comm_unique_id: made on rank 0, broadcast to the other ranks by the caller's launcher."""
+    lib = lib or load_library()
+    buf = C.create_string_buffer(A.COMM_ID_BYTES)
+    rc = lib.sipnet_gpu_comm_unique_id(buf)
+    if rc != 0:
+        raise SipnetGpuError(rc, (lib.sipnet_gpu_last_error() or b"").decode())
+    return buf.raw
+
+
+class MultiEnsemble(Ensemble):
+    """One process, several GPUs (sipnet_gpu_multi_*): the single-GPU configuration, partitioned by the library.
+    gather-style accessors return exactly what one GPU would."""
+
+    def __init__(self, sites: Sequence[SiteData], params: np.ndarray, member_site: Optional[np.ndarray] = None,
+                 flags: Optional[dict] = None, outputs: int = A.OUT_FULL, math: int = A.MATH_VALIDATION,
+                 devices: Optional[Sequence[int]] = None, out_steps_capacity: int = 0,
+                 summary_cols: Sequence[int] = (), quantiles: Sequence[float] = (), nee_sigma: float = 1.0,
+                 max_event_records: int = 0, block_threads: int = 0, ring_slots: int = 0, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self.handle = None
+        cfg = self._configure(sites, params, member_site, flags, outputs, math, 0, out_steps_capacity, summary_cols,
+                              quantiles, nee_sigma, max_event_records, block_threads, 0, ring_slots)
+        devs = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+        self.multi = C.c_void_p()
+        rc = self.lib.sipnet_gpu_multi_init(C.byref(cfg), int(devs.size), devs.ctypes.data if devs.size else None,
+                                            C.byref(self.multi))
+        if rc != 0:
+            self.multi = None
+            raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())
+        self.last_range = (0, 0)
+        self._ring_slots = int(self.lib.sipnet_gpu_ring_slots(self.lib.sipnet_gpu_multi_handle(self.multi, 0)))
+
+    @property
+    def ndevices(self) -> int:
+        return int(self.lib.sipnet_gpu_multi_ndevices(self.multi))
+
+    @property
+    def ring_slots(self) -> int:
+        return self._ring_slots
+
+    def run(self, step_begin: int = 0, step_end: Optional[int] = None) -> None:
+        if step_end is None:
+            step_end = self.max_steps
+        self._check(self.lib.sipnet_gpu_multi_run(self.multi, step_begin, step_end))
+        self.last_range = (step_begin, step_end)
+
+    def gather_into(self, what: int, out: np.ndarray) -> None:
+        self._check(self.lib.sipnet_gpu_multi_gather(self.multi, what, out.ctypes.data_as(C.c_void_p), out.nbytes))
+
+    def event_records(self):
+        n = self.nmembers * self.max_event_records
+        buf = (A.EventRecord * n)()
+        self._check(self.lib.sipnet_gpu_multi_gather(self.multi, A.GATHER_EVENT_RECORDS, C.cast(buf, C.c_void_p), C.sizeof(buf)))
+        counts = self.event_counts()
+        return [[buf[m * self.max_event_records + i] for i in range(min(int(counts[m]), self.max_event_records))]
+                for m in range(self.nmembers)]
+
+    def sync(self) -> None:
+        self.lib.sipnet_gpu_multi_sync(self.multi)
+
+    def reset(self) -> None:
+        self._check(self.lib.sipnet_gpu_multi_reset(self.multi))
+        self.last_range = (0, 0)
+
+    def close(self) -> None:
+        if getattr(self, "multi", None):
+            self.lib.sipnet_gpu_multi_destroy(self.multi)
+            self.multi = None

@@ -138,6 +138,18 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
   if (recCount != nullptr) recCount[m] = 0;
 }
 
+// (3) which device parameter rows hold the same value (bit for bit) for every member: those rows take one slot per
+// block in the packed tile of the throughput variants (sip_step.cuh PackedTile).  One block per row.
+__global__ void uniform_rows_kernel(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform) {
+  const int k = blockIdx.x;
+  const unsigned long long *row = reinterpret_cast<const unsigned long long *>(params) + (int64_t)k * ld;
+  const unsigned long long first = row[0];
+  int same = 1;
+  for (int64_t m = threadIdx.x; m < nmembers; m += blockDim.x) same &= (row[m] == first) ? 1 : 0;
+  same = __syncthreads_and(same);
+  if (threadIdx.x == 0) uniform[k] = same;
+}
+
 // ---- host-side launchers (C++ linkage inside the library) -------------------------------------
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
@@ -170,6 +182,11 @@ cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t
   const int threads = 128;
   const int blocks = (int)((nmembers + threads - 1) / threads);
   derive_params_kernel<<<blocks, threads, 0, stream>>>(params, ld, nmembers, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream) {
+  uniform_rows_kernel<<<kNParamDev, 256, 0, stream>>>(params, ld, nmembers, uniform);
   return cudaGetLastError();
 }
 

@@ -25,14 +25,29 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "sip_step.cuh"
+
+#ifndef SIP_MIN_BLOCKS_128
+#define SIP_MIN_BLOCKS_128 1
+#endif
 
 namespace sip {
 namespace k1 {
 
+constexpr int kChunkSteps = 32;  // steps staged per TMA chunk (default): 32 * 176 B = 5632 B
 
-constexpr int kChunkSteps = 32;  // steps staged per TMA chunk: 32 * 128 B = 4096 B
+// Tuning policy of one instantiation.  The default is what the latency-bound configurations want (a lone warp per
+// scheduler: everything unrolled, 255 registers, one value per thread for every parameter row).  The throughput
+// policies trade per-warp speed for resident warps: registers capped by MIN_BLOCKS, the packed parameter tile,
+// smaller forcing chunks (shared memory) and smaller canopy groups (fewer live values).
+template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), bool PACKED = false,
+          int CHUNK = kChunkSteps, int CANOPY = 7>
+struct Tune {
+  static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK, kCanopy = CANOPY;
+  static constexpr bool kPacked = PACKED;
+};
 
 // ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -231,21 +246,21 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-#ifndef SIP_MIN_BLOCKS_128
-#define SIP_MIN_BLOCKS_128 1
-#endif
 // One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
 // `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN>
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN>
 __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t blk, int64_t itemBegin, int64_t itemEnd,
                                          int &sc, double *tile, ClimRec *climBuf, uint64_t *libmTab, uint64_t *bars) {
+  constexpr int kChunkSteps = TN::kChunk;
   const int tid = threadIdx.x;
   const BlockDesc bd = a.blocks[blk];
   const SiteDev site = a.sites[bd.site];
   const int64_t m = (int64_t)bd.member0 + tid;
   bool active = tid < bd.count;
   if (REPLAY) {
-    active = active && ((a.status[m] & SIPNET_GPU_ST_REPLAY) != 0) && ((a.statusBackup[m] & SIPNET_GPU_ST_REPLAY) == 0);
+    // kStNeedsReplay is per segment: set by the optimistic kernel of THIS segment only (statusBackup never holds it),
+    // so a member that leaves the guards in several segments is replayed in every one of them
+    active = active && ((a.status[m] & kStNeedsReplay) != 0);
     if (!__syncthreads_or(active ? 1 : 0)) return;  // nothing to replay in this block (the normal case)
   }
 
@@ -253,10 +268,30 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
 
   // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
-  for (int k = 0; k < kNParamDev; ++k) {
-    const int slot = tile_slot(k);
-    if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+  if constexpr (TN::kPacked) {
+    // (with dynamic scheduling the barrier at the top of the item loop already separates this fill from the
+    // previous item's readers of the block-uniform slots)
+    unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
+    for (int k = 0; k < kNParamDev; ++k) {
+      if (tile_slot(k) < 0) continue;
+      if (a.rowOM[k].y == 0u) {
+        *reinterpret_cast<double *>(tb + a.rowOM[k].x + 8u * (uint32_t)tid) = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+      } else if (tid == 0) {  // same value for every member of the launch: one slot per block
+        *reinterpret_cast<double *>(tb + a.rowOM[k].x) = a.params[(int64_t)k * a.ld + bd.member0];
+      }
+    }
+    __syncthreads();  // the block-uniform slots are read by every thread
+  } else {
+    for (int k = 0; k < kNParamDev; ++k) {
+      const int slot = tile_slot(k);
+      if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
+    }
   }
+  using PT = std::conditional_t<TN::kPacked, PackedTile<TN::kCanopy>, DirectTile>;
+  const PT prm = [&]() -> PT {
+    if constexpr (TN::kPacked) return PT{reinterpret_cast<const unsigned char *>(tile) + 8 * tid, 8u * (uint32_t)tid, a};
+    else return PT{tile + tid, BLOCK};
+  }();
 
   auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, min(cs + kChunkSteps, t1)) as chunk `serial`
     const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
@@ -282,7 +317,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
       if (a.recCount != nullptr) a.recCount[m] = a.recCountBackup[m];
     }
     load_member<DYN>(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
-    if (REPLAY) mb.status |= SIPNET_GPU_ST_REPLAY;
+    if (REPLAY) mb.status = (mb.status & ~kStNeedsReplay) | SIPNET_GPU_ST_REPLAY;  // sticky, informational
     if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) {  // reference would have exited (sipnet.c:1117-1122)
       active = false;
       // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
@@ -304,12 +339,13 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     // the member-constant divisors must be ordinary numbers (sip_num.cuh divisor_check)
     const int divisors[] = {SIPNET_P_leafCSpWt, kPsnTRangeSqSlot, SIPNET_P_halfSatPar, SIPNET_P_soilWHC, kTwoWhc,
                             SIPNET_P_leafCN,    SIPNET_P_woodCN,  SIPNET_P_fineRootCN, SIPNET_P_fAnoxia, kOneMinusFa};
-    for (int k : divisors) nm.divisor_check(tile[tile_slot(k) * BLOCK + tid]);
-    if (fl.on(F_CSAT)) nm.divisor_check(tile[tile_slot(SIPNET_P_soilCSaturation) * BLOCK + tid]);
+    for (int k : divisors) nm.divisor_check(prm(k));
+    if (fl.on(F_CSAT)) nm.divisor_check(prm(SIPNET_P_soilCSaturation));
   }
   const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
-  const ParamTile prm{tile + tid, BLOCK};
   const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
+  if (active) ring_load_head(mb, rg);
+  else mb.headW = mb.headV = 0.0;
   RecSinkT<DYN> rec{nullptr, nullptr, a.maxRecs, 0};
   if (a.recCount != nullptr && active) {
     rec.count = a.recCount + m;
@@ -338,7 +374,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     __syncthreads();  // everyone is done reading this buffer before it is refilled
   }
   if (active) {
-    if (NM::kFast && nm.bad) mb.status |= SIPNET_GPU_ST_REPLAY;  // outside the optimistic guards: general kernel re-runs it
+    if (NM::kFast && nm.bad) mb.status |= kStNeedsReplay;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
     if (a.loglik != nullptr && site.neeObs != nullptr) {  // running sums continue across segments in step order
       a.loglik[m] = emit.ll;
@@ -352,14 +388,20 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
 // itemSteps steps), handed out in sub-range-major order by an atomic counter, so a member count that fills a
 // fractional number of waves no longer leaves SMs idle.  Item (b, s) needs (b, s-1); items are claimed in order,
 // so the predecessor was claimed earlier by a running CTA that waits for nothing later -- no deadlock.
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1))
-    run_kernel(const __grid_constant__ RunArgs a) {
+template <class TN>
+__host__ __device__ constexpr size_t fixed_smem_bytes() {  // forcing ring + libm tables + mbarriers
+  return 2 * (size_t)TN::kChunk * sizeof(ClimRec) + kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
+}
+
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN = Tune<BLOCK>>
+__global__ void __launch_bounds__(BLOCK, TN::kMinBlocks) run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *tile = reinterpret_cast<double *>(smem_raw);                                   // [kNTileRows][BLOCK]
-  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw + sizeof(double) * kNTileRows * BLOCK);  // [2][kChunkSteps]
-  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * kChunkSteps);           // [kLibmTabWords]
-  uint64_t *bars = libmTab + kLibmTabWords;                                              // [2]
+  // [forcing ring 2 x kChunk][libm tables][mbarriers][parameter tile]: the tile comes last because the packed
+  // tile's size is only known at launch
+  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw);                     // [2][kChunk]
+  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * TN::kChunk);   // [kLibmTabWords]
+  uint64_t *bars = libmTab + kLibmTabWords;                                     // [2]
+  double *tile = reinterpret_cast<double *>(bars + 2);                          // direct: [kNTileRows][BLOCK]
 
   const int tid = threadIdx.x;
   const FL fl(a.flags);
@@ -376,7 +418,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
 
   int sc = 0;
   if constexpr (!DYN) {
-    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
+    run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false, TN>(a, fl, blockIdx.x, a.stepBegin, a.stepEnd, sc, tile, climBuf, libmTab, bars);
   } else {
     __shared__ long long sItem;
     const int64_t nsub = (a.stepEnd - a.stepBegin + a.itemSteps - 1) / a.itemSteps;
@@ -396,7 +438,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1)
       }
       const int64_t itemBegin = a.stepBegin + sub * (int64_t)a.itemSteps;
       const int64_t itemEnd = itemBegin + a.itemSteps < a.stepEnd ? itemBegin + a.itemSteps : a.stepEnd;
-      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
+      run_item<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true, TN>(a, fl, blk, itemBegin, itemEnd, sc, tile, climBuf, libmTab, bars);
       __syncthreads();  // every member's state is stored ...
       if (tid == 0) {   // ... before the sub-range is published (release)
         const int64_t w1 = sItem;
@@ -427,22 +469,21 @@ inline int dynamic_max_waves() {
 
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * kNTileRows * BLOCK + 2 * kChunkSteps * sizeof(ClimRec) +
-                      kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
-  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false>;
+  using TN = Tune<BLOCK>;
+  const size_t smem = fixed_smem_bytes<TN>() + sizeof(double) * kNTileRows * BLOCK;
+  auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false, TN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   RunArgs args = a;
   args.nblocks = nblocks;
   args.itemSteps = kItemSteps;
   int grid = nblocks;
-  bool dynamic = false;
   if constexpr (!REPLAY && !DEBUG && NM::kFast) {
     if (a.workCounter != nullptr) {
       // More block descriptors than resident CTAs: whole waves would quantise the run time (1.4 waves cost 2,
       // 3.46 cost ~3.6), so a persistent grid pulls (block, sub-range) items instead.  Measured: 32 768 members
       // 57.6 -> 42.3 ms, 131 072 members 122.6 -> 108.3 ms, 262 144 members (6.9 waves) 219.4 -> 216.8 ms.
-      auto dyn = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true>;
+      auto dyn = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, true, TN>;
       int dev = 0, sms = 0, perSm = 0;
       if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
       if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -450,17 +491,57 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, BLOCK, smem)) != cudaSuccess) return e;
       const int resident = sms * perSm;
       if (resident > 0 && nblocks > resident && nblocks < dynamic_max_waves() * resident) {
-        dynamic = true;
         grid = resident;
         dyn<<<grid, BLOCK, smem, stream>>>(args);
         return cudaGetLastError();
       }
     }
   }
-  (void)dynamic;
   args.workCounter = nullptr;
   kern<<<grid, BLOCK, smem, stream>>>(args);
   return cudaGetLastError();
+}
+
+// Throughput variants (128-member blocks, dynamic scheduling, packed tile): MINB resident blocks per SM.
+// Returns cudaErrorInvalidConfiguration when the variant does not apply (the caller falls back to launch_one):
+// no packed tile, no dynamic-scheduling words, or the packed tile is too large for MINB blocks to share an SM.
+template <class FL, bool FULL, int MINB>
+static cudaError_t launch_packed(const RunArgs &a, int nblocks, cudaStream_t stream) {
+#ifdef SIP_EXPERIMENT_PACK_MINB  // measurement builds: the packed tile at another register budget
+  using TN = Tune<128, SIP_EXPERIMENT_PACK_MINB, true, 16, 7>;
+#else
+  using TN = Tune<128, MINB, true, 16, (MINB >= 4 ? 2 : 4)>;
+#endif
+  if (a.packedTileBytes <= 0 || a.workCounter == nullptr) return cudaErrorInvalidConfiguration;
+  const size_t smem = fixed_smem_bytes<TN>() + (size_t)a.packedTileBytes;
+  auto dyn = run_kernel<FL, false, FastNum, 128, false, FULL, true, TN>;
+  cudaError_t e;
+  int dev = 0, sms = 0, perSm = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if (cudaFuncSetAttribute(dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return cudaErrorInvalidConfiguration;
+  }
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, 128, smem)) != cudaSuccess) return e;
+  if (perSm < TN::kMinBlocks) return cudaErrorInvalidConfiguration;  // the tile has too many per-member rows for this variant
+  const int resident = sms * perSm;
+  if (nblocks < resident) return cudaErrorInvalidConfiguration;  // not enough members to fill the extra slots
+  RunArgs args = a;
+  args.nblocks = nblocks;
+  args.itemSteps = kItemSteps;
+  dyn<<<resident, 128, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// A/B switch for measurements: SIPNET_GPU_OCC = 2 (never use the throughput variants), 3 or 4 (prefer that variant)
+inline int preferred_occupancy() {
+  static const int v = [] {
+    const char *e = getenv("SIPNET_GPU_OCC");
+    const int n = e ? atoi(e) : 0;
+    return (n >= 2 && n <= 4) ? n : 0;
+  }();
+  return v;
 }
 
 template <class FL, int BLOCK>

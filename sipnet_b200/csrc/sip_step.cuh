@@ -42,12 +42,32 @@ struct RuntimeFlags {
   __device__ __forceinline__ bool on(uint32_t bit) const { return (mask & bit) != 0; }
 };
 
-// ---- parameter tile in shared memory: element k of this thread at tile[k * stride] ----
-struct ParamTile {
+// ---- parameter tile in shared memory ----------------------------------------------------------
+// DirectTile: every staged row holds one value per thread, element k of this thread at tile[slot(k) * stride].
+// kCanopyGroup = how many canopy layers of calcLightEff() are issued stage by stage together (7 = all).
+struct DirectTile {
+  static constexpr int kCanopyGroup = 7;
   const double *base;  // already offset by threadIdx.x
   int stride;
   // k is always a compile-time constant at the call sites, so tile_slot(k) folds to a constant
   __device__ __forceinline__ double operator()(int k) const { return base[tile_slot(k) * stride]; }
+};
+// PackedTile (throughput variants): a row whose value is the same for EVERY member of the launch -- in a real
+// ensemble most of the 80 parameters are fixed and only the "estimated" ones are drawn per member -- is stored once
+// per block (8 bytes, read as a broadcast) instead of once per thread.  Which rows are uniform is found on the
+// device after every parameter upload (uniform_rows_kernel) and reaches the kernel as two words per row in its
+// parameter space: byte offset and an all-ones / zero mask for the thread's own offset.  The tile shrinks from
+// 90 x BLOCK x 8 B to (varying rows) x BLOCK x 8 B, which is what lets 3-4 blocks share an SM.
+template <int GROUP>
+struct PackedTile {
+  static constexpr int kCanopyGroup = GROUP;
+  const unsigned char *mine;  // shared-memory tile + threadIdx.x * 8
+  uint32_t tid8;              // threadIdx.x * 8
+  const RunArgs &a;           // __grid_constant__ kernel parameter: rowOff / rowMask reads are constant-bank operands
+  // rowMask[k] = 0 for a per-member row, all ones for a block-uniform row (whose slot takes no thread offset)
+  __device__ __forceinline__ double operator()(int k) const {
+    return *reinterpret_cast<const double *>(mine + (int)(a.rowOM[k].x - (tid8 & a.rowOM[k].y)));
+  }
 };
 #define SIP_P(name) prm(SIPNET_P_##name)
 
@@ -74,6 +94,9 @@ struct Member {
   double gdd, totNee, wetFrac;
   double dTill;    // eventTrackers.d_till_mod, events.h:213-221
   double ringSum;  // MeanTracker.sum, runmean.h
+  // the ring's oldest entry (slot ringStart), loaded one step ahead of its use: the push at the end of step t needs
+  // it first, and a load issued there would sit on the critical path with an L2 round trip
+  double headW, headV;
   int ringStart, ringLast;
   int trkLastYear;   // trackers.lastYear
   int phenLastYear;  // phenologyTrackers.lastYear
@@ -110,11 +133,19 @@ struct RingRefT {
 };
 
 template <class RG>
+__device__ __forceinline__ void ring_load_head(Member &mb, const RG &rg) {
+  mb.headW = rg.wgt(mb.ringStart);
+  mb.headV = rg.val(mb.ringStart);
+}
+
+template <class RG>
 __device__ __forceinline__ void ring_reset(Member &mb, const RG &rg, double v) {  // runmean.c:44-51
   mb.ringStart = mb.ringLast = 0;
   rg.set_val(0, v);
   rg.set_wgt(0, kMeanNppDays);
   mb.ringSum = v * kMeanNppDays;
+  mb.headW = kMeanNppDays;
+  mb.headV = v;
 }
 
 template <class RG>
@@ -127,9 +158,8 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
   double left = weight;
   int i = mb.ringStart;
   double sum = mb.ringSum;
+  double wi = mb.headW, vi = mb.headV;  // slot ringStart, loaded at the end of the previous step
   while (left > 0) {
-    const double wi = rg.wgt(i);
-    const double vi = rg.val(i);
     if (wi > left) {
       rg.set_wgt(i, wi - left);
       sum -= left * vi;
@@ -138,6 +168,10 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
       sum -= wi * vi;
       left -= wi;
       i = (i + 1 == rg.cap) ? 0 : i + 1;
+      if (left > 0) {
+        wi = rg.wgt(i);
+        vi = rg.val(i);
+      }
     }
   }
   mb.ringStart = i;
@@ -147,6 +181,7 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
     sum += weight * rg.val(i);
     mb.ringSum = sum;
     mb.status |= SIPNET_GPU_ST_RING_OVERFLOW;
+    ring_load_head(mb, rg);
     return;
   }
   mb.ringLast = i;
@@ -154,6 +189,7 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
   rg.set_wgt(i, weight);
   sum += value * weight;
   mb.ringSum = sum;
+  ring_load_head(mb, rg);  // next step's head (after the stores above: it may be the entry just written)
 }
 
 // ---- small helpers ---------------------------------------------------------------
@@ -512,19 +548,25 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
     const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = prm(kSeedHalfSatPar);
     double eff[7];
-    // the seven layers are independent: each stage is issued for all layers before the next one
+    // the layers are independent: each stage is issued for a group of layers before the next stage (all seven
+    // together for the latency-bound variants; smaller groups keep fewer values live when registers are capped)
+    constexpr int G = PT::kCanopyGroup;
 #pragma unroll
-    for (int layer = 0; layer <= 6; ++layer) {
-      const double cumLai = lai * ((double)layer / 6);
-      eff[layer] = nm.exp(-1.0 * att * cumLai);
+    for (int g0 = 0; g0 <= 6; g0 += G) {
+#pragma unroll
+      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
+        const double cumLai = lai * ((double)layer / 6);
+        eff[layer] = nm.exp(-1.0 * att * cumLai);
+      }
+#pragma unroll
+      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
+        const double inten = c.par * eff[layer];
+        eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
+      }
+#pragma unroll
+      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer)
+        eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
     }
-#pragma unroll
-    for (int layer = 0; layer <= 6; ++layer) {
-      const double inten = c.par * eff[layer];
-      eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
-    }
-#pragma unroll
-    for (int layer = 0; layer <= 6; ++layer) eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
     double cum = 0.0;
 #pragma unroll
     for (int layer = 0; layer <= 6; ++layer) {

@@ -21,6 +21,9 @@ constexpr double kTiny = 0.000001;  // reference common/util.h:14
 constexpr double kEps = 1e-8;       // reference balance.h:6
 constexpr double kMeanNppDays = 5.0;  // MEAN_NPP_DAYS, sipnet.c:39
 constexpr int kRingMax = 250;         // MEAN_NPP_MAX_ENTRIES, sipnet.c:40
+// internal status bit (never visible after a run): the optimistic kernel met an input outside its guards in the
+// CURRENT segment; the replay kernel re-runs the member from the segment's start state and clears it
+constexpr uint32_t kStNeedsReplay = 0x80000000u;
 
 // Device parameter rows: the 80 of struct Parameters plus derived per-member constants.
 constexpr int kPsnTRangeSqSlot = SIPNET_GPU_NPARAMS;  // pow((psnTMax - psnTMin) / 2.0, 2), sipnet.c:622
@@ -172,6 +175,10 @@ struct RunArgs {
   unsigned long long *workCounter;  // next work item
   unsigned int *progress;           // [nblocks] sub-ranges completed per block descriptor
   int32_t nblocks, itemSteps;
+  // packed parameter tile of the throughput variants (sip_step.cuh PackedTile): per device row the byte offset in
+  // the tile and the mask of the thread's own offset to be taken off again (0 = one value per member, all ones = one per block)
+  uint2 rowOM[kNParamDev];  // .x = offset, .y = mask
+  int32_t packedTileBytes;  // size of the packed tile for 128-member blocks; 0 = not available
 };
 
 }  // namespace sip

@@ -15,14 +15,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "sip_handle.h"
 #include "sip_libm.cuh"
 #include "sip_types.cuh"
 
@@ -31,6 +34,7 @@ namespace k1 {
 // mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members
 cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream);
 cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);
+cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream);
 cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
                               const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
                               uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
@@ -46,7 +50,7 @@ cudaError_t eval_libm(int device, int op, const double *x, const double *y, doub
 using namespace sip;
 
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...) {
+int sip::fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -61,53 +65,6 @@ static int fail(int code, const char *fmt, ...) {
     if (e__ != cudaSuccess)                                                                        \
       return fail(SIPNET_GPU_ERR_NO_DEVICE, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
   } while (0)
-
-struct sipnet_gpu_handle {
-  int device = 0;
-  uint32_t flags = 0;
-  uint32_t outputs = 0;
-  int math = 0;
-  int64_t nmembers = 0, ld = 0, nsites = 0, maxSteps = 0, maxSiteMembers = 0;
-  int64_t outCap = 0;      // steps of output kept per run
-  int64_t stepsDone = 0;   // next step to run
-  int64_t lastBegin = 0, lastEnd = 0;
-  int blockThreads = 128, nblocks = 0, ringCap = 0;
-  int ncols = 0;  // column slots in `out`
-  int8_t colSlot[SIPNET_GPU_NOUT];
-  std::vector<int32_t> summaryCols;
-  std::vector<double> quantiles;
-  int maxRecs = 0;
-  double sigma = 1.0;
-  bool sitesDiffer = false;
-  bool anyObs = false;
-
-  cudaStream_t stream = nullptr;
-  bool ownStream = false;
-  cudaEvent_t evStart = nullptr, evStop = nullptr, evT0 = nullptr, evT1 = nullptr;
-  cudaStream_t copyStream = nullptr;
-  cudaEvent_t evRunDone[2] = {nullptr, nullptr}, evCopyDone[2] = {nullptr, nullptr};
-  int64_t launches = 0;
-
-  // device memory
-  double *params = nullptr, *state = nullptr, *ringV = nullptr, *ringW = nullptr;
-  uint32_t *status = nullptr;
-  int32_t *memberSite = nullptr;
-  BlockDesc *blocks = nullptr;
-  SiteDev *sites = nullptr;
-  std::vector<void *> siteAllocs;
-  double *out = nullptr, *dbg = nullptr, *loglik = nullptr, *loglikN = nullptr;
-  sipnet_gpu_event_record *recs = nullptr;
-  int32_t *recCount = nullptr;
-  double *mean = nullptr, *var = nullptr, *quant = nullptr;
-  bool staticSched = false;
-  unsigned char *sched = nullptr;  // work counter (8 B, padded to 16) + per-block progress words (dynamic scheduling)
-  // segment-start copies for the replay of members flagged by the optimistic kernel (MATH_FAST only)
-  double *stateBk = nullptr, *ringVBk = nullptr, *ringWBk = nullptr, *loglikBk = nullptr, *loglikNBk = nullptr;
-  uint32_t *statusBk = nullptr;
-  int32_t *recCountBk = nullptr;
-  bool summariesValid = false;
-  std::vector<SiteDev> hostSites;
-};
 
 static uint32_t flag_mask(const sipnet_gpu_flags &f) {
   uint32_t m = 0;
@@ -126,25 +83,42 @@ static uint32_t flag_mask(const sipnet_gpu_flags &f) {
   return m;
 }
 
-// Build one site's ClimRec stream with events bound to steps.  Returns 0 or a reference exit code.
-static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimRec> &recs, std::vector<EventDev> &evs,
-                      double &minLen, int64_t siteIndex) {
-  if (s.nsteps <= 0) return fail(SIPNET_GPU_ERR_INPUT_FILE, "site %lld: no climate data", (long long)siteIndex);
+template <class T>
+static cudaError_t dalloc(T **p, size_t count) {
+  return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// Build one site's ClimRec stream with events bound to steps, into recs[0 .. nsteps) and evs[0 .. nevents).
+// Returns 0 or a reference exit code with its message in `err` (called from worker threads: no global state).
+static int site_fail(std::string &err, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+
+static int64_t site_event_count(const sipnet_gpu_site &s, bool eventsOn) {
+  return (eventsOn && s.events != nullptr) ? s.nevents : 0;  // initEvents(), events.c:427-433
+}
+
+static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, EventDev *evs, double &minLen,
+                      int64_t siteIndex, std::string &err) {
+  if (s.nsteps <= 0) return site_fail(err, SIPNET_GPU_ERR_INPUT_FILE, "site %lld: no climate data", (long long)siteIndex);
   const void *need[] = {s.year, s.day, s.time, s.length, s.tair, s.tsoil, s.par, s.precip,
                         s.vpd,  s.vpdSoil, s.vPress, s.wspd, s.gdd};
   for (const void *p : need)
-    if (p == nullptr) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "site %lld: NULL climate array", (long long)siteIndex);
-  const int64_t nev = (eventsOn && s.events != nullptr) ? s.nevents : 0;  // initEvents(), events.c:427-433
+    if (p == nullptr) return site_fail(err, SIPNET_GPU_ERR_BAD_ARGUMENT, "site %lld: NULL climate array", (long long)siteIndex);
+  const int64_t nev = site_event_count(s, eventsOn);
   if (nev > 0) {  // frontend.c:217-222 / isFirstEventBefore(), events.c:437-447
     const sipnet_gpu_event &e0 = s.events[0];
     const bool before = (e0.year != s.year[0]) ? (e0.year < s.year[0]) : (e0.day < s.day[0]);
     if (before)
-      return fail(SIPNET_GPU_ERR_INPUT_FILE, "site %lld: first event occurs before the start of the climate file",
-                  (long long)siteIndex);
+      return site_fail(err, SIPNET_GPU_ERR_INPUT_FILE, "site %lld: first event occurs before the start of the climate file",
+                       (long long)siteIndex);
   }
-  recs.resize((size_t)s.nsteps);
-  evs.clear();
-  evs.reserve((size_t)nev);
   int64_t e = 0;
   for (int64_t t = 0; t < s.nsteps; ++t) {
     ClimRec &c = recs[(size_t)t];
@@ -162,8 +136,9 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimR
     c.year = s.year[t];
     c.day = s.day[t];
     if (!(c.length > 0))  // events.c:460-465
-      return fail(SIPNET_GPU_ERR_BAD_PARAMETER_VALUE, "site %lld: climate length (%f) on year %d day %d is non-positive",
-                  (long long)siteIndex, c.length, c.year, c.day);
+      return site_fail(err, SIPNET_GPU_ERR_BAD_PARAMETER_VALUE,
+                       "site %lld: climate length (%f) on year %d day %d is non-positive", (long long)siteIndex, c.length,
+                       c.year, c.day);
     minLen = std::min(minLen, c.length);
     c.tillDecay = std::exp(-c.length * (1 / 30.0));  // events.c:816, events.h:58
     {
@@ -185,24 +160,161 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, std::vector<ClimR
     while (e < nev && s.events[e].year <= c.year && s.events[e].day <= c.day) {  // events.c:471
       const sipnet_gpu_event &ev = s.events[e];
       if (ev.year < c.year || ev.day < c.day)  // events.c:476-481
-        return fail(SIPNET_GPU_ERR_INPUT_FILE,
-                    "site %lld: agronomic event for year %d day %d has no corresponding climate record",
-                    (long long)siteIndex, ev.year, ev.day);
+        return site_fail(err, SIPNET_GPU_ERR_INPUT_FILE,
+                         "site %lld: agronomic event for year %d day %d has no corresponding climate record",
+                         (long long)siteIndex, ev.year, ev.day);
       if (ev.type < SIPNET_EV_FERTILIZATION || ev.type > SIPNET_EV_PLANTDEATH)  // events.c:735-737
-        return fail(SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown event type %d", (long long)siteIndex, ev.type);
+        return site_fail(err, SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown event type %d", (long long)siteIndex, ev.type);
       if (ev.type == SIPNET_EV_IRRIGATION && ev.method != 0 && ev.method != 1)  // events.c:498-501
-        return fail(SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown irrigation method type: %d",
-                    (long long)siteIndex, ev.method);
-      EventDev d;
+        return site_fail(err, SIPNET_GPU_ERR_UNKNOWN_EVENT, "site %lld: unknown irrigation method type: %d",
+                         (long long)siteIndex, ev.method);
+      EventDev &d = evs[(size_t)e];
       for (int k = 0; k < 4; ++k) d.p[k] = ev.p[k];
       d.type = ev.type;
       d.method = ev.method;
       d.pad0 = d.pad1 = 0;
-      evs.push_back(d);
       ++e;
     }
     c.evEnd = (int32_t)e;
   }
+  // events past the last climate record never fire (the reference's pointer walk ends with the climate list);
+  // their slots keep a harmless filler
+  for (; e < nev; ++e) {
+    EventDev &d = evs[(size_t)e];
+    for (int k = 0; k < 4; ++k) d.p[k] = 0.0;
+    d.type = SIPNET_EV_PLANTDEATH;
+    d.method = d.pad0 = d.pad1 = 0;
+  }
+  return 0;
+}
+
+// All sites of a launch -> three device arenas (forcing records, events, observations), prepared by the host cores
+// in parallel and uploaded batch by batch from two pinned staging buffers, so the upload of one batch overlaps
+// the preparation of the next.  Sites are independent; the first failing site IN ORDER decides the error, as a
+// sequential pass would.  (10 000 ten-year sites: 12.9 GB of records; ~4 s on one thread with one allocation per
+// site before, a few hundred ms now.)
+static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, double &minLenOut) {
+  const int64_t S = cfg->nsites;
+  const bool eventsOn = cfg->flags.events != 0;
+  const bool wantObs = (cfg->outputs & SIPNET_GPU_OUT_LOGLIK) != 0;
+  std::vector<int64_t> recOff((size_t)S + 1, 0), evOff((size_t)S + 1, 0), obsOff((size_t)S + 1, 0);
+  for (int64_t s = 0; s < S; ++s) {
+    const sipnet_gpu_site &st = cfg->sites[s];
+    if (st.nsteps <= 0) return fail(SIPNET_GPU_ERR_INPUT_FILE, "site %lld: no climate data", (long long)s);
+    recOff[(size_t)s + 1] = recOff[(size_t)s] + st.nsteps;
+    evOff[(size_t)s + 1] = evOff[(size_t)s] + site_event_count(st, eventsOn);
+    obsOff[(size_t)s + 1] = obsOff[(size_t)s] + ((wantObs && st.nee_obs) ? st.nsteps : 0);
+  }
+  ClimRec *dRec = nullptr;
+  EventDev *dEv = nullptr;
+  double *dObs = nullptr;
+  CUDA_OK(dalloc(&dRec, (size_t)recOff[(size_t)S]));
+  h->siteAllocs.push_back(dRec);
+  CUDA_OK(dalloc(&dEv, (size_t)evOff[(size_t)S]));
+  h->siteAllocs.push_back(dEv);
+  CUDA_OK(dalloc(&dObs, (size_t)obsOff[(size_t)S]));
+  h->siteAllocs.push_back(dObs);
+
+  // batches of whole sites, about kBatchBytes of records each
+  const size_t kBatchBytes = (size_t)256 << 20;
+  std::vector<int64_t> batchBegin{0};
+  {
+    size_t acc = 0;
+    for (int64_t s = 0; s < S; ++s) {
+      const size_t b = (size_t)cfg->sites[s].nsteps * sizeof(ClimRec) +
+                       (size_t)(evOff[(size_t)s + 1] - evOff[(size_t)s]) * sizeof(EventDev);
+      if (acc > 0 && acc + b > kBatchBytes) {
+        batchBegin.push_back(s);
+        acc = 0;
+      }
+      acc += b;
+    }
+    batchBegin.push_back(S);
+  }
+  size_t stageBytes = 0;
+  for (size_t b = 0; b + 1 < batchBegin.size(); ++b) {
+    const int64_t s0 = batchBegin[b], s1 = batchBegin[b + 1];
+    stageBytes = std::max(stageBytes, (size_t)(recOff[(size_t)s1] - recOff[(size_t)s0]) * sizeof(ClimRec) +
+                                          (size_t)(evOff[(size_t)s1] - evOff[(size_t)s0]) * sizeof(EventDev));
+  }
+  unsigned char *stage[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  const int nbuf = batchBegin.size() > 2 ? 2 : 1;
+  int rc = 0;
+  std::vector<int> siteRc((size_t)S, 0);
+  std::vector<std::string> siteErr((size_t)S);
+  std::vector<double> siteMin((size_t)S, 1e300);
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char *e = getenv("SIPNET_GPU_INIT_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+  nthreads = std::max(1u, std::min(nthreads, 64u));
+  for (int i = 0; i < nbuf && rc == 0; ++i) {
+    if (cudaHostAlloc((void **)&stage[i], std::max<size_t>(stageBytes, 16), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) != cudaSuccess)
+      rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "pinned staging allocation of %zu bytes failed", stageBytes);
+  }
+  for (size_t b = 0; rc == 0 && b + 1 < batchBegin.size(); ++b) {
+    const int64_t s0 = batchBegin[b], s1 = batchBegin[b + 1];
+    const int buf = (int)(b % (size_t)nbuf);
+    if (b >= (size_t)nbuf && cudaEventSynchronize(copied[buf]) != cudaSuccess) {  // this buffer's previous upload is done
+      rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "site upload failed");
+      break;
+    }
+    ClimRec *recs = reinterpret_cast<ClimRec *>(stage[buf]);
+    const size_t nrec = (size_t)(recOff[(size_t)s1] - recOff[(size_t)s0]);
+    EventDev *evs = reinterpret_cast<EventDev *>(stage[buf] + nrec * sizeof(ClimRec));
+    const size_t nev = (size_t)(evOff[(size_t)s1] - evOff[(size_t)s0]);
+    std::atomic<int64_t> next{s0};
+    auto work = [&]() {
+      for (;;) {
+        const int64_t s = next.fetch_add(1);
+        if (s >= s1) break;
+        siteRc[(size_t)s] = build_site(cfg->sites[s], eventsOn, recs + (recOff[(size_t)s] - recOff[(size_t)s0]),
+                                       evs + (evOff[(size_t)s] - evOff[(size_t)s0]), siteMin[(size_t)s], s, siteErr[(size_t)s]);
+      }
+    };
+    const unsigned nt = (unsigned)std::min<int64_t>(nthreads, s1 - s0);
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < nt; ++i) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+    for (int64_t s = s0; s < s1 && rc == 0; ++s)
+      if (siteRc[(size_t)s]) rc = fail(siteRc[(size_t)s], "%s", siteErr[(size_t)s].c_str());
+    if (rc) break;
+    cudaError_t e = cudaMemcpyAsync(dRec + recOff[(size_t)s0], recs, nrec * sizeof(ClimRec), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nev > 0)
+      e = cudaMemcpyAsync(dEv + evOff[(size_t)s0], evs, nev * sizeof(EventDev), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(copied[buf], h->stream);
+    if (e != cudaSuccess) rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "site upload failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "site upload failed");
+  for (int i = 0; i < 2; ++i) {
+    if (copied[i]) cudaEventDestroy(copied[i]);
+    if (stage[i]) cudaFreeHost(stage[i]);
+  }
+  if (rc) return rc;
+  // observations go up straight from the caller's arrays
+  int64_t firstLen = cfg->sites[0].nsteps;
+  minLenOut = 1e300;
+  for (int64_t s = 0; s < S; ++s) {
+    const sipnet_gpu_site &st = cfg->sites[s];
+    SiteDev &sd = h->hostSites[(size_t)s];
+    sd.nsteps = st.nsteps;
+    sd.member0 = 0;
+    sd.memberCount = 0;
+    sd.clim = dRec + recOff[(size_t)s];
+    sd.events = dEv + evOff[(size_t)s];
+    sd.neeObs = nullptr;
+    if (wantObs && st.nee_obs) {
+      CUDA_OK(cudaMemcpyAsync(dObs + obsOff[(size_t)s], st.nee_obs, (size_t)st.nsteps * sizeof(double), cudaMemcpyHostToDevice,
+                              h->stream));
+      sd.neeObs = dObs + obsOff[(size_t)s];
+      h->anyObs = true;
+    }
+    h->maxSteps = std::max(h->maxSteps, sd.nsteps);
+    if (sd.nsteps != firstLen) h->sitesDiffer = true;
+    minLenOut = std::min(minLenOut, siteMin[(size_t)s]);
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -213,7 +325,7 @@ static void free_handle(sipnet_gpu_handle *h) {
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
                   h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant,
                   h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
-                  h->recCountBk, h->sched};
+                  h->recCountBk, h->sched, h->uniformRows};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : h->siteAllocs)
@@ -229,11 +341,6 @@ static void free_handle(sipnet_gpu_handle *h) {
   if (h->copyStream) cudaStreamDestroy(h->copyStream);
   if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
-}
-
-template <class T>
-static cudaError_t dalloc(T **p, size_t count) {
-  return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
 }
 
 static int run_init_state(sipnet_gpu_handle *h) {
@@ -336,40 +443,11 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   // ---- sites ----
   h->hostSites.resize((size_t)cfg->nsites);
   double minLen = 1e300;
-  std::vector<ClimRec> recs;
-  std::vector<EventDev> evs;
-  int64_t firstLen = cfg->sites[0].nsteps;
-  for (int64_t s = 0; s < cfg->nsites; ++s) {
-    int rc = build_site(cfg->sites[s], cfg->flags.events != 0, recs, evs, minLen, s);
+  {
+    const int rc = upload_sites(h, cfg, minLen);
     if (rc) {
       free_handle(h);
       return rc;
-    }
-    SiteDev &sd = h->hostSites[(size_t)s];
-    sd.nsteps = cfg->sites[s].nsteps;
-    sd.member0 = 0;
-    sd.memberCount = 0;
-    h->maxSteps = std::max(h->maxSteps, sd.nsteps);
-    if (sd.nsteps != firstLen) h->sitesDiffer = true;
-    ClimRec *dClim = nullptr;
-    INIT_CUDA(dalloc(&dClim, recs.size()));
-    h->siteAllocs.push_back(dClim);
-    INIT_CUDA(cudaMemcpyAsync(dClim, recs.data(), recs.size() * sizeof(ClimRec), cudaMemcpyHostToDevice, h->stream));
-    INIT_CUDA(cudaStreamSynchronize(h->stream));  // recs is reused for the next site
-    sd.clim = dClim;
-    EventDev *dEv = nullptr;
-    INIT_CUDA(dalloc(&dEv, evs.size()));
-    h->siteAllocs.push_back(dEv);
-    if (!evs.empty()) INIT_CUDA(cudaMemcpy(dEv, evs.data(), evs.size() * sizeof(EventDev), cudaMemcpyHostToDevice));
-    sd.events = dEv;
-    sd.neeObs = nullptr;
-    if ((cfg->outputs & SIPNET_GPU_OUT_LOGLIK) && cfg->sites[s].nee_obs) {
-      double *dObs = nullptr;
-      INIT_CUDA(dalloc(&dObs, (size_t)sd.nsteps));
-      h->siteAllocs.push_back(dObs);
-      INIT_CUDA(cudaMemcpy(dObs, cfg->sites[s].nee_obs, (size_t)sd.nsteps * sizeof(double), cudaMemcpyHostToDevice));
-      sd.neeObs = dObs;
-      h->anyObs = true;
     }
   }
   // ring capacity: occupancy <= 1 partially evicted entry + floor(5/minLen) whole entries (+ slack), capped like
@@ -515,6 +593,35 @@ static int derive_params(sipnet_gpu_handle *h) {
   cudaError_t e = k1::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "derive launch failed: %s", cudaGetErrorString(e));
+  // layout of the packed tile: rows that vary between members first (one value per thread), then one 8-byte slot
+  // per row that is the same for every member
+  h->packedTileBytes = 0;
+  if (h->blockThreads == 128) {
+    if (!h->uniformRows) CUDA_OK(dalloc(&h->uniformRows, (size_t)kNParamDev));
+    e = k1::launch_uniform_rows(h->params, h->ld, h->nmembers, h->uniformRows, h->stream);
+    h->launches++;
+    if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "uniform-row launch failed: %s", cudaGetErrorString(e));
+    int32_t uni[kNParamDev];
+    CUDA_OK(cudaMemcpyAsync(uni, h->uniformRows, sizeof uni, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    int nVar = 0, nUni = 0;
+    for (int k = 0; k < kNParamDev; ++k)
+      if (tile_slot(k) >= 0 && !uni[k]) ++nVar;
+    h->nVaryingRows = nVar;
+    int v = 0;
+    for (int k = 0; k < kNParamDev; ++k) {
+      h->rowOM[k].x = 0;
+      h->rowOM[k].y = 0;
+      if (tile_slot(k) < 0) continue;
+      if (!uni[k]) {
+        h->rowOM[k].x = (uint32_t)(v++) * 128u * 8u;
+      } else {  // the mask removes the thread's own offset again
+        h->rowOM[k].x = (uint32_t)nVar * 128u * 8u + (uint32_t)(nUni++) * 8u;
+        h->rowOM[k].y = 0xffffffffu;
+      }
+    }
+    h->packedTileBytes = nVar * 128 * 8 + (nUni * 8 + 15) / 16 * 16;
+  }
   return 0;
 }
 
@@ -668,6 +775,8 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
     a.loglikNBackup = h->loglikNBk;
     a.recCountBackup = h->recCountBk;
   }
+  memcpy(a.rowOM, h->rowOM, sizeof a.rowOM);
+  a.packedTileBytes = h->packedTileBytes;
   if (!h->staticSched) {
     CUDA_OK(cudaMemsetAsync(h->sched, 0, 16 + (size_t)h->nblocks * sizeof(unsigned int), h->stream));
     a.workCounter = reinterpret_cast<unsigned long long *>(h->sched);
@@ -726,11 +835,15 @@ extern "C" int sipnet_gpu_run_to_host(sipnet_gpu_handle *h, int64_t step_begin, 
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(h->evRunDone[b], h->stream));
     CUDA_OK(cudaStreamWaitEvent(h->copyStream, h->evRunDone[b], 0));
-    for (int c = 0; c < SIPNET_GPU_NOUT; ++c) {
-      double *d = dst + ((size_t)c * (size_t)total + (size_t)(t0 - step_begin)) * M;
-      const double *src = bufs[b] + (size_t)c * (size_t)n * (size_t)h->ld;
-      CUDA_OK(cudaMemcpy2DAsync(d, M * sizeof(double), src, (size_t)h->ld * sizeof(double), M * sizeof(double), (size_t)n,
-                                cudaMemcpyDeviceToHost, h->copyStream));
+    {  // all 32 columns of the segment in ONE 3-D copy: device [col][n][ld] -> host [col][total][M] at step t0
+      cudaMemcpy3DParms p3;
+      memset(&p3, 0, sizeof p3);
+      p3.srcPtr = make_cudaPitchedPtr(bufs[b], (size_t)h->ld * sizeof(double), M * sizeof(double), (size_t)n);
+      p3.dstPtr = make_cudaPitchedPtr(dst, M * sizeof(double), M * sizeof(double), (size_t)total);
+      p3.dstPos = make_cudaPos(0, (size_t)(t0 - step_begin), 0);
+      p3.extent = make_cudaExtent(M * sizeof(double), (size_t)n, SIPNET_GPU_NOUT);
+      p3.kind = cudaMemcpyDeviceToHost;
+      CUDA_OK(cudaMemcpy3DAsync(&p3, h->copyStream));
     }
     CUDA_OK(cudaEventRecord(h->evCopyDone[b], h->copyStream));
   }
@@ -743,7 +856,7 @@ extern "C" int sipnet_gpu_run_to_host(sipnet_gpu_handle *h, int64_t step_begin, 
   return SIPNET_GPU_OK;
 }
 
-static int ensure_summaries(sipnet_gpu_handle *h) {
+int sip::ensure_summaries(sipnet_gpu_handle *h) {
   if (h->summariesValid) return 0;
   const int64_t n = h->lastEnd - h->lastBegin;
   if (n <= 0) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no run range to summarise");

@@ -45,18 +45,22 @@ def combine_moments(counts: Sequence[np.ndarray], means: Sequence[np.ndarray], v
     """Chan et al. pairwise combination, applied in rank order.  Inputs are per-rank arrays of the
     same shape (population variance); returns (count, mean, variance)."""
     n = np.array(counts[0], dtype=np.float64)
-    mu = np.array(means[0], dtype=np.float64)
-    m2 = np.array(variances[0], dtype=np.float64) * n
+    # a rank with no finite member in a row reports (0, NaN, NaN): it must not poison the combination
+    mu = np.where(n > 0, np.array(means[0], dtype=np.float64), 0.0)
+    m2 = np.where(n > 0, np.array(variances[0], dtype=np.float64) * n, 0.0)
     for nb, mub, varb in zip(counts[1:], means[1:], variances[1:]):
         nb = np.asarray(nb, dtype=np.float64)
+        has = nb > 0
+        mub = np.where(has, np.asarray(mub, dtype=np.float64), mu)
+        varb = np.where(has, np.asarray(varb, dtype=np.float64), 0.0)
         tot = n + nb
-        delta = np.asarray(mub, dtype=np.float64) - mu
+        delta = mub - mu
         safe = np.where(tot > 0, tot, 1.0)
         mu = mu + delta * nb / safe
-        m2 = m2 + np.asarray(varb, dtype=np.float64) * nb + delta * delta * n * nb / safe
+        m2 = m2 + varb * nb + delta * delta * n * nb / safe
         n = tot
     with np.errstate(invalid="ignore", divide="ignore"):
-        return n, mu, np.where(n > 0, m2 / np.where(n > 0, n, 1.0), np.nan)
+        return n, np.where(n > 0, mu, np.nan), np.where(n > 0, m2 / np.where(n > 0, n, 1.0), np.nan)
 
 
 def all_gather_members(local: "torch.Tensor", local_counts: List[int], group=None) -> "torch.Tensor":

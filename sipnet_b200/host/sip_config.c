@@ -136,6 +136,8 @@ static void usage(const char *prog) {
          "      --site-list <file>       several sites in one launch (extension).  One site per line:\n"
          "                               <file-prefix> [<events-prefix> [<member-list>]]; defaults: events next to the\n"
          "                               site's files, one member from <file-prefix>.param; all sites share this run's flags\n"
+         "      --devices <n>            GPUs to use for --ensemble-params / --site-list launches (0 = all visible,\n"
+         "                               the default): whole sites per GPU, or an even share of one site's members\n"
          "      --validation-math        run the general (reference-shaped) kernel instead of the optimistic one\n"
          "  model flags (prefix with no- to turn off): --events --gdd --growth-resp --leaf-water --litter-pool --snow\n"
          "      --soil-phenol --water-hresp --nitrogen-cycle --anaerobic --flooding --carbon-saturation\n"
@@ -144,7 +146,7 @@ static void usage(const char *prog) {
 }
 
 int sip_parse_cli(sip_context *c, int argc, char **argv) {
-  enum { OPT_RESTART_IN = 1001, OPT_RESTART_OUT, OPT_DEBUG_LOG, OPT_ENSEMBLE, OPT_VALIDATION, OPT_SITE_LIST };
+  enum { OPT_RESTART_IN = 1001, OPT_RESTART_OUT, OPT_DEBUG_LOG, OPT_ENSEMBLE, OPT_VALIDATION, OPT_SITE_LIST, OPT_DEVICES };
   struct option opts[2 * kNumFlagSettings + 16];
   char names[kNumFlagSettings][40];
   int flagValue = 0, n = 0;
@@ -162,6 +164,7 @@ int sip_parse_cli(sip_context *c, int argc, char **argv) {
   opts[n++] = (struct option){"debug-log", required_argument, 0, OPT_DEBUG_LOG};
   opts[n++] = (struct option){"ensemble-params", required_argument, 0, OPT_ENSEMBLE};
   opts[n++] = (struct option){"site-list", required_argument, 0, OPT_SITE_LIST};
+  opts[n++] = (struct option){"devices", required_argument, 0, OPT_DEVICES};
   opts[n++] = (struct option){"validation-math", no_argument, 0, OPT_VALIDATION};
   opts[n++] = (struct option){"help", no_argument, 0, 'h'};
   opts[n++] = (struct option){"version", no_argument, 0, 'v'};
@@ -202,6 +205,13 @@ int sip_parse_cli(sip_context *c, int argc, char **argv) {
       case OPT_SITE_LIST:
         strncpy(c->siteList, optarg, SIP_NAME_MAX - 1);
         break;
+      case OPT_DEVICES: {
+        char *end = NULL;
+        const long v = strtol(optarg, &end, 10);
+        if (end == optarg || *end != '\0' || v < 0 || v > 64)
+          return sip_fail(SIPNET_GPU_ERR_BAD_CLI, "--devices takes a count between 0 (all) and 64, got '%s'", optarg);
+        c->devices = (int32_t)v;
+      } break;
       case OPT_VALIDATION:
         c->validationMath = 1;
         break;

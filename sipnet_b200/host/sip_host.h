@@ -51,6 +51,7 @@ typedef struct sip_context {
   int32_t validationMath;               /* --validation-math: run the general kernel */
   int32_t helpOrVersion;                /* 1 = --help printed, 2 = --version printed (caller exits 0) */
   char siteList[SIP_NAME_MAX];          /* --site-list FILE: one site per line, all sites in one launch (see usage) */
+  int32_t devices;                      /* --devices N: GPUs for many-member launches (0 = all visible) */
 } sip_context;
 
 const char *sip_host_error(void);

@@ -12,6 +12,8 @@
  *   --site-list FILE        one site per line: <file-prefix> [<events-prefix> [<member-list>]] -- each site has its
  *                           own .clim / .param (or member list) / events files and gets its own output files; all
  *                           sites run under this invocation's flags
+ *   --devices N             GPUs used by those launches (0 = all visible): one host thread drives them through
+ *                           sipnet_gpu_multi_* -- whole sites per GPU, or an even share of one site's members
  * --debug-log <prefix> writes the reference's three per-step debug logs from the device's validation dump.
  * --restart-in / --restart-out read and write the reference's checkpoint format (sip_restart.c), so a segmented
  * run can alternate between this binary and the reference's.
@@ -140,7 +142,7 @@ int main(int argc, char **argv) {
   }
 
   /* ---- inputs: initModel() + initEvents() per site, sipnet.c:2001-2009, events.c:427-433 ---- */
-  int64_t M = 0, Tmax = 0, maxEvents = 0;
+  int64_t M = 0, Tmax = 0, maxEvents = 0, maxYears = 0;
   for (int64_t s = 0; s < njobs; ++s) {
     if ((rc = read_member_list(&jobs[s]))) return rc;
     jobs[s].member0 = M;
@@ -170,6 +172,10 @@ int main(int argc, char **argv) {
     sip_site_view(&job->data, &views[s]);
     if (job->data.nsteps > Tmax) Tmax = job->data.nsteps;
     if (job->data.nevents > maxEvents) maxEvents = job->data.nevents;
+    if (job->data.nsteps > 0) {
+      const int64_t years = (int64_t)job->data.year[job->data.nsteps - 1] - (int64_t)job->data.year[0] + 1;
+      if (years > maxYears) maxYears = years;
+    }
   }
 
   /* ---- the run: setupModel() + the updateState() loop, on the device ---- */
@@ -189,9 +195,22 @@ int main(int argc, char **argv) {
   /* checkpoints carry the reference's 250-slot mean-NPP ring slot for slot (restart.c:799-806) */
   cfg.ring_slots = useRestart ? SIPNET_GPU_RING_SLOTS_REFERENCE : 0;
   cfg.math = ctx.validationMath ? SIPNET_GPU_MATH_VALIDATION : SIPNET_GPU_MATH_FAST;
-  cfg.max_event_records = ctx.flags.events ? (int32_t)(maxEvents + 4 * (Tmax / 300 + 8)) : 0;
+  /* events.out rows per member: the file's events (a harvest also logs nothing extra; leaf-on/off rows are computed)
+   * plus the computed rows -- leaf on, leaf off, plant death / re-emergence -- budgeted per YEAR of the record,
+   * whatever the step length */
+  cfg.max_event_records = ctx.flags.events ? (int32_t)(2 * maxEvents + 6 * (maxYears + 1) + 16) : 0;
+  /* many members: every visible GPU (or --devices N) through the multi-GPU entry points; the single-member
+   * features (restart, debug log) stay on one handle */
   sipnet_gpu_handle *h = NULL;
-  if ((rc = sipnet_gpu_init(&cfg, &h))) return die(rc, sipnet_gpu_last_error());
+  sipnet_gpu_multi *mh = NULL;
+  if (many) {
+    if ((rc = sipnet_gpu_multi_init(&cfg, ctx.devices, NULL, &mh))) return die(rc, sipnet_gpu_last_error());
+    if (!ctx.quiet) printf("[INFO   ] %lld member(s) of %lld site(s) on %d GPU(s)\n", (long long)M, (long long)njobs,
+                           (int)sipnet_gpu_multi_ndevices(mh));
+  } else if ((rc = sipnet_gpu_init(&cfg, &h))) {
+    return die(rc, sipnet_gpu_last_error());
+  }
+#define SIP_GATHER(what, dst, bytes) (mh ? sipnet_gpu_multi_gather(mh, what, dst, bytes) : sipnet_gpu_gather(h, what, dst, bytes))
   const int64_t T = Tmax;
   const sip_site_data *site0 = &jobs[0].data; /* the single-member features below have exactly one site */
   long long processedBefore = 0; /* meta_info.processed_steps keeps counting across segments (restart.c:160, 905) */
@@ -207,10 +226,10 @@ int main(int argc, char **argv) {
     if ((rc = sipnet_gpu_set_state(h, state, 1, ringV, ringW, 1, 0))) return die(rc, sipnet_gpu_last_error());
     free(rs);
   }
-  if ((rc = sipnet_gpu_run(h, 0, T))) return die(rc, sipnet_gpu_last_error());
+  if ((rc = mh ? sipnet_gpu_multi_run(mh, 0, T) : sipnet_gpu_run(h, 0, T))) return die(rc, sipnet_gpu_last_error());
 
   uint32_t *status = (uint32_t *)malloc((size_t)M * sizeof *status);
-  if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_STATUS, status, (size_t)M * sizeof *status)))
+  if ((rc = SIP_GATHER(SIPNET_GPU_GATHER_STATUS, status, (size_t)M * sizeof *status)))
     return die(rc, sipnet_gpu_last_error());
   for (int64_t m = 0; m < M; ++m) {
     if (status[m] & SIPNET_GPU_ST_BAD_ALLOCATION) /* ensureAllocation(), sipnet.c:1117-1122 */
@@ -225,7 +244,7 @@ int main(int argc, char **argv) {
     const size_t n = (size_t)SIPNET_GPU_NOUT * (size_t)T * (size_t)M;
     double *buf = (double *)malloc(n * sizeof(double));
     if (!buf) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
-    if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_FULL, buf, n * sizeof(double)))) return die(rc, sipnet_gpu_last_error());
+    if ((rc = SIP_GATHER(SIPNET_GPU_GATHER_FULL, buf, n * sizeof(double)))) return die(rc, sipnet_gpu_last_error());
     for (int64_t s = 0; s < njobs; ++s) {
       const site_job *job = &jobs[s];
       for (int64_t k = 0; k < job->nmembers; ++k) {
@@ -318,9 +337,9 @@ int main(int argc, char **argv) {
     const size_t nrec = (size_t)M * (size_t)cfg.max_event_records;
     sipnet_gpu_event_record *recs = (sipnet_gpu_event_record *)malloc((nrec ? nrec : 1) * sizeof *recs);
     int32_t *counts = (int32_t *)malloc((size_t)M * sizeof *counts);
-    if ((rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_EVENT_COUNTS, counts, (size_t)M * sizeof *counts)))
+    if ((rc = SIP_GATHER(SIPNET_GPU_GATHER_EVENT_COUNTS, counts, (size_t)M * sizeof *counts)))
       return die(rc, sipnet_gpu_last_error());
-    if (nrec && (rc = sipnet_gpu_gather(h, SIPNET_GPU_GATHER_EVENT_RECORDS, recs, nrec * sizeof *recs)))
+    if (nrec && (rc = SIP_GATHER(SIPNET_GPU_GATHER_EVENT_RECORDS, recs, nrec * sizeof *recs)))
       return die(rc, sipnet_gpu_last_error());
     for (int64_t s = 0; s < njobs; ++s) {
       const site_job *job = &jobs[s];
@@ -346,7 +365,8 @@ int main(int argc, char **argv) {
     free(recs);
     free(counts);
   }
-  sipnet_gpu_destroy(h);
+  if (mh) sipnet_gpu_multi_destroy(mh);
+  else sipnet_gpu_destroy(h);
   for (int64_t s = 0; s < njobs; ++s) {
     sip_site_free(&jobs[s].data);
     for (int64_t k = 0; k < jobs[s].nmembers; ++k) free(jobs[s].paramFiles[k]);

@@ -39,6 +39,20 @@ def test_combine_moments_matches_numpy():
     np.testing.assert_allclose(v, x.var(axis=2), rtol=1e-12)
 
 
+def test_combine_moments_skips_empty_ranks():
+    """A rank whose share of a row has no finite member reports (n=0, mean=NaN, var=NaN): it is a no-op in any
+    position (first, middle, last); a row that is empty on every rank stays NaN."""
+    full = (3.0, 2.0, 1.0)
+    empty = (0.0, np.nan, np.nan)
+    for order in ([empty, full], [full, empty], [empty, full, empty], [full, empty, full]):
+        n, mu, var = D.combine_moments([np.array([o[0]]) for o in order], [np.array([o[1]]) for o in order],
+                                       [np.array([o[2]]) for o in order])
+        k = sum(1 for o in order if o[0] > 0)
+        assert n[0] == 3.0 * k and mu[0] == 2.0 and abs(var[0] - 1.0) < 1e-15, order
+    n, mu, var = D.combine_moments([np.array([0.0])] * 2, [np.array([np.nan])] * 2, [np.array([np.nan])] * 2)
+    assert n[0] == 0 and np.isnan(mu[0]) and np.isnan(var[0])
+
+
 def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

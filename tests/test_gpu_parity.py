@@ -235,10 +235,14 @@ def test_fast_kernel_replays_members_outside_its_guards(oracle):
     re-run by the general kernel and still match the oracle bit for bit; others are untouched."""
     site = synth.synth_site(4, 2, "half-daily", with_events=True)
     P = synth.synth_params(48, stream=4)
-    weird = [3, 17, 40]
+    weird = [3, 17, 40, 29]
     for m in weird:
         P[A.P["laiInit"], m] = 2000.0
         P[A.P["leafTurnoverRate"], m] = 0.01
+    # member 29 keeps its canopy for the whole run: it leaves the guards in EVERY segment of the segmented run below
+    # (a member flagged in one segment must be replayed again in the next ones)
+    P[A.P["leafTurnoverRate"], 29] = 0.0
+    P[A.P["fracLeafFall"], 29] = 0.0
     res = run_gpu([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL, math=A.MATH_FAST)
     flagged = np.flatnonzero(res["status"] & A.ST_REPLAY)
     assert set(weird) <= set(flagged.tolist())
@@ -252,7 +256,9 @@ def test_fast_kernel_replays_members_outside_its_guards(oracle):
         ens.run(t0, min(site.nsteps, t0 + 400))
         outs.append(ens.output())
     ens.close()
-    assert np.array_equal(np.concatenate(outs, axis=1), res["out"], equal_nan=True)
+    seg = np.concatenate(outs, axis=1)
+    assert np.array_equal(seg[:, :, 29], res["out"][:, :, 29], equal_nan=True), "member outside the guards in every segment"
+    assert np.array_equal(seg, res["out"], equal_nan=True)
 
 
 def test_zz_validation_build_is_bit_identical():
