@@ -194,6 +194,10 @@ enum sipnet_gpu_out_col {
 #define SIPNET_GPU_NDEBUG_FLUX 56
 #define SIPNET_GPU_NDEBUG_TRACK 33
 #define SIPNET_GPU_NDEBUG (13 + 56 + 33 + 3 + 1)
+/* With the debug dump the kernel also evaluates the reference's mass-balance tracker (updateBalanceTracker*() and
+ * checkBalance(), balance.c:35-148, called from updatePoolsAndBalance(), sipnet.c:1769-1806): two check values per
+ * step, balanceTracker.deltaC and deltaN (zeroed below EPS = 1e-8 like the reference's). */
+#define SIPNET_GPU_NBALANCE 2
 
 /* ---- computed/applied event records (for the host-side events.out writer) --
  * One record per events.out row (events.c:379-402): the (up to 10) deltas the
@@ -270,7 +274,9 @@ enum sipnet_gpu_gather_what {
   SIPNET_GPU_GATHER_EVENT_RECORDS = 10, /* sipnet_gpu_event_record [M][max_event_records] */
   SIPNET_GPU_GATHER_LOGLIK_N = 11, /* double [M]: number of observations that entered the likelihood */
   SIPNET_GPU_GATHER_RING_VALUES = 12,  /* double [ring_slots][M]: MeanTracker.values, slot-major (runmean.h) */
-  SIPNET_GPU_GATHER_RING_WEIGHTS = 13  /* double [ring_slots][M]: MeanTracker.weights */
+  SIPNET_GPU_GATHER_RING_WEIGHTS = 13, /* double [ring_slots][M]: MeanTracker.weights */
+  SIPNET_GPU_GATHER_BALANCE = 14       /* double [SIPNET_GPU_NBALANCE][n][M]: deltaC, deltaN of the mass-balance check
+                                          (needs SIPNET_GPU_OUT_DEBUG) */
 };
 
 /* per-member status bits (instead of the reference's exit()) */
@@ -280,6 +286,8 @@ enum sipnet_gpu_gather_what {
 #define SIPNET_GPU_ST_DIED 0x8u           /* plant mortality happened at least once (sipnet.c:1702) */
 #define SIPNET_GPU_ST_EVREC_OVERFLOW 0x10u /* more event records than max_event_records */
 #define SIPNET_GPU_ST_NONFINITE 0x20u     /* a pool became NaN/Inf */
+#define SIPNET_GPU_ST_BALANCE 0x80u       /* the mass-balance check found a non-zero deltaC or deltaN on some step (the
+                                             reference's warning, balance.c:150-169; debug dump only) */
 #define SIPNET_GPU_ST_REPLAY 0x40u        /* the optimistic kernel met an input outside its guards and the member
                                              was re-run by the general kernel (informational; results are exact) */
 

@@ -88,6 +88,17 @@ class RefShim(_Runner):
             _dp(out), _dp(dbg) if dbg is not None else None, C.byref(done))
         return rc, int(done.value), out, dbg
 
+    def run_balance(self, flags: dict, params80: np.ndarray, site: SiteData):
+        """-> (rc, steps_done, balance[T][2]): balanceTracker.deltaC / deltaN after every updateState()
+        (checkBalance(), balance.c:129-148) of the unmodified reference."""
+        bal = np.full((site.nsteps, 2), np.nan)
+        self.lib.sipref_set_balance_out(_dp(bal), C.c_int64(site.nsteps))
+        try:
+            rc, done, _, _ = self.run(flags, params80, site, want_debug=False)
+        finally:
+            self.lib.sipref_set_balance_out(None, C.c_int64(0))
+        return rc, done, bal
+
     def read_clim(self, path: str, gdd: int = 1, cap: int = 1 << 20) -> SiteData:
         n = sum(1 for _ in open(path))
         cap = max(n + 8, 16)
@@ -140,3 +151,17 @@ class Oracle(_Runner):
             _ip(fl), _dp(p), *sargs, _dp(out), _dp(dbg) if dbg is not None else None,
             C.byref(done), recs, C.c_int32(max_event_records), C.byref(nrec))
         return rc, int(done.value), out, dbg, list(recs[:min(nrec.value, max_event_records)])
+
+    def run_balance(self, flags: dict, params80: np.ndarray, site: SiteData):
+        """-> (rc, steps_done, balance[T][2]): the mass-balance tracker's deltaC / deltaN per step."""
+        T = site.nsteps
+        fl = flags_array(flags)
+        p = np.ascontiguousarray(params80, dtype=np.float64)
+        bal = np.full((T, 2), np.nan)
+        done = C.c_int64(0)
+        clim = (C.POINTER(C.c_double) * 11)(*[_dp(site.clim[k]) for k in A.CLIM_COLS])
+        arr, n = site.event_array()
+        self.lib.sipnet_oracle_run_balance.restype = C.c_int
+        rc = self.lib.sipnet_oracle_run_balance(_ip(fl), _dp(p), C.c_int64(T), _ip(site.year), _ip(site.day), clim,
+                                                C.c_int64(n), C.cast(arr, C.POINTER(A.Event)), _dp(bal), C.byref(done))
+        return rc, int(done.value), bal

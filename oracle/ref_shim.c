@@ -215,6 +215,14 @@ static void ensure_context(void) {
   }
 }
 
+/* Where the next sipref_run() stores balanceTracker.deltaC / deltaN per step ([cap][2]); NULL = nowhere. */
+static double *sipref_balance_out = NULL;
+static int64_t sipref_balance_cap = 0;
+void sipref_set_balance_out(double *buf, int64_t cap) {
+  sipref_balance_out = buf;
+  sipref_balance_cap = cap;
+}
+
 /*
  * Run one member through the reference.  Arrays are per step, already in the
  * units readClimData() leaves them in.  out32 is [T][32], dbg is [T][106]
@@ -316,6 +324,10 @@ int sipref_run(const int32_t *flags, const double *params_in, int64_t T,
       }
       if (out32) dump_out(out32 + done * SIPNET_GPU_NOUT);
       if (dbg) dump_debug(dbg + done * SIPNET_GPU_NDEBUG);
+      if (sipref_balance_out && done < sipref_balance_cap) { /* checkBalance()'s results, balance.c:129-148 */
+        sipref_balance_out[2 * done] = balanceTracker.deltaC;
+        sipref_balance_out[2 * done + 1] = balanceTracker.deltaN;
+      }
       ++done;
       climate = climate->nextClim;
     }

@@ -21,7 +21,7 @@
 #include <string.h>
 
 #define OR_TINY 0.000001 /* common/util.h:14 */
-#define OR_EPS 1e-8      /* balance.h:6 (only used for the clamp warning) */
+#define OR_EPS 1e-8      /* balance.h:6 */
 #define OR_RING 250      /* MEAN_NPP_MAX_ENTRIES, sipnet.c:39-40 */
 #define OR_MEAN_DAYS 5.0 /* MEAN_NPP_DAYS, sipnet.c:39 */
 
@@ -90,6 +90,7 @@ typedef struct {
   sipnet_gpu_event_record *recs;
   int32_t max_recs, nrec;
   int64_t step;
+  double balDeltaC, balDeltaN; /* balanceTracker.deltaC / deltaN of the last step, balance.h:46-47 */
   int exit_code;
 } OrSim;
 
@@ -805,12 +806,29 @@ static void clamp_stock(double *v, double floor_) { /* ensureNonNegative, sipnet
   }
 }
 
-/* ---- updatePoolsAndBalance: sipnet.c:1769-1806 (balance tracker has no
- * feedback on state, balance.c; omitted) --------------------------------------- */
+/* getMassTotals, balance.c:13-33 */
+static void mass_totals(const OrSim *s, double *carbon, double *nitrogen) {
+  const OrPools *e = &s->e;
+  *carbon = (e->plantWoodC + e->plantCAccountingDelta) + e->plantLeafC + e->fineRootC + e->coarseRootC + e->soilC;
+  if (s->f.litterPool) {
+    *carbon += e->litterC;
+  }
+  if (s->f.nitrogenCycle) {
+    *nitrogen = e->plantWoodC / P(woodCN) + e->plantLeafC / P(leafCN) + e->fineRootC / P(fineRootCN) +
+                e->coarseRootC / P(woodCN) + e->soilOrgN + e->litterN + e->minN + e->plantStorageN;
+  } else {
+    *nitrogen = 0.0;
+  }
+}
+
+/* ---- updatePoolsAndBalance: sipnet.c:1769-1806.  The balance tracker (balance.c) is diagnostic -- nothing in it
+ * feeds back into state -- and is restated for its two check values, deltaC and deltaN. ------------------------- */
 static void step_pools(OrSim *s) {
   OrPools *e = &s->e;
   const OrRates *r = &s->r;
   const double len = s->c.length;
+  double preC, preN, postC, postN, finalC, finalN;
+  mass_totals(s, &preC, &preN); /* updateBalanceTrackerPreUpdate, balance.c:35-38 */
 
   /* updatePoolsForEvents, events.c:744-790 */
   e->plantWoodC += r->eventWoodC * len;
@@ -881,6 +899,8 @@ static void step_pools(OrSim *s) {
     e->litterN += r->nOrgLitter * len;
   }
 
+  mass_totals(s, &postC, &postN); /* updateBalanceTrackerPostUpdate, balance.c:40-43 */
+
   /* checkForMortality, sipnet.c:1688-1767 */
   if (!s->isAlive) {
     if (enough_biomass(s)) {
@@ -930,6 +950,48 @@ static void step_pools(OrSim *s) {
   clamp_stock(&e->soilOrgN, 0);
   clamp_stock(&e->litterN, 0);
   clamp_stock(&e->plantStorageN, 0);
+
+  /* updateBalanceTrackerPostClamp, balance.c:45-104 */
+  mass_totals(s, &finalC, &finalN);
+  double clampedC = finalC - postC;
+  if (clampedC < OR_EPS) {
+    clampedC = 0;
+  }
+  double clampedN = finalN - postN;
+  if (clampedN < OR_EPS) {
+    clampedN = 0;
+  }
+  double inputsC = r->photosynthesis + r->eventInputC;
+  double outputsC = r->rVeg + r->rFineRoot + r->rCoarseRoot + r->rSoil + r->soilMethane + r->eventOutputC;
+  if (s->f.litterPool) {
+    outputsC += r->rLitter + r->litterMethane;
+  }
+  inputsC *= len;
+  outputsC *= len;
+  double inputsN = 0.0, outputsN = 0.0; /* initBalanceTracker, balance.c:106-127 (never written without nitrogen) */
+  if (s->f.nitrogenCycle) {
+    inputsN = r->nFixation + r->eventInputN;
+    outputsN = r->nLeaching + r->nVolatilization + r->eventOutputN;
+    inputsN *= len;
+    outputsN *= len;
+  }
+  inputsC += clampedC;
+  if (s->f.nitrogenCycle) {
+    inputsN += clampedN;
+  }
+  /* checkBalance, balance.c:129-176 */
+  double poolCDelta = finalC - preC;
+  double systemCDelta = inputsC - outputsC;
+  s->balDeltaC = poolCDelta - systemCDelta;
+  double poolNDelta = finalN - preN;
+  double systemNDelta = outputsN - inputsN;
+  s->balDeltaN = poolNDelta + systemNDelta;
+  if (fabs(s->balDeltaC) < OR_EPS) {
+    s->balDeltaC = 0.0;
+  }
+  if (fabs(s->balDeltaN) < OR_EPS) {
+    s->balDeltaN = 0.0;
+  }
 }
 
 /* ---- updateTrackers: sipnet.c:1420-1496 -------------------------------------- */
@@ -1163,7 +1225,7 @@ static void load_clim(OrSim *s, int64_t t, const int32_t *year, const int32_t *d
 static int run_member(OrSim *s, const int32_t *flags, const double *params, int64_t pstride, int64_t T,
                       const int32_t *year, const int32_t *day, const double *const *cl, int64_t nev,
                       const sipnet_gpu_event *ev, double *out32, double *dbg, int64_t *steps_done,
-                      double *final_out32, sipnet_gpu_event_record *recs, int32_t max_recs) {
+                      double *final_out32, sipnet_gpu_event_record *recs, int32_t max_recs, double *balance) {
   memset(s, 0, sizeof *s);
   s->recs = recs;
   s->max_recs = max_recs;
@@ -1198,6 +1260,10 @@ static int run_member(OrSim *s, const int32_t *flags, const double *params, int6
     }
     if (out32) write_out32(s, out32 + t * SIPNET_GPU_NOUT);
     if (dbg) write_debug(s, dbg + t * SIPNET_GPU_NDEBUG);
+    if (balance) {
+      balance[2 * t] = s->balDeltaC;
+      balance[2 * t + 1] = s->balDeltaN;
+    }
     ++done;
   }
   if (final_out32 && done > 0) write_out32(s, final_out32);
@@ -1214,8 +1280,19 @@ int sipnet_oracle_run(const int32_t *flags, const double *params, int64_t T, con
   const double *cl[11] = {time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd};
   OrSim *s = (OrSim *)malloc(sizeof(OrSim));
   if (!s) return SIPNET_GPU_ERR_INTERNAL;
-  int rc = run_member(s, flags, params, 1, T, year, day, cl, nev, ev, out32, dbg, steps_done, NULL, recs, max_recs);
+  int rc = run_member(s, flags, params, 1, T, year, day, cl, nev, ev, out32, dbg, steps_done, NULL, recs, max_recs, NULL);
   if (nrec) *nrec = s->nrec;
+  free(s);
+  return rc;
+}
+
+/* One member's run with the balance tracker's check values: balance[t] = {deltaC, deltaN} (balance.c:129-148). */
+int sipnet_oracle_run_balance(const int32_t *flags, const double *params, int64_t T, const int32_t *year,
+                              const int32_t *day, const double *const *clim11, int64_t nev, const sipnet_gpu_event *ev,
+                              double *balance, int64_t *steps_done) {
+  OrSim *s = (OrSim *)malloc(sizeof(OrSim));
+  if (!s) return SIPNET_GPU_ERR_INTERNAL;
+  int rc = run_member(s, flags, params, 1, T, year, day, clim11, nev, ev, NULL, NULL, steps_done, NULL, NULL, 0, balance);
   free(s);
   return rc;
 }
@@ -1240,7 +1317,7 @@ static void *ensemble_worker(void *arg) {
   for (int64_t m = j->m0; m < j->m1; ++m) {
     int64_t done = 0;
     int rc = run_member(s, j->flags, j->params + m, j->ld, j->T, j->year, j->day, j->cl, j->nev, j->ev, NULL,
-                        NULL, &done, j->final_out32 + m * SIPNET_GPU_NOUT, NULL, 0);
+                        NULL, &done, j->final_out32 + m * SIPNET_GPU_NOUT, NULL, 0, NULL);
     if (rc && !j->rc) j->rc = rc;
   }
   free(s);

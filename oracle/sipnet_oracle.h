@@ -46,6 +46,14 @@ int sipnet_oracle_run(const int32_t *flags, const double *params, int64_t T,
                       int64_t *steps_done, sipnet_gpu_event_record *recs,
                       int32_t max_recs, int32_t *nrec);
 
+/* One member's run returning the mass-balance tracker's check values per step (balance.c:129-148):
+ * balance[2 t] = deltaC, balance[2 t + 1] = deltaN.  clim11 = the eleven climate arrays in the order above. */
+int sipnet_oracle_run_balance(const int32_t *flags, const double *params, int64_t T,
+                              const int32_t *year, const int32_t *day,
+                              const double *const *clim11, int64_t nev,
+                              const sipnet_gpu_event *ev, double *balance,
+                              int64_t *steps_done);
+
 /*
  * Ensemble form used by the CPU baseline: run `nmembers` parameter vectors
  * (SoA [80][ld]) on one site with `nthreads` POSIX threads; only the 32

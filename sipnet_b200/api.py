@@ -337,6 +337,10 @@ class Ensemble:
     def debug(self) -> np.ndarray:
         return self._gather(A.GATHER_DEBUG, np.float64, (A.NDEBUG, self.nrun, self.nmembers))
 
+    def balance(self) -> np.ndarray:
+        """[2][n][M]: deltaC, deltaN of the reference's mass-balance check (balance.c:129-148); needs OUT_DEBUG."""
+        return self._gather(A.GATHER_BALANCE, np.float64, (A.NBALANCE, self.nrun, self.nmembers))
+
     def loglik(self) -> np.ndarray:
         return self._gather(A.GATHER_LOGLIK, np.float64, (self.nmembers,))
 

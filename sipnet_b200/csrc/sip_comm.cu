@@ -688,6 +688,7 @@ static bool member_output_shape(const sipnet_gpu_multi *m, int what, size_t *col
   switch (what) {
     case SIPNET_GPU_GATHER_FULL: *cols = SIPNET_GPU_NOUT; *perStep = true; return (h0->outputs & SIPNET_GPU_OUT_FULL) != 0;
     case SIPNET_GPU_GATHER_DEBUG: *cols = SIPNET_GPU_NDEBUG; *perStep = true; return h0->dbg != nullptr;
+    case SIPNET_GPU_GATHER_BALANCE: *cols = SIPNET_GPU_NBALANCE; *perStep = true; return h0->dbg != nullptr;
     case SIPNET_GPU_GATHER_LOGLIK:
     case SIPNET_GPU_GATHER_LOGLIK_N: *cols = 1; return h0->loglik != nullptr;
     case SIPNET_GPU_GATHER_STATUS: *cols = 1; *elem = 4; return true;

@@ -328,7 +328,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
           if (a.colSlot[c] >= 0)
             for (int64_t t = o0; t < o1; ++t) a.out[((int64_t)a.colSlot[c] * a.outSteps + t) * a.ld + m] = nanv;
       if (a.dbg != nullptr)
-        for (int k = 0; k < SIPNET_GPU_NDEBUG; ++k)
+        for (int k = 0; k < SIPNET_GPU_NDEBUG + SIPNET_GPU_NBALANCE; ++k)
           for (int64_t t = o0; t < o1; ++t) a.dbg[((int64_t)k * a.outSteps + t) * a.ld + m] = nanv;
     }
   }

@@ -361,6 +361,20 @@ __device__ __forceinline__ double ratio(NM &nm, double num, double den) {
   return nm.div(num, d);
 }
 
+// getMassTotals, balance.c:13-33 (validation dump only)
+template <class FL, class NM, class PT>
+__device__ __forceinline__ void mass_totals(const FL &fl, NM &nm, const PT &prm, const Member &mb, double &carbon,
+                                            double &nitrogen) {
+  carbon = (mb.wood + mb.delta) + mb.leaf + mb.fine + mb.coarse + mb.soil;
+  if (fl.on(F_LITTER_POOL)) carbon += mb.litter;
+  if (fl.on(F_NITROGEN)) {
+    nitrogen = nm.div(mb.wood, SIP_P(woodCN)) + nm.div(mb.leaf, SIP_P(leafCN)) + nm.div(mb.fine, SIP_P(fineRootCN)) +
+               nm.div(mb.coarse, SIP_P(woodCN)) + mb.orgN + mb.litN + mb.minN + mb.storN;
+  } else {
+    nitrogen = 0.0;
+  }
+}
+
 // ---- the step ----------------------------------------------------------------------
 // Emit is a functor: emit.outputs(column) stores the outputState() columns it keeps and, in the
 // DEBUG instantiation, emit.dbg(index, value) for the debug-log fields.
@@ -896,6 +910,9 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   }
 
   // ---------------- updatePoolsAndBalance, sipnet.c:1769-1806 ---------------------------
+  // the mass-balance tracker (balance.c) is diagnostic: only the validation dump evaluates it
+  double balPreC = 0.0, balPreN = 0.0, balPostC = 0.0, balPostN = 0.0;
+  if (DEBUG) mass_totals(fl, nm, prm, mb, balPreC, balPreN);  // updateBalanceTrackerPreUpdate, balance.c:35-38
   // updatePoolsForEvents, events.c:744-790
   mb.wood += r.eventWoodC * len;
   mb.leaf += r.eventLeafC * len;
@@ -962,6 +979,8 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     mb.litN += r.nOrgLitter * len;
   }
 
+  if (DEBUG) mass_totals(fl, nm, prm, mb, balPostC, balPostN);  // updateBalanceTrackerPostUpdate, balance.c:40-43
+
   // checkForMortality, sipnet.c:1688-1767
   if (!alive) {
     if (has_biomass(mb)) alive = true;
@@ -1006,6 +1025,39 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   clamp_stock(mb.orgN, 0, mb.status);
   clamp_stock(mb.litN, 0, mb.status);
   clamp_stock(mb.storN, 0, mb.status);
+
+  double balDeltaC = 0.0, balDeltaN = 0.0;
+  if (DEBUG) {  // updateBalanceTrackerPostClamp + checkBalance, balance.c:45-148
+    double finalC, finalN;
+    mass_totals(fl, nm, prm, mb, finalC, finalN);
+    double clampedC = finalC - balPostC;
+    if (clampedC < kEps) clampedC = 0;
+    double clampedN = finalN - balPostN;
+    if (clampedN < kEps) clampedN = 0;
+    double inputsC = r.photosynthesis + r.eventInputC;
+    double outputsC = r.rVeg + r.rFineRoot + r.rCoarseRoot + r.rSoil + r.soilMethane + r.eventOutputC;
+    if (fl.on(F_LITTER_POOL)) outputsC += r.rLitter + r.litterMethane;
+    inputsC *= len;
+    outputsC *= len;
+    double inputsN = 0.0, outputsN = 0.0;
+    if (fl.on(F_NITROGEN)) {
+      inputsN = r.nFixation + r.eventInputN;
+      outputsN = r.nLeaching + r.nVolatilization + r.eventOutputN;
+      inputsN *= len;
+      outputsN *= len;
+    }
+    inputsC += clampedC;
+    if (fl.on(F_NITROGEN)) inputsN += clampedN;
+    const double poolCDelta = finalC - balPreC;
+    const double systemCDelta = inputsC - outputsC;
+    balDeltaC = poolCDelta - systemCDelta;
+    const double poolNDelta = finalN - balPreN;
+    const double systemNDelta = outputsN - inputsN;
+    balDeltaN = poolNDelta + systemNDelta;
+    if (fabs(balDeltaC) < kEps) balDeltaC = 0.0;
+    if (fabs(balDeltaN) < kEps) balDeltaN = 0.0;
+    if (fabs(balDeltaC) > 0.0 || fabs(balDeltaN) > 0.0) mb.status |= SIPNET_GPU_ST_BALANCE;  // the reference warns
+  }
 
   // ---------------- updateTrackers, sipnet.c:1420-1496 ------------------------------------
   StepTrack t;
@@ -1140,6 +1192,8 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     emit.dbg(k++, (double)mb.didFall);
     emit.dbg(k++, (double)mb.phenLastYear);
     emit.dbg(k++, alive ? 1.0 : 0.0);
+    emit.dbg(k++, balDeltaC);  // rows SIPNET_GPU_NDEBUG ..: SIPNET_GPU_GATHER_BALANCE
+    emit.dbg(k++, balDeltaN);
   }
 
   // ---------------- updateEventTrackers, events.c:811-822 -------------------------------------

@@ -531,7 +531,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
       if (h->colSlot[c] < 0) h->colSlot[c] = (int8_t)h->ncols++;
   }
   if (h->ncols > 0) INIT_CUDA(dalloc(&h->out, (size_t)h->ncols * h->outCap * h->ld));
-  if (cfg->outputs & SIPNET_GPU_OUT_DEBUG) INIT_CUDA(dalloc(&h->dbg, (size_t)SIPNET_GPU_NDEBUG * h->outCap * h->ld));
+  if (cfg->outputs & SIPNET_GPU_OUT_DEBUG) INIT_CUDA(dalloc(&h->dbg, (size_t)(SIPNET_GPU_NDEBUG + SIPNET_GPU_NBALANCE) * h->outCap * h->ld));
   if (cfg->outputs & SIPNET_GPU_OUT_LOGLIK) {
     INIT_CUDA(dalloc(&h->loglik, (size_t)h->ld));
     INIT_CUDA(dalloc(&h->loglikN, (size_t)h->ld));
@@ -751,7 +751,8 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
   if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
     if (outbuf) CUDA_OK(cudaMemsetAsync(outbuf, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
     if (h->dbg)
-      CUDA_OK(cudaMemsetAsync(h->dbg, 0xFF, (size_t)SIPNET_GPU_NDEBUG * a.outSteps * h->ld * sizeof(double), h->stream));
+      CUDA_OK(cudaMemsetAsync(h->dbg, 0xFF, (size_t)(SIPNET_GPU_NDEBUG + SIPNET_GPU_NBALANCE) * a.outSteps * h->ld * sizeof(double),
+                              h->stream));
   }
   const bool debug = h->dbg != nullptr;
   const bool optimistic = (h->math == SIPNET_GPU_MATH_FAST) && !debug;
@@ -886,6 +887,7 @@ extern "C" size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what) 
   switch (what) {
     case SIPNET_GPU_GATHER_FULL: return (h->outputs & SIPNET_GPU_OUT_FULL) ? SIPNET_GPU_NOUT * n * M * 8 : 0;
     case SIPNET_GPU_GATHER_DEBUG: return h->dbg ? (size_t)SIPNET_GPU_NDEBUG * n * M * 8 : 0;
+    case SIPNET_GPU_GATHER_BALANCE: return h->dbg ? (size_t)SIPNET_GPU_NBALANCE * n * M * 8 : 0;
     case SIPNET_GPU_GATHER_LOGLIK:
     case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglik ? M * 8 : 0;
     case SIPNET_GPU_GATHER_STATUS: return M * 4;
@@ -920,6 +922,8 @@ extern "C" int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size
   switch (what) {
     case SIPNET_GPU_GATHER_FULL: return copy_rows(h, dst, h->out, SIPNET_GPU_NOUT * n, 8);
     case SIPNET_GPU_GATHER_DEBUG: return copy_rows(h, dst, h->dbg, (size_t)SIPNET_GPU_NDEBUG * n, 8);
+    case SIPNET_GPU_GATHER_BALANCE:
+      return copy_rows(h, dst, h->dbg + (size_t)SIPNET_GPU_NDEBUG * n * (size_t)h->ld, (size_t)SIPNET_GPU_NBALANCE * n, 8);
     case SIPNET_GPU_GATHER_LOGLIK: return copy_rows(h, dst, h->loglik, 1, 8);
     case SIPNET_GPU_GATHER_LOGLIK_N: return copy_rows(h, dst, h->loglikN, 1, 8);
     case SIPNET_GPU_GATHER_STATUS: return copy_rows(h, dst, h->status, 1, 4);

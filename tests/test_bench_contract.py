@@ -41,15 +41,32 @@ def test_our_arm_refuses_to_run_without_a_gpu():
 
 @pytest.mark.gpu
 def test_our_arm_line():
-    r, line = run_bench("--steps", "2", "--warmup", "3", "--members", "512", "--years", "1", "--no-cpu-baseline")
+    r, line = run_bench("--steps", "2", "--warmup", "3", "--members", "2048", "--years", "1", "--no-cpu-baseline")
     assert r.returncode == 0 and line is not None, r.stderr[-2000:]
     assert BASE_KEYS <= set(line) and "impl" not in line
     assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["scaling"] == "weak"
+    assert line["comm_nranks"] == 1 and "C4" in line["config"]["workload"]
     roof = line["roofline"]
     assert roof["bound"] in ("fp64", "hbm") and roof["unit"] in ("TFLOP/s", "GB/s")
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and 0 < roof["frac"] < 1
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-    assert line["gpu_launches"] >= 2 * line["steps"]              # init_state + step kernel (+ replay) per bench step
+    assert line["gpu_launches"] >= 4 * line["steps"]              # init_state, step kernel, replay, summary kernels per pass
     e2e = line["e2e"]
-    assert e2e["h2d_bytes_per_step"] == 80 * 512 * 8 and e2e["d2h_bytes_per_step"] == 32 * line["config"]["model_steps"] * 512 * 8
+    T = line["config"]["model_steps"]
+    assert e2e["h2d_bytes_per_step"] == 80 * 2048 * 8 and e2e["d2h_bytes_per_step"] == (2 + 2 + 6) * T * 8
     assert 0 < e2e["value"] < line["value"]                       # the copies are inside the timed region
+    assert line["oracle_spot_check"]["bit_identical_to_oracle"] is True
+    assert line["c5"]["comm_nranks"] == 1 and line["c5"]["value"] > 0
+    assert line["c2"]["e2e"]["d2h_bytes_per_step"] == 32 * T * 4096 * 8
+
+
+def test_both_arms_share_one_config_object():
+    """`config` must be the same dict in both arms (the driver compares them)."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(members=131072, years=10)
+    a = bench.bench_config(args, 7306)
+    assert a == bench.bench_config(args, 7306) and set(a) >= {"workload", "members_per_gpu", "model_steps"}
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": bench_config(args, T)') == 2      # our arm and the reference arm
