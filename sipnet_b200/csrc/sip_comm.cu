@@ -98,6 +98,7 @@ struct Local {
   double *q2All = nullptr;
   uint32_t *hist = nullptr;
   gs::GsRow *state = nullptr;
+  gs::GsTie *tieAll = nullptr;
   uint64_t *emitAll = nullptr;
   int32_t *flags = nullptr;
   double *llAll = nullptr;  // [nranks][maxMembers] log-likelihood gather
@@ -119,13 +120,14 @@ namespace {
 
 void free_local(Local &l) {
   if (l.h) cudaSetDevice(l.h->device);
-  void *ptrs[] = {l.statAll, l.q2All, l.hist, l.state, l.emitAll, l.flags, l.llAll};
+  void *ptrs[] = {l.statAll, l.q2All, l.hist, l.state, l.tieAll, l.emitAll, l.flags, l.llAll};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   l.statAll = nullptr;
   l.q2All = nullptr;
   l.hist = nullptr;
   l.state = nullptr;
+  l.tieAll = nullptr;
   l.emitAll = nullptr;
   l.flags = nullptr;
   l.llAll = nullptr;
@@ -187,6 +189,7 @@ int ensure_scratch(sipnet_gpu_comm *c, Local &l, int64_t rows) {
   CUDA_OK(cudaMalloc((void **)&l.q2All, (size_t)R * rows * sizeof(double)));
   CUDA_OK(cudaMalloc((void **)&l.hist, (size_t)rows * gs::kGsHistWords * sizeof(uint32_t)));
   CUDA_OK(cudaMalloc((void **)&l.state, (size_t)rows * sizeof(gs::GsRow)));
+  CUDA_OK(cudaMalloc((void **)&l.tieAll, (size_t)R * rows * gs::kGsMaxStat * sizeof(gs::GsTie)));
   CUDA_OK(cudaMalloc((void **)&l.emitAll, (size_t)R * rows * gs::kGsMaxStat * gs::kGsEmit * sizeof(uint64_t)));
   CUDA_OK(cudaMalloc((void **)&l.flags, 16));
   l.rowsCap = rows;
@@ -231,6 +234,7 @@ int team_summaries(sipnet_gpu_comm *c) {
     a.q2All = l.q2All;
     a.hist = l.hist;
     a.state = l.state;
+    a.tieAll = l.tieAll;
     a.emitAll = l.emitAll;
     a.flags = l.flags;
     a.mean = h->mean;
@@ -279,6 +283,8 @@ int team_summaries(sipnet_gpu_comm *c) {
       if (!flag) break;
       c->lastLevels = std::max(c->lastLevels, level);
       if (int rc = all_reduce_hist(c, (size_t)rows * gs::kGsHistWords)) return rc;
+      if (int rc = all_gather_bytes(c, (size_t)rows * gs::kGsMaxStat * sizeof(gs::GsTie), [](Local &l) -> void * { return l.tieAll; }))
+        return rc;
     }
     if (args[0].nq > 0) {
       for (size_t i = 0; i < c->local.size(); ++i) {

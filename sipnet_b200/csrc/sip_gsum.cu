@@ -11,7 +11,7 @@ namespace gs {
 
 constexpr int kThreads = 512;
 constexpr int kUnroll = 4;
-constexpr uint64_t kSent = ~0ull;  // never the key of a finite value
+constexpr uint64_t kSent = kGsNoKey;
 
 __host__ __device__ constexpr int bits_after(int level) { return level < 7 ? 11 + 8 * level : 64; }
 __host__ __device__ constexpr int shift_of(int level) { return 64 - bits_after(level); }
@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   __shared__ double red[kThreads];
   __shared__ GsRow S;
   __shared__ uint64_t slotTop[kGsMaxStat];
+  __shared__ unsigned long long tieRep[kGsMaxStat];
+  __shared__ unsigned int tieLo[kGsMaxStat], tieHi[kGsMaxStat];
   const int tid = threadIdx.x;
   const RowRef r = row_ref(a);
   const int64_t rows = gridDim.x;
@@ -260,6 +262,25 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   }
   __syncthreads();
   if (S.done == 0) {
+    if (level >= 2 && tid < 2 * a.nq && S.rbits[tid] == 0) {
+      // the previous pass looked at the keys of this statistic's slot on every rank: all equal => that key is it
+      const int slot = S.slotOf[tid];
+      bool any = false, same = true;
+      uint64_t rep = 0;
+      for (int q = 0; q < a.nranks; ++q) {
+        const GsTie t = a.tieAll[((int64_t)q * rows + r.row) * kGsMaxStat + slot];
+        if (t.rep == kGsNoKey) continue;
+        if (!any) {
+          rep = t.rep;
+          any = true;
+        }
+        if (t.diff != 0 || t.rep != rep) same = false;
+      }
+      if (any && same) {
+        S.prefix[tid] = rep;
+        S.rbits[tid] = 64;
+      }
+    }
     const unsigned int *g = a.hist + r.row * kGsHistWords;
     for (int i = tid; i < kGsHistWords; i += kThreads) hist[i] = g[i];
     __syncthreads();
@@ -277,6 +298,10 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   if (pass) {
     for (int i = tid; i < nslots * 256; i += kThreads) hist[i] = 0;
     if (tid < 2 * a.nq && S.slotOf[tid] != 0xff) slotTop[S.slotOf[tid]] = S.prefix[tid] >> shift_of(level - 1);
+    if (tid < kGsMaxStat) {
+      tieRep[tid] = kGsNoKey;
+      tieLo[tid] = tieHi[tid] = 0;
+    }
   }
   __syncthreads();
   const int sh0 = shift_of(level - 1), sh1 = shift_of(level), bmask = bins_of(level) - 1;
@@ -300,8 +325,24 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
         if (pass) {
           const uint64_t k = key_of(x[u]);
           const uint64_t top = k >> sh0;
+          int slot = -1;
           for (int s = 0; s < nslots; ++s)
-            if (slotTop[s] == top) code = s * 256 + (int)((k >> sh1) & (uint64_t)bmask);
+            if (slotTop[s] == top) slot = s;
+          if (slot >= 0) {
+            code = slot * 256 + (int)((k >> sh1) & (uint64_t)bmask);
+            // are the slot's keys all equal?  one representative (first come) and the OR of the differences
+            unsigned long long rep = *(volatile unsigned long long *)&tieRep[slot];
+            if (rep == kGsNoKey) {
+              const unsigned long long old = atomicCAS(&tieRep[slot], (unsigned long long)kGsNoKey, (unsigned long long)k);
+              rep = old == kGsNoKey ? k : old;
+            }
+            const uint64_t d = k ^ rep;
+            if (d) {
+              const unsigned int lo = (unsigned int)d, hi = (unsigned int)(d >> 32);
+              if (lo & ~*(volatile unsigned int *)&tieLo[slot]) atomicOr(&tieLo[slot], lo);
+              if (hi & ~*(volatile unsigned int *)&tieHi[slot]) atomicOr(&tieHi[slot], hi);
+            }
+          }
         }
       }
       if (pass) hist_add(hist, code);
@@ -315,6 +356,12 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
     __syncthreads();
     unsigned int *g = a.hist + r.row * kGsHistWords;
     for (int i = tid; i < nslots * 256; i += kThreads) g[i] = hist[i];
+    if (tid < kGsMaxStat) {
+      GsTie t;
+      t.rep = tieRep[tid];
+      t.diff = ((uint64_t)tieHi[tid] << 32) | tieLo[tid];
+      a.tieAll[((int64_t)a.rank * rows + r.row) * kGsMaxStat + tid] = t;
+    }
   }
 }
 

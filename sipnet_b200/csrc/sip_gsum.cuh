@@ -34,6 +34,12 @@ struct GsStat {  // per row and rank, pass 0
   uint64_t diff;  // OR of (key ^ rep) over the rank's finite members: 0 = they are all equal
 };
 
+struct GsTie {  // per row, histogram slot and rank, written by a level pass
+  uint64_t rep;   // one key of the rank's members in the slot (kGsNoKey = none)
+  uint64_t diff;  // OR of (key ^ rep) over them: 0 = they are all equal
+};
+constexpr uint64_t kGsNoKey = ~0ull;  // never the key of a finite value
+
 struct GsRow {  // selection state of a row; identical on every rank after each exchange
   uint64_t prefix[kGsMaxStat];  // resolved leading key bits of each wanted order statistic (the key when bits == 64)
   uint64_t k[kGsMaxStat];       // its rank among the keys sharing the prefix
@@ -66,6 +72,8 @@ struct GsArgs {
   double *q2All;
   uint32_t *hist;      // [rows][kGsHistWords], summed over ranks between the levels
   GsRow *state;        // [rows]
+  GsTie *tieAll;       // [nranks][rows][kGsMaxStat]: are the keys of a slot all equal? (order statistics inside a
+                       // large group of equal values -- exact zeros -- would otherwise need every key bit)
   uint64_t *emitAll;   // [nranks][rows][kGsMaxStat][kGsEmit]
   int32_t *flags;      // [0] = some row needs the next level
   // results, in the handle's layout: mean/var [site][col][n], quant [site][col][q][n]

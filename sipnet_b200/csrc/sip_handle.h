@@ -56,6 +56,8 @@ struct sipnet_gpu_handle {
   // packed parameter tile of the throughput variants (RunArgs::rowOM)
   int32_t *uniformRows = nullptr;  // device scratch [kNParamDev]
   uint2 rowOM[sip::kNParamDev] = {};
+  double uni[sip::kNParamDev] = {};  // first member's value of every device row
+  sip::StepConsts kc = {};           // launch-lifetime constants of the step (device-evaluated at init)
   int32_t packedTileBytes = 0, nVaryingRows = 0;
 };
 

@@ -150,6 +150,19 @@ __global__ void uniform_rows_kernel(const double *params, int64_t ld, int64_t nm
   if (threadIdx.x == 0) uniform[k] = same;
 }
 
+// (4) launch-lifetime constants (StepConsts): the division seeds of the literal divisors come from the device's own
+// reciprocal approximation, so they are evaluated here, once per handle
+__global__ void consts_kernel(StepConsts *out) {
+  const FastNum fn;
+  const libm::LogHL l2 = libm::pow_log(2.0);  // pow(2, y), sipnet.c:551
+  out->log2Hi = l2.hi;
+  out->log2Lo = l2.lo;
+  out->seed10 = fn.seed(10.0);
+  out->seed5 = fn.seed(kMeanNppDays);
+  out->seed18 = fn.seed(3.0 * 6);
+  out->seed24 = fn.seed(24.0);
+}
+
 // ---- host-side launchers (C++ linkage inside the library) -------------------------------------
 constexpr uint32_t kMaskDefault = F_EVENTS | F_GDD | F_SNOW | F_WATER_HRESP;                       // context.c:35-46
 constexpr uint32_t kMaskCropN = kMaskDefault | F_LITTER_POOL | F_ANAEROBIC | F_NITROGEN;          // russell_2 / C2-C5
@@ -187,6 +200,11 @@ cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t
 
 cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream) {
   uniform_rows_kernel<<<kNParamDev, 256, 0, stream>>>(params, ld, nmembers, uniform);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_consts(StepConsts *out, cudaStream_t stream) {
+  consts_kernel<<<1, 1, 0, stream>>>(out);
   return cudaGetLastError();
 }
 

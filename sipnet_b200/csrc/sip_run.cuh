@@ -25,7 +25,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <initializer_list>
 #include <type_traits>
+#include <utility>
 
 #include "sip_step.cuh"
 
@@ -42,11 +44,15 @@ constexpr int kChunkSteps = 32;  // steps staged per TMA chunk (default): 32 * 1
 // scheduler: everything unrolled, 255 registers, one value per thread for every parameter row).  The throughput
 // policies trade per-warp speed for resident warps: registers capped by MIN_BLOCKS, the packed parameter tile,
 // smaller forcing chunks (shared memory) and smaller canopy groups (fewer live values).
-template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), bool PACKED = false,
-          int CHUNK = kChunkSteps, int CANOPY = 7>
+enum TileKind { kTileDirect = 0, kTilePacked = 1, kTileMask = 2 };
+template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), int TILE = kTileDirect,
+          int CHUNK = kChunkSteps, int CANOPY = 7, class UM = RowMask<0, 0>>
 struct Tune {
-  static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK, kCanopy = CANOPY;
-  static constexpr bool kPacked = PACKED;
+  static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK, kCanopy = CANOPY, kTile = TILE;
+  static constexpr bool kPacked = TILE == kTilePacked;
+  using Mask = UM;
+  using Tile = std::conditional_t<TILE == kTileMask, MaskTile<UM, CANOPY, BLOCK>,
+                                  std::conditional_t<TILE == kTilePacked, PackedTile<CANOPY>, DirectTile>>;
 };
 
 // ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
@@ -246,6 +252,14 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// per-member rows of a compile-time mask -> their compact tile slots (slots are compile-time: one store per row)
+template <class UM, int BLOCK, int... K>
+__device__ __forceinline__ void mask_fill(double *mine, const double *src, int64_t ld, bool active,
+                                          std::integer_sequence<int, K...>) {
+  (void)std::initializer_list<int>{
+      ((tile_slot(K) >= 0 && !UM::uniform(K)) ? (mine[UM::slot(K) * BLOCK] = active ? src[(int64_t)K * ld] : 1.0, 0) : 0)...};
+}
+
 // One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
 // `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN>
@@ -268,7 +282,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
 
   // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
-  if constexpr (TN::kPacked) {
+  if constexpr (TN::kTile == kTilePacked) {
     // (with dynamic scheduling the barrier at the top of the item loop already separates this fill from the
     // previous item's readers of the block-uniform slots)
     unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
@@ -281,15 +295,23 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
       }
     }
     __syncthreads();  // the block-uniform slots are read by every thread
+  } else if constexpr (TN::kTile == kTileMask) {
+    using UM = typename TN::Mask;
+    mask_fill<UM, BLOCK>(tile + tid, a.params + m, a.ld, active, std::make_integer_sequence<int, kNParamDev>{});
+    // launch-uniform rows: one copy per block behind the per-member rows (written once per kernel would do; the
+    // values never change, so rewriting them per item needs no barrier against readers)
+    for (int k = tid; k < kNParamDev; k += BLOCK) tile[UM::rows() * BLOCK + k] = a.uni[k];
+    __syncthreads();
   } else {
     for (int k = 0; k < kNParamDev; ++k) {
       const int slot = tile_slot(k);
       if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
     }
   }
-  using PT = std::conditional_t<TN::kPacked, PackedTile<TN::kCanopy>, DirectTile>;
+  using PT = typename TN::Tile;
   const PT prm = [&]() -> PT {
-    if constexpr (TN::kPacked) return PT{reinterpret_cast<const unsigned char *>(tile) + 8 * tid, 8u * (uint32_t)tid, a};
+    if constexpr (TN::kTile == kTilePacked) return PT{reinterpret_cast<const unsigned char *>(tile) + 8 * tid, 8u * (uint32_t)tid, a};
+    else if constexpr (TN::kTile == kTileMask) return PT{tile + tid, tile + TN::Mask::rows() * BLOCK};
     else return PT{tile + tid, BLOCK};
   }();
 
@@ -337,12 +359,19 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     nm.expTab = libmTab;
     nm.powlogTab = libmTab + 2 * 128;
     // the member-constant divisors must be ordinary numbers (sip_num.cuh divisor_check)
-    const int divisors[] = {SIPNET_P_leafCSpWt, kPsnTRangeSqSlot, SIPNET_P_halfSatPar, SIPNET_P_soilWHC, kTwoWhc,
-                            SIPNET_P_leafCN,    SIPNET_P_woodCN,  SIPNET_P_fineRootCN, SIPNET_P_fAnoxia, kOneMinusFa};
-    for (int k : divisors) nm.divisor_check(prm(k));
-    if (fl.on(F_CSAT)) nm.divisor_check(prm(SIPNET_P_soilCSaturation));
+    nm.divisor_check(SIP_P(leafCSpWt));
+    nm.divisor_check(SIP_K(kPsnTRangeSqSlot));
+    nm.divisor_check(SIP_P(halfSatPar));
+    nm.divisor_check(SIP_P(soilWHC));
+    nm.divisor_check(SIP_K(kTwoWhc));
+    nm.divisor_check(SIP_P(leafCN));
+    nm.divisor_check(SIP_P(woodCN));
+    nm.divisor_check(SIP_P(fineRootCN));
+    nm.divisor_check(SIP_P(fAnoxia));
+    nm.divisor_check(SIP_K(kOneMinusFa));
+    if (fl.on(F_CSAT)) nm.divisor_check(SIP_P(soilCSaturation));
   }
-  const StepConsts kc = make_consts(nm, a.log2Hi, a.log2Lo);
+  const StepConsts &kc = a.kc;
   const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
   if (active) ring_load_head(mb, rg);
   else mb.headW = mb.headV = 0.0;
@@ -507,13 +536,27 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
 // no packed tile, no dynamic-scheduling words, or the packed tile is too large for MINB blocks to share an SM.
 template <class FL, bool FULL, int MINB>
 static cudaError_t launch_packed(const RunArgs &a, int nblocks, cudaStream_t stream) {
-#ifdef SIP_EXPERIMENT_PACK_MINB  // measurement builds: the packed tile at another register budget
-  using TN = Tune<128, SIP_EXPERIMENT_PACK_MINB, true, 16, 7>;
-#else
-  using TN = Tune<128, MINB, true, 16, (MINB >= 4 ? 2 : 4)>;
+#if defined(SIP_EXPERIMENT_MASK_LO)  // measurement builds: the uniform rows as a compile-time mask
+#ifndef SIP_EXPERIMENT_CANOPY
+#define SIP_EXPERIMENT_CANOPY 1
 #endif
+#ifndef SIP_EXPERIMENT_MINB
+#define SIP_EXPERIMENT_MINB MINB
+#endif
+#ifndef SIP_EXPERIMENT_CHUNK
+#define SIP_EXPERIMENT_CHUNK 16
+#endif
+  using TN = Tune<128, SIP_EXPERIMENT_MINB, kTileMask, SIP_EXPERIMENT_CHUNK, SIP_EXPERIMENT_CANOPY,
+                  RowMask<SIP_EXPERIMENT_MASK_LO, SIP_EXPERIMENT_MASK_HI>>;
+  if (a.workCounter == nullptr) return cudaErrorInvalidConfiguration;
+  for (int k = 0; k < kNParamDev; ++k)  // the mask must hold for this ensemble
+    if (TN::Mask::uniform(k) && tile_slot(k) >= 0 && a.rowOM[k].y == 0u) return cudaErrorInvalidConfiguration;
+  const size_t smem = fixed_smem_bytes<TN>() + sizeof(double) * ((size_t)TN::Mask::rows() * 128 + kNParamDev);
+#else
+  using TN = Tune<128, MINB, kTilePacked, 16, (MINB >= 4 ? 2 : 4)>;
   if (a.packedTileBytes <= 0 || a.workCounter == nullptr) return cudaErrorInvalidConfiguration;
   const size_t smem = fixed_smem_bytes<TN>() + (size_t)a.packedTileBytes;
+#endif
   auto dyn = run_kernel<FL, false, FastNum, 128, false, FULL, true, TN>;
   cudaError_t e;
   int dev = 0, sms = 0, perSm = 0;
@@ -539,7 +582,7 @@ inline int preferred_occupancy() {
   static const int v = [] {
     const char *e = getenv("SIPNET_GPU_OCC");
     const int n = e ? atoi(e) : 0;
-    return (n >= 2 && n <= 4) ? n : 0;
+    return (n >= 2 && n <= 4) ? n : 2;  // the throughput variants are opt-in until they beat the dense kernel
   }();
   return v;
 }

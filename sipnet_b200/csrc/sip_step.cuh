@@ -49,8 +49,12 @@ struct DirectTile {
   static constexpr int kCanopyGroup = 7;
   const double *base;  // already offset by threadIdx.x
   int stride;
-  // k is always a compile-time constant at the call sites, so tile_slot(k) folds to a constant
-  __device__ __forceinline__ double operator()(int k) const { return base[tile_slot(k) * stride]; }
+  template <int K>
+  __device__ __forceinline__ double at() const {
+    constexpr int slot = tile_slot(K);
+    static_assert(slot >= 0, "the step reads a parameter row that is not staged (sip_types.cuh SIP_TILE_SKIP_LIST)");
+    return base[slot * stride];
+  }
 };
 // PackedTile (throughput variants): a row whose value is the same for EVERY member of the launch -- in a real
 // ensemble most of the 80 parameters are fixed and only the "estimated" ones are drawn per member -- is stored once
@@ -65,11 +69,45 @@ struct PackedTile {
   uint32_t tid8;              // threadIdx.x * 8
   const RunArgs &a;           // __grid_constant__ kernel parameter: rowOff / rowMask reads are constant-bank operands
   // rowMask[k] = 0 for a per-member row, all ones for a block-uniform row (whose slot takes no thread offset)
-  __device__ __forceinline__ double operator()(int k) const {
-    return *reinterpret_cast<const double *>(mine + (int)(a.rowOM[k].x - (tid8 & a.rowOM[k].y)));
+  template <int K>
+  __device__ __forceinline__ double at() const {
+    return *reinterpret_cast<const double *>(mine + (int)(a.rowOM[K].x - (tid8 & a.rowOM[K].y)));
   }
 };
-#define SIP_P(name) prm(SIPNET_P_##name)
+// MaskTile: the set of launch-uniform rows is a COMPILE-TIME mask (bit k of LO:HI = device row k is uniform).  A uniform
+// row is then an operand straight from the kernel's parameter space (constant bank: no load instruction, no
+// register), a per-member row a shared-memory load at a compile-time offset in a tile of just those rows.  The
+// launcher checks the mask against the rows found uniform on the device and falls back when it does not hold.
+template <uint64_t LO, uint64_t HI>
+struct RowMask {
+  static constexpr uint64_t kLo = LO, kHi = HI;
+  __host__ __device__ static constexpr bool uniform(int k) { return k < 64 ? ((LO >> k) & 1ull) != 0 : ((HI >> (k - 64)) & 1ull) != 0; }
+  // slot of per-member row k in the compact tile = staged per-member rows below it
+  __host__ __device__ static constexpr int slot(int k) {
+    int s = 0;
+    for (int i = 0; i < k; ++i)
+      if (tile_slot(i) >= 0 && !uniform(i)) ++s;
+    return s;
+  }
+  __host__ __device__ static constexpr int rows() { return slot(kNParamDev); }
+};
+template <class UM, int GROUP, int BLOCK>
+struct MaskTile {
+  static constexpr int kCanopyGroup = GROUP;
+  const double *base;  // shared-memory tile of the per-member rows, already offset by threadIdx.x
+  const double *uni;   // shared-memory copy of the launch-uniform rows, [kNParamDev], one per block (broadcast reads)
+  template <int K>
+  __device__ __forceinline__ double at() const {
+    if constexpr (UM::uniform(K)) {
+      return uni[K];
+    } else {
+      constexpr int slot = UM::slot(K);
+      return base[slot * BLOCK];
+    }
+  }
+};
+#define SIP_P(name) prm.template at<SIPNET_P_##name>()
+#define SIP_K(k) prm.template at<(k)>()
 
 // Loads / stores of carried per-member data (ring slots, event counters, state rows).  COHERENT = true goes
 // through L2 (ld.cg / st.cg): with dynamic scheduling consecutive sub-ranges of a member may run on different SMs
@@ -250,23 +288,6 @@ struct StepTrack {
       nLeaching, nFixation, nUptake, meanNPP;
 };
 
-// kernel-lifetime constants: log_inline(2.0) and the division seeds of the literal divisors
-struct StepConsts {
-  double log2Hi, log2Lo;
-  double seed10, seed5, seed18, seed24;  // 10.0 (Q10 exponents), MEAN_NPP_DAYS, 3.0 * NUM_LAYERS, 24.0 (hours)
-};
-template <class NM>
-__device__ __forceinline__ StepConsts make_consts(const NM &nm, double log2Hi, double log2Lo) {
-  StepConsts k;
-  k.log2Hi = log2Hi;
-  k.log2Lo = log2Lo;
-  k.seed10 = nm.seed(10.0);
-  k.seed5 = nm.seed(kMeanNppDays);
-  k.seed18 = nm.seed(3.0 * 6);
-  k.seed24 = nm.seed(24.0);
-  return k;
-}
-
 // per-step divisor context: x / length and the member-constant C:N divisors
 template <class NM, class PT>
 struct Div {
@@ -278,12 +299,12 @@ struct Div {
     if (NM::kFast && invLenPow2 != 0.0) return a * invLenPow2;  // exact: length is a power of two
     return nm.divs(a, len, seedLen);
   }
-  __device__ __forceinline__ double byLeafCN(double a) const { return nm.divs(a, SIP_P(leafCN), prm(kSeedLeafCN)); }
-  __device__ __forceinline__ double byWoodCN(double a) const { return nm.divs(a, SIP_P(woodCN), prm(kSeedWoodCN)); }
+  __device__ __forceinline__ double byLeafCN(double a) const { return nm.divs(a, SIP_P(leafCN), SIP_K(kSeedLeafCN)); }
+  __device__ __forceinline__ double byWoodCN(double a) const { return nm.divs(a, SIP_P(woodCN), SIP_K(kSeedWoodCN)); }
   __device__ __forceinline__ double byFineCN(double a) const {
-    return nm.divs(a, SIP_P(fineRootCN), prm(kSeedFineRootCN));
+    return nm.divs(a, SIP_P(fineRootCN), SIP_K(kSeedFineRootCN));
   }
-  __device__ __forceinline__ double byWhc(double a) const { return nm.divs(a, SIP_P(soilWHC), prm(kSeedWhc)); }
+  __device__ __forceinline__ double byWhc(double a) const { return nm.divs(a, SIP_P(soilWHC), SIP_K(kSeedWhc)); }
 };
 
 // ---- nitrogen helpers, nitrogen.c ----------------------------------------------------
@@ -535,64 +556,83 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // ---------------- calculateFluxes, sipnet.c:1256-1336 -------------------------------
   const double whc = SIP_P(soilWHC);
-  const double lai = nm.divs(mb.leaf, SIP_P(leafCSpWt), prm(kSeedLeafCSpWt));  // :1274
+  const double lai = nm.divs(mb.leaf, SIP_P(leafCSpWt), SIP_K(kSeedLeafCSpWt));  // :1274
   const double meanNpp = nm.divs(mb.ringSum, kMeanNppDays, kc.seed5);          // getMeanTrackerMean, runmean.c:118
   const double woodTot = mb.wood + mb.delta;                                   // getTotalWoodC
 
   // state-independent Q10 / VPD factors first: six independent exp-class evaluations
-  const double q10Fol = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1),
+  const double q10Fol = nm.powc(SIP_P(vegRespQ10), SIP_K(kLogVegQ10), SIP_K(kLogVegQ10 + 1),
                                 nm.divs(c.tair - SIP_P(psnTOpt), 10.0, kc.seed10));      // sipnet.c:1056
-  const double q10Wood = nm.powc(SIP_P(vegRespQ10), prm(kLogVegQ10), prm(kLogVegQ10 + 1), c.tair10);  // :1067
+  const double q10Wood = nm.powc(SIP_P(vegRespQ10), SIP_K(kLogVegQ10), SIP_K(kLogVegQ10 + 1), c.tair10);  // :1067
   const double tsoil10 = c.tsoil10;
-  const double q10Coarse = nm.powc(SIP_P(coarseRootQ10), prm(kLogCoarseQ10), prm(kLogCoarseQ10 + 1), tsoil10);  // :1076
-  const double q10Fine = nm.powc(SIP_P(fineRootQ10), prm(kLogFineQ10), prm(kLogFineQ10 + 1), tsoil10);
-  const double tempEffect = nm.powc(SIP_P(soilRespQ10), prm(kLogSoilQ10), prm(kLogSoilQ10 + 1), tsoil10);  // depeffects.c:72-75
+  const double q10Coarse = nm.powc(SIP_P(coarseRootQ10), SIP_K(kLogCoarseQ10), SIP_K(kLogCoarseQ10 + 1), tsoil10);  // :1076
+  const double q10Fine = nm.powc(SIP_P(fineRootQ10), SIP_K(kLogFineQ10), SIP_K(kLogFineQ10 + 1), tsoil10);
+  const double tempEffect = nm.powc(SIP_P(soilRespQ10), SIP_K(kLogSoilQ10), SIP_K(kLogSoilQ10 + 1), tsoil10);  // depeffects.c:72-75
   const double vpdPow = nm.powc(c.vpd, c.logVpdHi, c.logVpdLo, SIP_P(dVpdExp));                // :626
 
   // potPsn, :590-641
-  const double respPerGram = prm(kRespPerGram);
-  const double grossAMax = prm(kGrossAMax);
+  const double respPerGram = SIP_K(kRespPerGram);
+  const double grossAMax = SIP_K(kGrossAMax);
   // kPsnTRangeSqSlot holds pow((psnTMax - psnTMin) / 2.0, 2), evaluated once per member by the setup kernel
-  double dTemp = nm.divs((SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)), prm(kPsnTRangeSqSlot),
-                         prm(kSeedPsnTRangeSq));
+  double dTemp = nm.divs((SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)), SIP_K(kPsnTRangeSqSlot),
+                         SIP_K(kSeedPsnTRangeSq));
   dTemp = fmax(dTemp, 0.0);
   double dVpd = 1.0 - SIP_P(dVpdSlope) * vpdPow;
   dVpd = fmax(dVpd, 0.0);
   double dLight;
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
-    const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = prm(kSeedHalfSatPar);
-    double eff[7];
-    // the layers are independent: each stage is issued for a group of layers before the next stage (all seven
-    // together for the latency-bound variants; smaller groups keep fewer values live when registers are capped)
-    constexpr int G = PT::kCanopyGroup;
-#pragma unroll
-    for (int g0 = 0; g0 <= 6; g0 += G) {
-#pragma unroll
-      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
-        const double cumLai = lai * ((double)layer / 6);
-        eff[layer] = nm.exp(-1.0 * att * cumLai);
-      }
-#pragma unroll
-      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
-        const double inten = c.par * eff[layer];
-        eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
-      }
-#pragma unroll
-      for (int layer = g0; layer < g0 + G && layer <= 6; ++layer)
-        eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
-    }
+    const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = SIP_K(kSeedHalfSatPar);
     double cum = 0.0;
+    constexpr int G = PT::kCanopyGroup;
+    if constexpr (G == 1) {
+      // one layer per trip of a real loop (throughput variants): the loop body is a fifth of the step's code, and the
+      // instruction cache, not the arithmetic, limits how many warps an SM can keep busy.  Same operations in the
+      // same order: cumLai = lai * (layer / 6), cum += coeff * eff in layer order, then the last layer once off.
+      static constexpr double kFrac[7] = {0.0 / 6, 1.0 / 6, 2.0 / 6, 3.0 / 6, 4.0 / 6, 5.0 / 6, 6.0 / 6};
+      static constexpr double kCoeff[7] = {1, 4, 2, 4, 2, 4, 2};
+      double last = 0.0;
+#pragma unroll 1
+      for (int layer = 0; layer <= 6; ++layer) {
+        const double cumLai = lai * kFrac[layer];
+        const double e = nm.exp(-1.0 * att * cumLai);
+        const double inten = c.par * e;
+        const double q = nm.divs(-1.0 * inten, hsp, seedHsp);
+        last = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, q));
+        cum += kCoeff[layer] * last;
+      }
+      cum -= last;
+    } else {
+      double eff[7];
+      // the layers are independent: each stage is issued for a group of layers before the next stage (all seven
+      // together for the latency-bound variants; smaller groups keep fewer values live when registers are capped)
 #pragma unroll
-    for (int layer = 0; layer <= 6; ++layer) {
-      const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
-      cum += coeff * eff[layer];
+      for (int g0 = 0; g0 <= 6; g0 += G) {
+#pragma unroll
+        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
+          const double cumLai = lai * ((double)layer / 6);
+          eff[layer] = nm.exp(-1.0 * att * cumLai);
+        }
+#pragma unroll
+        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
+          const double inten = c.par * eff[layer];
+          eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
+        }
+#pragma unroll
+        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer)
+          eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
+      }
+#pragma unroll
+      for (int layer = 0; layer <= 6; ++layer) {
+        const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
+        cum += coeff * eff[layer];
+      }
+      cum -= eff[6];
     }
-    cum -= eff[6];
     dLight = nm.divs(cum, 3.0 * 6, kc.seed18);
   } else {
     dLight = 0;
   }
-  const double conv = prm(kConvBase) * lai * 86400.0;
+  const double conv = SIP_K(kConvBase) * lai * 86400.0;
   const double potPsn = grossAMax * dTemp * dVpd * dLight * conv;
   const double baseFolResp = respPerGram * conv;
 
@@ -753,7 +793,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // shared dependency terms (depeffects.c); each is a pure function of (tsoil, soilWater, params)
   double anaerobicIdx = 0.0;  // calcAnaerobicIndex :15-22
   if (fl.on(F_ANAEROBIC) || fl.on(F_NITROGEN)) {
-    anaerobicIdx = clip01(nm.divs(waterFrac - SIP_P(fAnoxia), prm(kOneMinusFa), prm(kSeedOneMinusFa)));
+    anaerobicIdx = clip01(nm.divs(waterFrac - SIP_P(fAnoxia), SIP_K(kOneMinusFa), SIP_K(kSeedOneMinusFa)));
   }
   double moistEffect;  // calcRespMoistEffect :24-63
   if (!fl.on(F_WATER_HRESP) || c.tsoil < 0) {
@@ -761,7 +801,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   } else if (!fl.on(F_ANAEROBIC)) {
     moistEffect = nm.pow(waterFrac, SIP_P(soilRespMoistEffect));
   } else {
-    const double dAer = clip01(nm.divs(waterFrac, SIP_P(fAnoxia), prm(kSeedFAnoxia)));
+    const double dAer = clip01(nm.divs(waterFrac, SIP_P(fAnoxia), SIP_K(kSeedFAnoxia)));
     moistEffect = (1 - anaerobicIdx) * dAer + SIP_P(anaerobicDecompRate) * anaerobicIdx;
   }
   const double tillEffect = 1 + mb.dTill;  // calcTillageEffect :77
@@ -779,7 +819,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     if (fl.on(F_NITROGEN)) cn = nm.div(SIP_P(kCN), SIP_P(kCN) + litterCN);
     const double breakdown = mb.litter * SIP_P(litterBreakdownRate) * tempEffect * moistEffect * tillEffect * cn;
     r.rLitter = breakdown * SIP_P(fracLitterRespired);
-    r.litterToSoil = breakdown * prm(kOneMinusFracLitResp);
+    r.litterToSoil = breakdown * SIP_K(kOneMinusFracLitResp);
   }
 
   // calcRootFluxes, :1176-1196
@@ -860,7 +900,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       const double l2sN = nm.div(r.litterToSoil, litterCN);
       const double inputs = l2sN + dv.byFineCN(r.fineRootLoss) + dv.byWoodCN(r.coarseRootLoss);
       const double sat =
-          fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), prm(kSeedCSat))) : 0.0;
+          fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), SIP_K(kSeedCSat))) : 0.0;
       r.nOrgLitter = dv.byLeafCN(r.leafLitter) - r.leafOffNResorption + dv.byWoodCN(r.woodLitter) - litterMin -
                      l2sN + (inputs * sat);
       r.nOrgSoil = inputs * (1 - sat) - soilMin;
@@ -954,7 +994,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // updatePoolsForSoil, sipnet.c:1634-1680
   if (fl.on(F_LITTER_POOL)) {
     const double inputs = r.coarseRootLoss + r.fineRootLoss + r.litterToSoil;
-    const double sat = fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), prm(kSeedCSat))) : 0.0;
+    const double sat = fl.on(F_CSAT) ? clip01(nm.divs(mb.soil, SIP_P(soilCSaturation), SIP_K(kSeedCSat))) : 0.0;
     mb.litter +=
         (r.woodLitter + r.leafLitter + (inputs * sat) - r.litterToSoil - r.rLitter - r.litterMethane) * len;
     mb.soil += (inputs * (1 - sat) - r.rSoil - r.soilMethane) * len;
@@ -1092,7 +1132,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   t.woodCreation = r.woodCreation * len;
   t.methane = (r.soilMethane + r.litterMethane) * len;
   t.evapotranspiration = (r.transpiration + r.immedEvap + r.evaporation + r.sublimation + r.eventEvap) * len;
-  mb.wetFrac = nm.divs(oldSoilWater + mb.water, prm(kTwoWhc), prm(kSeedTwoWhc));
+  mb.wetFrac = nm.divs(oldSoilWater + mb.water, SIP_K(kTwoWhc), SIP_K(kSeedTwoWhc));
   if (DEBUG) ext.yLitter += r.leafLitter + r.eventLeafOffLitter;
   if (DEBUG) {
     ext.harvRemoved = harvRemoved;

@@ -134,7 +134,16 @@ struct BlockDesc {
   int32_t site, member0, count, pad;
 };
 
+// launch-lifetime constants of the step: log_inline(2.0) and the division seeds (sip_num.cuh FastNum::seed) of the
+// literal divisors.  Evaluated once per handle on the device (consts_kernel) and handed to every launch in the
+// kernel's parameter space, where they are constant-bank operands instead of registers.
+struct StepConsts {
+  double log2Hi, log2Lo;
+  double seed10, seed5, seed18, seed24;  // 10.0 (Q10 exponents), MEAN_NPP_DAYS, 3.0 * NUM_LAYERS, 24.0 (hours)
+};
+
 struct RunArgs {
+  StepConsts kc;
   int64_t ld;
   int64_t nmembers;
   const double *params;
@@ -164,7 +173,6 @@ struct RunArgs {
   int32_t maxRecs;
   int32_t ringCap;
   uint32_t flags;          // runtime flag mask (generic kernel)
-  double log2Hi, log2Lo;   // log_inline(2.0) for pow(2, y), sipnet.c:551
   double invSigma;         // 1 / nee_sigma
   double logNorm;          // -log(sigma) - 0.5*log(2*pi)
   int8_t colSlot[SIPNET_GPU_NOUT];  // output column -> slot in `out`, or -1
@@ -179,6 +187,7 @@ struct RunArgs {
   // the tile and the mask of the thread's own offset to be taken off again (0 = one value per member, all ones = one per block)
   uint2 rowOM[kNParamDev];  // .x = offset, .y = mask
   int32_t packedTileBytes;  // size of the packed tile for 128-member blocks; 0 = not available
+  double uni[kNParamDev];   // row k's value when it is the same for every member (else member 0's)
 };
 
 }  // namespace sip

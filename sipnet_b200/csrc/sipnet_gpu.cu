@@ -34,6 +34,7 @@ namespace k1 {
 // mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members
 cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream);
 cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);
+cudaError_t launch_consts(StepConsts *out, cudaStream_t stream);
 cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream);
 cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
                               const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
@@ -568,6 +569,17 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     h->staticSched = env && env[0] == '1';
   }
 
+  {  // launch-lifetime constants, evaluated by the device
+    StepConsts *dkc = nullptr;
+    INIT_CUDA(dalloc(&dkc, 1));
+    cudaError_t e = k1::launch_consts(dkc, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h->kc, dkc, sizeof h->kc, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dkc);
+    INIT_CUDA(e);
+  }
+
   // ---- setupModel() on the device ----
   {
     int rc = derive_params(h);
@@ -603,6 +615,8 @@ static int derive_params(sipnet_gpu_handle *h) {
     if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "uniform-row launch failed: %s", cudaGetErrorString(e));
     int32_t uni[kNParamDev];
     CUDA_OK(cudaMemcpyAsync(uni, h->uniformRows, sizeof uni, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaMemcpy2DAsync(h->uni, sizeof(double), h->params, (size_t)h->ld * sizeof(double), sizeof(double), kNParamDev,
+                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     int nVar = 0, nUni = 0;
     for (int k = 0; k < kNParamDev; ++k)
@@ -734,11 +748,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
   a.maxRecs = h->maxRecs;
   a.ringCap = h->ringCap;
   a.flags = h->flags;
-  {
-    const libm::LogHL l2 = libm::pow_log(2.0);
-    a.log2Hi = l2.hi;
-    a.log2Lo = l2.lo;
-  }
+  a.kc = h->kc;
   a.invSigma = 1.0 / h->sigma;
   a.logNorm = -std::log(h->sigma) - 0.5 * std::log(2.0 * M_PI);
   memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);
@@ -777,6 +787,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
     a.recCountBackup = h->recCountBk;
   }
   memcpy(a.rowOM, h->rowOM, sizeof a.rowOM);
+  memcpy(a.uni, h->uni, sizeof a.uni);
   a.packedTileBytes = h->packedTileBytes;
   if (!h->staticSched) {
     CUDA_OK(cudaMemsetAsync(h->sched, 0, 16 + (size_t)h->nblocks * sizeof(unsigned int), h->stream));
