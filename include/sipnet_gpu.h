@@ -221,8 +221,13 @@ typedef struct sipnet_gpu_event_record {
 
 /* ---- arithmetic build selection -------------------------------------------- */
 #define SIPNET_GPU_RING_SLOTS_REFERENCE 250
-#define SIPNET_GPU_MATH_VALIDATION 0 /* -fmad=false, IEEE div: mirrors the reference's gcc -O0 x86-64 arithmetic */
-#define SIPNET_GPU_MATH_FAST 1       /* -fmad=true perf build; re-gated at 1e-10 */
+#define SIPNET_GPU_MATH_VALIDATION 0 /* the general kernel: IEEE division, full libm restatement; bit-identical to the
+                                        reference's gcc -O0 x86-64 binary */
+#define SIPNET_GPU_MATH_FAST 1       /* the optimistic kernel: branch-free main paths of the same arithmetic, members
+                                        outside its guards replayed by the general kernel; ALSO bit-identical */
+#define SIPNET_GPU_MATH_THROUGHPUT 2 /* tolerance-budgeted: reciprocal-multiply division, -fmad=true model arithmetic;
+                                        within 1e-10 relative of the reference (north_star's bound), branch / clamp /
+                                        event decisions unchanged on every test ensemble; NOT bit-identical */
 
 typedef struct sipnet_gpu_config {
   int32_t abi_version; /* SIPNET_GPU_ABI_VERSION */

@@ -128,7 +128,7 @@ EVENT_NAME_BY_TYPE = {v: k for k, v in EVENT_TYPE_BY_NAME.items()}
 
 OUT_FULL, OUT_DEBUG, OUT_LOGLIK, OUT_MOMENTS, OUT_QUANTILES, OUT_EVENTS = (
     0x01, 0x02, 0x04, 0x08, 0x10, 0x20)
-MATH_VALIDATION, MATH_FAST = 0, 1
+MATH_VALIDATION, MATH_FAST, MATH_THROUGHPUT = 0, 1, 2
 
 (GATHER_FULL, GATHER_DEBUG, GATHER_LOGLIK, GATHER_STATUS, GATHER_STATE,
  GATHER_MEAN, GATHER_VARIANCE, GATHER_QUANTILES, GATHER_EVENT_COUNTS,

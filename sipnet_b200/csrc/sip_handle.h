@@ -53,12 +53,7 @@ struct sipnet_gpu_handle {
   int32_t *recCountBk = nullptr;
   bool summariesValid = false;
   std::vector<sip::SiteDev> hostSites;
-  // packed parameter tile of the throughput variants (RunArgs::rowOM)
-  int32_t *uniformRows = nullptr;  // device scratch [kNParamDev]
-  uint2 rowOM[sip::kNParamDev] = {};
-  double uni[sip::kNParamDev] = {};  // first member's value of every device row
   sip::StepConsts kc = {};           // launch-lifetime constants of the step (device-evaluated at init)
-  int32_t packedTileBytes = 0, nVaryingRows = 0;
 };
 
 namespace sip {

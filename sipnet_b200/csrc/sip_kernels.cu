@@ -138,19 +138,7 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
   if (recCount != nullptr) recCount[m] = 0;
 }
 
-// (3) which device parameter rows hold the same value (bit for bit) for every member: those rows take one slot per
-// block in the packed tile of the throughput variants (sip_step.cuh PackedTile).  One block per row.
-__global__ void uniform_rows_kernel(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform) {
-  const int k = blockIdx.x;
-  const unsigned long long *row = reinterpret_cast<const unsigned long long *>(params) + (int64_t)k * ld;
-  const unsigned long long first = row[0];
-  int same = 1;
-  for (int64_t m = threadIdx.x; m < nmembers; m += blockDim.x) same &= (row[m] == first) ? 1 : 0;
-  same = __syncthreads_and(same);
-  if (threadIdx.x == 0) uniform[k] = same;
-}
-
-// (4) launch-lifetime constants (StepConsts): the division seeds of the literal divisors come from the device's own
+// (3) launch-lifetime constants (StepConsts): the division seeds of the literal divisors come from the device's own
 // reciprocal approximation, so they are evaluated here, once per handle
 __global__ void consts_kernel(StepConsts *out) {
   const FastNum fn;
@@ -176,14 +164,28 @@ cudaError_t launch_fast_cropn_128(const RunArgs &a, int nblocks, bool full, cuda
 cudaError_t launch_fast_generic_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
 cudaError_t launch_fast_generic_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
 
-// mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members (exact)
+cudaError_t launch_thr_default_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_thr_default_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_thr_cropn_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_thr_cropn_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_thr_generic_32(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+cudaError_t launch_thr_generic_128(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
+
+// mode: 0 = exact (validation), 1 = fast (optimistic), 2 = replay of flagged members (exact), 3 = throughput policy
 cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream) {
   if (blockThreads != 32 && blockThreads != 128) return cudaErrorInvalidValue;
-  if (mode != 1 || debug) return launch_exact(a, nblocks, blockThreads, debug, mode, stream);
+  if ((mode != 1 && mode != 3) || debug) return launch_exact(a, nblocks, blockThreads, debug, mode, stream);
   const uint32_t arith = a.flags & ~(uint32_t)F_SNOW;  // ctx.snow has no arithmetic effect (SURVEY 8a trap 6)
   bool full = a.out != nullptr;
   for (int c = 0; c < SIPNET_GPU_NOUT; ++c) full = full && a.colSlot[c] == c;
   const bool wide = blockThreads == 128;
+  if (mode == 3) {
+    if (arith == (kMaskDefault & ~(uint32_t)F_SNOW))
+      return wide ? launch_thr_default_128(a, nblocks, full, stream) : launch_thr_default_32(a, nblocks, full, stream);
+    if (arith == (kMaskCropN & ~(uint32_t)F_SNOW))
+      return wide ? launch_thr_cropn_128(a, nblocks, full, stream) : launch_thr_cropn_32(a, nblocks, full, stream);
+    return wide ? launch_thr_generic_128(a, nblocks, full, stream) : launch_thr_generic_32(a, nblocks, full, stream);
+  }
   if (arith == (kMaskDefault & ~(uint32_t)F_SNOW))
     return wide ? launch_fast_default_128(a, nblocks, full, stream) : launch_fast_default_32(a, nblocks, full, stream);
   if (arith == (kMaskCropN & ~(uint32_t)F_SNOW))
@@ -195,11 +197,6 @@ cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t
   const int threads = 128;
   const int blocks = (int)((nmembers + threads - 1) / threads);
   derive_params_kernel<<<blocks, threads, 0, stream>>>(params, ld, nmembers, status);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream) {
-  uniform_rows_kernel<<<kNParamDev, 256, 0, stream>>>(params, ld, nmembers, uniform);
   return cudaGetLastError();
 }
 

@@ -25,9 +25,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
-#include <initializer_list>
-#include <type_traits>
-#include <utility>
 
 #include "sip_step.cuh"
 
@@ -40,19 +37,11 @@ namespace k1 {
 
 constexpr int kChunkSteps = 32;  // steps staged per TMA chunk (default): 32 * 176 B = 5632 B
 
-// Tuning policy of one instantiation.  The default is what the latency-bound configurations want (a lone warp per
-// scheduler: everything unrolled, 255 registers, one value per thread for every parameter row).  The throughput
-// policies trade per-warp speed for resident warps: registers capped by MIN_BLOCKS, the packed parameter tile,
-// smaller forcing chunks (shared memory) and smaller canopy groups (fewer live values).
-enum TileKind { kTileDirect = 0, kTilePacked = 1, kTileMask = 2 };
-template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), int TILE = kTileDirect,
-          int CHUNK = kChunkSteps, int CANOPY = 7, class UM = RowMask<0, 0>>
+// Tuning policy of one instantiation: block size, resident blocks per SM asked of the compiler, steps per staged
+// forcing chunk.
+template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), int CHUNK = kChunkSteps>
 struct Tune {
-  static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK, kCanopy = CANOPY, kTile = TILE;
-  static constexpr bool kPacked = TILE == kTilePacked;
-  using Mask = UM;
-  using Tile = std::conditional_t<TILE == kTileMask, MaskTile<UM, CANOPY, BLOCK>,
-                                  std::conditional_t<TILE == kTilePacked, PackedTile<CANOPY>, DirectTile>>;
+  static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK;
 };
 
 // ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
@@ -252,14 +241,6 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// per-member rows of a compile-time mask -> their compact tile slots (slots are compile-time: one store per row)
-template <class UM, int BLOCK, int... K>
-__device__ __forceinline__ void mask_fill(double *mine, const double *src, int64_t ld, bool active,
-                                          std::integer_sequence<int, K...>) {
-  (void)std::initializer_list<int>{
-      ((tile_slot(K) >= 0 && !UM::uniform(K)) ? (mine[UM::slot(K) * BLOCK] = active ? src[(int64_t)K * ld] : 1.0, 0) : 0)...};
-}
-
 // One work item: block descriptor `blk` (up to BLOCK members of one site) over steps [itemBegin, itemEnd).
 // `sc` counts the forcing chunks this CTA has staged so far (chunk sc uses buffer sc & 1, mbarrier parity (sc >> 1) & 1).
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN>
@@ -282,38 +263,11 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
 
   // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
-  if constexpr (TN::kTile == kTilePacked) {
-    // (with dynamic scheduling the barrier at the top of the item loop already separates this fill from the
-    // previous item's readers of the block-uniform slots)
-    unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
-    for (int k = 0; k < kNParamDev; ++k) {
-      if (tile_slot(k) < 0) continue;
-      if (a.rowOM[k].y == 0u) {
-        *reinterpret_cast<double *>(tb + a.rowOM[k].x + 8u * (uint32_t)tid) = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
-      } else if (tid == 0) {  // same value for every member of the launch: one slot per block
-        *reinterpret_cast<double *>(tb + a.rowOM[k].x) = a.params[(int64_t)k * a.ld + bd.member0];
-      }
-    }
-    __syncthreads();  // the block-uniform slots are read by every thread
-  } else if constexpr (TN::kTile == kTileMask) {
-    using UM = typename TN::Mask;
-    mask_fill<UM, BLOCK>(tile + tid, a.params + m, a.ld, active, std::make_integer_sequence<int, kNParamDev>{});
-    // launch-uniform rows: one copy per block behind the per-member rows (written once per kernel would do; the
-    // values never change, so rewriting them per item needs no barrier against readers)
-    for (int k = tid; k < kNParamDev; k += BLOCK) tile[UM::rows() * BLOCK + k] = a.uni[k];
-    __syncthreads();
-  } else {
-    for (int k = 0; k < kNParamDev; ++k) {
-      const int slot = tile_slot(k);
-      if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
-    }
+  for (int k = 0; k < kNParamDev; ++k) {
+    const int slot = tile_slot(k);
+    if (slot >= 0) tile[slot * BLOCK + tid] = active ? a.params[(int64_t)k * a.ld + m] : 1.0;
   }
-  using PT = typename TN::Tile;
-  const PT prm = [&]() -> PT {
-    if constexpr (TN::kTile == kTilePacked) return PT{reinterpret_cast<const unsigned char *>(tile) + 8 * tid, 8u * (uint32_t)tid, a};
-    else if constexpr (TN::kTile == kTileMask) return PT{tile + tid, tile + TN::Mask::rows() * BLOCK};
-    else return PT{tile + tid, BLOCK};
-  }();
+  const DirectTile prm{tile + tid, BLOCK};
 
   auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, min(cs + kChunkSteps, t1)) as chunk `serial`
     const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
@@ -373,8 +327,6 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   }
   const StepConsts &kc = a.kc;
   const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
-  if (active) ring_load_head(mb, rg);
-  else mb.headW = mb.headV = 0.0;
   RecSinkT<DYN> rec{nullptr, nullptr, a.maxRecs, 0};
   if (a.recCount != nullptr && active) {
     rec.count = a.recCount + m;
@@ -425,8 +377,7 @@ __host__ __device__ constexpr size_t fixed_smem_bytes() {  // forcing ring + lib
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN = Tune<BLOCK>>
 __global__ void __launch_bounds__(BLOCK, TN::kMinBlocks) run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [forcing ring 2 x kChunk][libm tables][mbarriers][parameter tile]: the tile comes last because the packed
-  // tile's size is only known at launch
+  // [forcing ring 2 x kChunk][libm tables][mbarriers][parameter tile]
   ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw);                     // [2][kChunk]
   uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * TN::kChunk);   // [kLibmTabWords]
   uint64_t *bars = libmTab + kLibmTabWords;                                     // [2]
@@ -531,66 +482,10 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
   return cudaGetLastError();
 }
 
-// Throughput variants (128-member blocks, dynamic scheduling, packed tile): MINB resident blocks per SM.
-// Returns cudaErrorInvalidConfiguration when the variant does not apply (the caller falls back to launch_one):
-// no packed tile, no dynamic-scheduling words, or the packed tile is too large for MINB blocks to share an SM.
-template <class FL, bool FULL, int MINB>
-static cudaError_t launch_packed(const RunArgs &a, int nblocks, cudaStream_t stream) {
-#if defined(SIP_EXPERIMENT_MASK_LO)  // measurement builds: the uniform rows as a compile-time mask
-#ifndef SIP_EXPERIMENT_CANOPY
-#define SIP_EXPERIMENT_CANOPY 1
-#endif
-#ifndef SIP_EXPERIMENT_MINB
-#define SIP_EXPERIMENT_MINB MINB
-#endif
-#ifndef SIP_EXPERIMENT_CHUNK
-#define SIP_EXPERIMENT_CHUNK 16
-#endif
-  using TN = Tune<128, SIP_EXPERIMENT_MINB, kTileMask, SIP_EXPERIMENT_CHUNK, SIP_EXPERIMENT_CANOPY,
-                  RowMask<SIP_EXPERIMENT_MASK_LO, SIP_EXPERIMENT_MASK_HI>>;
-  if (a.workCounter == nullptr) return cudaErrorInvalidConfiguration;
-  for (int k = 0; k < kNParamDev; ++k)  // the mask must hold for this ensemble
-    if (TN::Mask::uniform(k) && tile_slot(k) >= 0 && a.rowOM[k].y == 0u) return cudaErrorInvalidConfiguration;
-  const size_t smem = fixed_smem_bytes<TN>() + sizeof(double) * ((size_t)TN::Mask::rows() * 128 + kNParamDev);
-#else
-  using TN = Tune<128, MINB, kTilePacked, 16, (MINB >= 4 ? 2 : 4)>;
-  if (a.packedTileBytes <= 0 || a.workCounter == nullptr) return cudaErrorInvalidConfiguration;
-  const size_t smem = fixed_smem_bytes<TN>() + (size_t)a.packedTileBytes;
-#endif
-  auto dyn = run_kernel<FL, false, FastNum, 128, false, FULL, true, TN>;
-  cudaError_t e;
-  int dev = 0, sms = 0, perSm = 0;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if (cudaFuncSetAttribute(dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return cudaErrorInvalidConfiguration;
-  }
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, dyn, 128, smem)) != cudaSuccess) return e;
-  if (perSm < TN::kMinBlocks) return cudaErrorInvalidConfiguration;  // the tile has too many per-member rows for this variant
-  const int resident = sms * perSm;
-  if (nblocks < resident) return cudaErrorInvalidConfiguration;  // not enough members to fill the extra slots
-  RunArgs args = a;
-  args.nblocks = nblocks;
-  args.itemSteps = kItemSteps;
-  dyn<<<resident, 128, smem, stream>>>(args);
-  return cudaGetLastError();
-}
-
-// A/B switch for measurements: SIPNET_GPU_OCC = 2 (never use the throughput variants), 3 or 4 (prefer that variant)
-inline int preferred_occupancy() {
-  static const int v = [] {
-    const char *e = getenv("SIPNET_GPU_OCC");
-    const int n = e ? atoi(e) : 0;
-    return (n >= 2 && n <= 4) ? n : 2;  // the throughput variants are opt-in until they beat the dense kernel
-  }();
-  return v;
-}
-
-template <class FL, int BLOCK>
+template <class FL, int BLOCK, class NM = FastNum>
 static cudaError_t launch_fast(const RunArgs &a, int nblocks, bool full, cudaStream_t stream) {
-  return full ? launch_one<FL, false, FastNum, BLOCK, false, true>(a, nblocks, stream)
-              : launch_one<FL, false, FastNum, BLOCK, false, false>(a, nblocks, stream);
+  return full ? launch_one<FL, false, NM, BLOCK, false, true>(a, nblocks, stream)
+              : launch_one<FL, false, NM, BLOCK, false, false>(a, nblocks, stream);
 }
 
 }  // namespace k1

@@ -2,15 +2,4 @@
 #define SIP_FL StaticFlags<kMaskDefault>
 #define SIP_BLOCK 128
 #define SIP_NAME launch_fast_default_128
-#define SIP_PACK launch_pack_default
 #include "sip_run_fast.inc"
-
-namespace sip {
-namespace k1 {
-cudaError_t launch_pack_default_3(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
-cudaError_t launch_pack_default_4(const RunArgs &a, int nblocks, bool full, cudaStream_t stream);
-cudaError_t launch_pack_default(const RunArgs &a, int nblocks, bool full, int occ, cudaStream_t stream) {
-  return occ == 4 ? launch_pack_default_4(a, nblocks, full, stream) : launch_pack_default_3(a, nblocks, full, stream);
-}
-}  // namespace k1
-}  // namespace sip

@@ -1,0 +1,5 @@
+// throughput policy, flag policy "cropn", 128-member blocks (see sip_run_thr.inc); compiled with -fmad=true
+#define SIP_FL StaticFlags<kMaskCropN>
+#define SIP_BLOCK 128
+#define SIP_NAME launch_thr_cropn_128
+#include "sip_run_thr.inc"

@@ -1,0 +1,5 @@
+// throughput policy, flag policy "default", 32-member blocks (see sip_run_thr.inc); compiled with -fmad=true
+#define SIP_FL StaticFlags<kMaskDefault>
+#define SIP_BLOCK 32
+#define SIP_NAME launch_thr_default_32
+#include "sip_run_thr.inc"

@@ -42,11 +42,10 @@ struct RuntimeFlags {
   __device__ __forceinline__ bool on(uint32_t bit) const { return (mask & bit) != 0; }
 };
 
-// ---- parameter tile in shared memory ----------------------------------------------------------
-// DirectTile: every staged row holds one value per thread, element k of this thread at tile[slot(k) * stride].
-// kCanopyGroup = how many canopy layers of calcLightEff() are issued stage by stage together (7 = all).
+// ---- parameter tile in shared memory: row K of this thread at tile[slot(K) * stride] -----------------------------
+// K is a template argument, so the slot folds to a constant and a read of a row the tile does not stage is a
+// compile-time error.
 struct DirectTile {
-  static constexpr int kCanopyGroup = 7;
   const double *base;  // already offset by threadIdx.x
   int stride;
   template <int K>
@@ -54,56 +53,6 @@ struct DirectTile {
     constexpr int slot = tile_slot(K);
     static_assert(slot >= 0, "the step reads a parameter row that is not staged (sip_types.cuh SIP_TILE_SKIP_LIST)");
     return base[slot * stride];
-  }
-};
-// PackedTile (throughput variants): a row whose value is the same for EVERY member of the launch -- in a real
-// ensemble most of the 80 parameters are fixed and only the "estimated" ones are drawn per member -- is stored once
-// per block (8 bytes, read as a broadcast) instead of once per thread.  Which rows are uniform is found on the
-// device after every parameter upload (uniform_rows_kernel) and reaches the kernel as two words per row in its
-// parameter space: byte offset and an all-ones / zero mask for the thread's own offset.  The tile shrinks from
-// 90 x BLOCK x 8 B to (varying rows) x BLOCK x 8 B, which is what lets 3-4 blocks share an SM.
-template <int GROUP>
-struct PackedTile {
-  static constexpr int kCanopyGroup = GROUP;
-  const unsigned char *mine;  // shared-memory tile + threadIdx.x * 8
-  uint32_t tid8;              // threadIdx.x * 8
-  const RunArgs &a;           // __grid_constant__ kernel parameter: rowOff / rowMask reads are constant-bank operands
-  // rowMask[k] = 0 for a per-member row, all ones for a block-uniform row (whose slot takes no thread offset)
-  template <int K>
-  __device__ __forceinline__ double at() const {
-    return *reinterpret_cast<const double *>(mine + (int)(a.rowOM[K].x - (tid8 & a.rowOM[K].y)));
-  }
-};
-// MaskTile: the set of launch-uniform rows is a COMPILE-TIME mask (bit k of LO:HI = device row k is uniform).  A uniform
-// row is then an operand straight from the kernel's parameter space (constant bank: no load instruction, no
-// register), a per-member row a shared-memory load at a compile-time offset in a tile of just those rows.  The
-// launcher checks the mask against the rows found uniform on the device and falls back when it does not hold.
-template <uint64_t LO, uint64_t HI>
-struct RowMask {
-  static constexpr uint64_t kLo = LO, kHi = HI;
-  __host__ __device__ static constexpr bool uniform(int k) { return k < 64 ? ((LO >> k) & 1ull) != 0 : ((HI >> (k - 64)) & 1ull) != 0; }
-  // slot of per-member row k in the compact tile = staged per-member rows below it
-  __host__ __device__ static constexpr int slot(int k) {
-    int s = 0;
-    for (int i = 0; i < k; ++i)
-      if (tile_slot(i) >= 0 && !uniform(i)) ++s;
-    return s;
-  }
-  __host__ __device__ static constexpr int rows() { return slot(kNParamDev); }
-};
-template <class UM, int GROUP, int BLOCK>
-struct MaskTile {
-  static constexpr int kCanopyGroup = GROUP;
-  const double *base;  // shared-memory tile of the per-member rows, already offset by threadIdx.x
-  const double *uni;   // shared-memory copy of the launch-uniform rows, [kNParamDev], one per block (broadcast reads)
-  template <int K>
-  __device__ __forceinline__ double at() const {
-    if constexpr (UM::uniform(K)) {
-      return uni[K];
-    } else {
-      constexpr int slot = UM::slot(K);
-      return base[slot * BLOCK];
-    }
   }
 };
 #define SIP_P(name) prm.template at<SIPNET_P_##name>()
@@ -132,9 +81,6 @@ struct Member {
   double gdd, totNee, wetFrac;
   double dTill;    // eventTrackers.d_till_mod, events.h:213-221
   double ringSum;  // MeanTracker.sum, runmean.h
-  // the ring's oldest entry (slot ringStart), loaded one step ahead of its use: the push at the end of step t needs
-  // it first, and a load issued there would sit on the critical path with an L2 round trip
-  double headW, headV;
   int ringStart, ringLast;
   int trkLastYear;   // trackers.lastYear
   int phenLastYear;  // phenologyTrackers.lastYear
@@ -171,21 +117,15 @@ struct RingRefT {
 };
 
 template <class RG>
-__device__ __forceinline__ void ring_load_head(Member &mb, const RG &rg) {
-  mb.headW = rg.wgt(mb.ringStart);
-  mb.headV = rg.val(mb.ringStart);
-}
-
-template <class RG>
 __device__ __forceinline__ void ring_reset(Member &mb, const RG &rg, double v) {  // runmean.c:44-51
   mb.ringStart = mb.ringLast = 0;
   rg.set_val(0, v);
   rg.set_wgt(0, kMeanNppDays);
   mb.ringSum = v * kMeanNppDays;
-  mb.headW = kMeanNppDays;
-  mb.headV = v;
 }
 
+// (Loading the ring's oldest entry one step ahead of its use -- the load sits at the end of the step -- was measured:
+// no change on the filled GPU, and the four extra registers cost the C2 kernel a spill.  Left as it is.)
 template <class RG>
 __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value, double weight) {
   // addValueToMeanTracker, runmean.c:61-115 (weight <= 0 is rejected at init: events.c:460)
@@ -196,8 +136,9 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
   double left = weight;
   int i = mb.ringStart;
   double sum = mb.ringSum;
-  double wi = mb.headW, vi = mb.headV;  // slot ringStart, loaded at the end of the previous step
   while (left > 0) {
+    const double wi = rg.wgt(i);
+    const double vi = rg.val(i);
     if (wi > left) {
       rg.set_wgt(i, wi - left);
       sum -= left * vi;
@@ -206,10 +147,6 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
       sum -= wi * vi;
       left -= wi;
       i = (i + 1 == rg.cap) ? 0 : i + 1;
-      if (left > 0) {
-        wi = rg.wgt(i);
-        vi = rg.val(i);
-      }
     }
   }
   mb.ringStart = i;
@@ -219,7 +156,6 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
     sum += weight * rg.val(i);
     mb.ringSum = sum;
     mb.status |= SIPNET_GPU_ST_RING_OVERFLOW;
-    ring_load_head(mb, rg);
     return;
   }
   mb.ringLast = i;
@@ -227,7 +163,6 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
   rg.set_wgt(i, weight);
   sum += value * weight;
   mb.ringSum = sum;
-  ring_load_head(mb, rg);  // next step's head (after the stores above: it may be the entry just written)
 }
 
 // ---- small helpers ---------------------------------------------------------------
@@ -582,52 +517,27 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   double dLight;
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
     const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = SIP_K(kSeedHalfSatPar);
-    double cum = 0.0;
-    constexpr int G = PT::kCanopyGroup;
-    if constexpr (G == 1) {
-      // one layer per trip of a real loop (throughput variants): the loop body is a fifth of the step's code, and the
-      // instruction cache, not the arithmetic, limits how many warps an SM can keep busy.  Same operations in the
-      // same order: cumLai = lai * (layer / 6), cum += coeff * eff in layer order, then the last layer once off.
-      static constexpr double kFrac[7] = {0.0 / 6, 1.0 / 6, 2.0 / 6, 3.0 / 6, 4.0 / 6, 5.0 / 6, 6.0 / 6};
-      static constexpr double kCoeff[7] = {1, 4, 2, 4, 2, 4, 2};
-      double last = 0.0;
-#pragma unroll 1
-      for (int layer = 0; layer <= 6; ++layer) {
-        const double cumLai = lai * kFrac[layer];
-        const double e = nm.exp(-1.0 * att * cumLai);
-        const double inten = c.par * e;
-        const double q = nm.divs(-1.0 * inten, hsp, seedHsp);
-        last = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, q));
-        cum += kCoeff[layer] * last;
-      }
-      cum -= last;
-    } else {
-      double eff[7];
-      // the layers are independent: each stage is issued for a group of layers before the next stage (all seven
-      // together for the latency-bound variants; smaller groups keep fewer values live when registers are capped)
+    double eff[7];
+    // the seven layers are independent: each stage is issued for all layers before the next one
 #pragma unroll
-      for (int g0 = 0; g0 <= 6; g0 += G) {
-#pragma unroll
-        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
-          const double cumLai = lai * ((double)layer / 6);
-          eff[layer] = nm.exp(-1.0 * att * cumLai);
-        }
-#pragma unroll
-        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer) {
-          const double inten = c.par * eff[layer];
-          eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
-        }
-#pragma unroll
-        for (int layer = g0; layer < g0 + G && layer <= 6; ++layer)
-          eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
-      }
-#pragma unroll
-      for (int layer = 0; layer <= 6; ++layer) {
-        const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
-        cum += coeff * eff[layer];
-      }
-      cum -= eff[6];
+    for (int layer = 0; layer <= 6; ++layer) {
+      const double cumLai = lai * ((double)layer / 6);
+      eff[layer] = nm.exp(-1.0 * att * cumLai);
     }
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) {
+      const double inten = c.par * eff[layer];
+      eff[layer] = nm.divs(-1.0 * inten, hsp, seedHsp);
+    }
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) eff[layer] = (1 - nm.powc(2.0, kc.log2Hi, kc.log2Lo, eff[layer]));
+    double cum = 0.0;
+#pragma unroll
+    for (int layer = 0; layer <= 6; ++layer) {
+      const int coeff = (layer == 0) ? 1 : 2 * (1 + layer % 2);
+      cum += coeff * eff[layer];
+    }
+    cum -= eff[6];
     dLight = nm.divs(cum, 3.0 * 6, kc.seed18);
   } else {
     dLight = 0;

@@ -183,11 +183,6 @@ struct RunArgs {
   unsigned long long *workCounter;  // next work item
   unsigned int *progress;           // [nblocks] sub-ranges completed per block descriptor
   int32_t nblocks, itemSteps;
-  // packed parameter tile of the throughput variants (sip_step.cuh PackedTile): per device row the byte offset in
-  // the tile and the mask of the thread's own offset to be taken off again (0 = one value per member, all ones = one per block)
-  uint2 rowOM[kNParamDev];  // .x = offset, .y = mask
-  int32_t packedTileBytes;  // size of the packed tile for 128-member blocks; 0 = not available
-  double uni[kNParamDev];   // row k's value when it is the same for every member (else member 0's)
 };
 
 }  // namespace sip

@@ -35,7 +35,6 @@ namespace k1 {
 cudaError_t launch_run(const RunArgs &a, int nblocks, int blockThreads, bool debug, int mode, cudaStream_t stream);
 cudaError_t launch_derive(double *params, int64_t ld, int64_t nmembers, uint32_t *status, cudaStream_t stream);
 cudaError_t launch_consts(StepConsts *out, cudaStream_t stream);
-cudaError_t launch_uniform_rows(const double *params, int64_t ld, int64_t nmembers, int32_t *uniform, cudaStream_t stream);
 cudaError_t launch_init_state(const double *params, int64_t ld, int64_t nmembers, const int32_t *memberSite,
                               const SiteDev *sites, uint32_t flags, double *state, double *ringV, double *ringW,
                               uint32_t *status, double *loglik, double *loglikN, int32_t *recCount,
@@ -326,7 +325,7 @@ static void free_handle(sipnet_gpu_handle *h) {
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
                   h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant,
                   h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
-                  h->recCountBk, h->sched, h->uniformRows};
+                  h->recCountBk, h->sched};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (void *p : h->siteAllocs)
@@ -369,7 +368,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   if (cfg->nsites <= 0 || !cfg->sites) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no sites");
   if (cfg->nmembers <= 0 || !cfg->params) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "no members / params");
   if (cfg->params_ld < cfg->nmembers) return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "params_ld < nmembers");
-  if (cfg->math != SIPNET_GPU_MATH_VALIDATION && cfg->math != SIPNET_GPU_MATH_FAST)
+  if (cfg->math != SIPNET_GPU_MATH_VALIDATION && cfg->math != SIPNET_GPU_MATH_FAST && cfg->math != SIPNET_GPU_MATH_THROUGHPUT)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "unknown math mode %d", cfg->math);
   if (cfg->block_threads != 0 && cfg->block_threads != 32 && cfg->block_threads != 128)
     return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "block_threads must be 0, 32 or 128");
@@ -541,7 +540,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     INIT_CUDA(dalloc(&h->recCount, (size_t)h->ld));
     if (h->maxRecs > 0) INIT_CUDA(dalloc(&h->recs, (size_t)h->nmembers * h->maxRecs));
   }
-  if (h->math == SIPNET_GPU_MATH_FAST) {
+  if (h->math != SIPNET_GPU_MATH_VALIDATION) {
     INIT_CUDA(dalloc(&h->stateBk, (size_t)SIPNET_GPU_NSTATE * h->ld));
     INIT_CUDA(dalloc(&h->ringVBk, (size_t)h->ringCap * h->ld));
     INIT_CUDA(dalloc(&h->ringWBk, (size_t)h->ringCap * h->ld));
@@ -605,37 +604,6 @@ static int derive_params(sipnet_gpu_handle *h) {
   cudaError_t e = k1::launch_derive(h->params, h->ld, h->nmembers, h->status, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "derive launch failed: %s", cudaGetErrorString(e));
-  // layout of the packed tile: rows that vary between members first (one value per thread), then one 8-byte slot
-  // per row that is the same for every member
-  h->packedTileBytes = 0;
-  if (h->blockThreads == 128) {
-    if (!h->uniformRows) CUDA_OK(dalloc(&h->uniformRows, (size_t)kNParamDev));
-    e = k1::launch_uniform_rows(h->params, h->ld, h->nmembers, h->uniformRows, h->stream);
-    h->launches++;
-    if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "uniform-row launch failed: %s", cudaGetErrorString(e));
-    int32_t uni[kNParamDev];
-    CUDA_OK(cudaMemcpyAsync(uni, h->uniformRows, sizeof uni, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaMemcpy2DAsync(h->uni, sizeof(double), h->params, (size_t)h->ld * sizeof(double), sizeof(double), kNParamDev,
-                              cudaMemcpyDeviceToHost, h->stream));
-    CUDA_OK(cudaStreamSynchronize(h->stream));
-    int nVar = 0, nUni = 0;
-    for (int k = 0; k < kNParamDev; ++k)
-      if (tile_slot(k) >= 0 && !uni[k]) ++nVar;
-    h->nVaryingRows = nVar;
-    int v = 0;
-    for (int k = 0; k < kNParamDev; ++k) {
-      h->rowOM[k].x = 0;
-      h->rowOM[k].y = 0;
-      if (tile_slot(k) < 0) continue;
-      if (!uni[k]) {
-        h->rowOM[k].x = (uint32_t)(v++) * 128u * 8u;
-      } else {  // the mask removes the thread's own offset again
-        h->rowOM[k].x = (uint32_t)nVar * 128u * 8u + (uint32_t)(nUni++) * 8u;
-        h->rowOM[k].y = 0xffffffffu;
-      }
-    }
-    h->packedTileBytes = nVar * 128 * 8 + (nUni * 8 + 15) / 16 * 16;
-  }
   return 0;
 }
 
@@ -765,7 +733,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
                               h->stream));
   }
   const bool debug = h->dbg != nullptr;
-  const bool optimistic = (h->math == SIPNET_GPU_MATH_FAST) && !debug;
+  const bool optimistic = (h->math != SIPNET_GPU_MATH_VALIDATION) && !debug;
   if (optimistic) {  // keep the segment's start state so flagged members can be replayed exactly
     const size_t ldB = (size_t)h->ld * sizeof(double);
     CUDA_OK(cudaMemcpyAsync(h->stateBk, h->state, SIPNET_GPU_NSTATE * ldB, cudaMemcpyDeviceToDevice, h->stream));
@@ -786,16 +754,14 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
     a.loglikNBackup = h->loglikNBk;
     a.recCountBackup = h->recCountBk;
   }
-  memcpy(a.rowOM, h->rowOM, sizeof a.rowOM);
-  memcpy(a.uni, h->uni, sizeof a.uni);
-  a.packedTileBytes = h->packedTileBytes;
   if (!h->staticSched) {
     CUDA_OK(cudaMemsetAsync(h->sched, 0, 16 + (size_t)h->nblocks * sizeof(unsigned int), h->stream));
     a.workCounter = reinterpret_cast<unsigned long long *>(h->sched);
     a.progress = reinterpret_cast<unsigned int *>(h->sched + 16);
   }
   CUDA_OK(cudaEventRecord(h->evStart, h->stream));
-  cudaError_t e = k1::launch_run(a, h->nblocks, h->blockThreads, debug, optimistic ? 1 : 0, h->stream);
+  const int mode = !optimistic ? 0 : (h->math == SIPNET_GPU_MATH_THROUGHPUT ? 3 : 1);
+  cudaError_t e = k1::launch_run(a, h->nblocks, h->blockThreads, debug, mode, h->stream);
   h->launches++;
   if (e != cudaSuccess) return fail(SIPNET_GPU_ERR_NO_DEVICE, "run launch failed: %s", cudaGetErrorString(e));
   CUDA_OK(cudaEventRecord(h->evStop, h->stream));

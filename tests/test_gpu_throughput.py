@@ -1,0 +1,94 @@
+"""GPU: the tolerance-budgeted throughput policy (SIPNET_GPU_MATH_THROUGHPUT: reciprocal-multiply division,
+-fmad=true model arithmetic; sip_num.cuh ThroughNum).  north_star's bar for a non-bit-exact build: every pool and
+flux within 1e-10 relative of the reference, event day/type application and pool-clamping branches EXACTLY.
+
+Checked against the oracle (bit-identical to the reference) on the golden cases, 10-year wide-prior ensembles with
+the full event schedule (deaths and re-emergences included), a multi-site run and random flag combinations:
+  * all 32 outputState() columns within RTOL = 1e-10 (tests/gpu_util.py metric, plantWoodC floor for the
+    cancellation accumulator),
+  * events.out rows: same steps, types, variants (exact), values within RTOL,
+  * the empty / non-empty pattern of every pool column (clamp and mortality outcomes) and the status bit DIED
+    exactly.  "Empty" = below 1e-12 of the column's magnitude: after a complete leaf drop or a root die-back the
+    reference itself is left with a rounding residue (plantLeafC = 1.7e-18 for hundreds of steps in golden
+    synth_unequal_m1) where another rounding gives -1e-18, which the clamp turns into 0 -- not a decision of the
+    model, and invisible at 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import Golden, golden_names
+from gpu_util import RTOL, assert_close, out_scales, random_flag_cases
+from sipnet_b200 import _abi as A, api, synth
+
+pytestmark = pytest.mark.gpu
+
+POOL_COLS = [A.O[n] for n in ("plantWoodC", "plantLeafC", "soilC", "coarseRootC", "fineRootC", "litterC", "soilWater", "snow",
+                              "minN", "soilOrgN", "litterN", "plantStorageN")]
+WORST = {"err": 0.0}
+
+
+def run_throughput(sites, params, ms, flags, **kw):
+    with api.Ensemble(sites, params, ms, flags, outputs=A.OUT_FULL | A.OUT_EVENTS, math=A.MATH_THROUGHPUT,
+                      max_event_records=4096, **kw) as ens:
+        ens.run()
+        return dict(out=ens.output(), status=ens.status(), recs=ens.event_records())
+
+
+def check(res, m, o_out, o_recs, tag):
+    T = o_out.shape[0]
+    g = res["out"][:, :T, m].T
+    WORST["err"] = max(WORST["err"], assert_close(g, o_out, out_scales(o_out), A.OUT_NAMES, RTOL, tag))
+    tiny = 1e-12 * np.maximum(np.nanmax(np.abs(o_out[:, POOL_COLS]), axis=0), 1e-300)
+    assert np.array_equal(np.abs(g[:, POOL_COLS]) <= tiny, np.abs(o_out[:, POOL_COLS]) <= tiny), \
+        f"{tag}: pool clamp / mortality pattern differs"
+    got = res["recs"][m]
+    assert [(r.step, r.type, r.variant, r.nval) for r in got] == [(r.step, r.type, r.variant, r.nval) for r in o_recs], \
+        f"{tag}: event rows differ"
+    for a, b in zip(got, o_recs):
+        for k in range(b.nval):
+            assert abs(a.val[k] - b.val[k]) <= RTOL * max(abs(a.val[k]), abs(b.val[k]), 1e-6), (tag, b.type, k)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_cases_within_budget(oracle, name):
+    g = Golden(name)
+    P = np.ascontiguousarray((g.params if g.params.ndim == 2 else g.params.reshape(A.NPARAMS, 1)))
+    res = run_throughput([g.site], P, None, g.flags)
+    for m in range(P.shape[1]):
+        rc, done, o_out, _, o_recs = oracle.run(g.flags, P[:, m], g.site, want_debug=False, max_event_records=4096)
+        assert rc == g.rc
+        if rc == 0:
+            check(res, m, o_out[:done], o_recs, f"{name}[{m}]")
+
+
+@pytest.mark.parametrize("variant", ["half-daily", "unequal"])
+def test_wide_prior_ensemble_10yr_within_budget(oracle, variant):
+    site = synth.synth_site(2, 10, variant, with_events=True)
+    P = synth.synth_params(96, stream=3)
+    res = run_throughput([site], P, None, synth.SYNTH_FLAGS)
+    died = 0
+    for m in range(0, 96, 4):
+        rc, done, o_out, _, o_recs = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, want_debug=False, max_event_records=4096)
+        assert rc == 0
+        check(res, m, o_out, o_recs, f"{variant}[{m}]")
+        died += int(any(r.type == 7 for r in o_recs))
+        assert bool(res["status"][m] & A.ST_DIED) == any(r.type == 7 for r in o_recs)
+    assert died > 0, "the ensemble should exercise mortality"
+
+
+def test_multi_site_and_random_flags_within_budget(oracle):
+    sites, P, ms, flags = synth.config_c3(nsites=4, members_per_site=24, nyears=3)
+    res = run_throughput(sites, P, ms, flags)
+    for m in range(0, P.shape[1], 5):
+        rc, done, o_out, _, o_recs = oracle.run(flags, P[:, m], sites[ms[m]], want_debug=False, max_event_records=4096)
+        check(res, m, o_out, o_recs, f"c3[{m}]")
+    for trial, f, site, Pt in random_flag_cases(ntrials=16, members=4, seed=99):
+        res = run_throughput([site], Pt, None, f)
+        for m in range(Pt.shape[1]):
+            rc, done, o_out, _, o_recs = oracle.run(f, Pt[:, m], site, want_debug=False, max_event_records=4096)
+            if rc == 0:
+                check(res, m, o_out, o_recs if f["events"] else [], f"flags[{trial}][{m}]")
+
+
+def test_zz_report_worst_error():
+    print(f"throughput policy: worst relative error vs the oracle {WORST['err']:.3e} (budget {RTOL:.0e})")
+    assert WORST["err"] <= RTOL

@@ -36,7 +36,8 @@ def child(args):
         kw = dict(outputs=A.OUT_MOMENTS, summary_cols=[A.O["nee"], A.O["gpp"]])
     else:  # full output, segmented
         kw = dict(outputs=A.OUT_FULL, out_steps_capacity=64)
-    ens = api.Ensemble([site], params, None, flags, math=A.MATH_FAST, device=0, **kw)
+    math = {"fast": A.MATH_FAST, "throughput": A.MATH_THROUGHPUT, "validation": A.MATH_VALIDATION}[args.math]
+    ens = api.Ensemble([site], params, None, flags, math=math, device=0, **kw)
     T = ens.max_steps
 
     def one():
@@ -61,7 +62,7 @@ def child(args):
     st = ens.status()
     ens.close()
     k = float(np.mean(ms))
-    print(json.dumps({"mode": args.mode, "members": M, "occ": os.environ.get("SIPNET_GPU_OCC", "auto"),
+    print(json.dumps({"mode": args.mode, "math": args.math, "members": M, "occ": os.environ.get("SIPNET_GPU_OCC", "auto"),
                       "lib": os.path.basename(os.environ.get("SIPNET_GPU_LIB", "default")), "kernel_ms": round(k, 3),
                       "member_steps_per_s": M * T / (k * 1e-3), "checksum": digest,
                       "replayed": int((st & A.ST_REPLAY).astype(bool).sum())}), flush=True)
@@ -75,6 +76,7 @@ def main():
     ap.add_argument("--occ", default="2,3,4")
     ap.add_argument("--libs", default="")
     ap.add_argument("--mode", default="")
+    ap.add_argument("--math", default="fast", help="fast | throughput | validation (comma list in the parent)")
     args = ap.parse_args()
     if args.mode:
         return child(args)
@@ -82,13 +84,14 @@ def main():
     for lib in libs:
         for mode in args.modes.split(","):
             for occ in args.occ.split(","):
-                env = dict(os.environ)
-                if occ != "auto":
-                    env["SIPNET_GPU_OCC"] = occ
-                if lib:
-                    env["SIPNET_GPU_LIB"] = os.path.abspath(lib)
-                subprocess.call([sys.executable, os.path.abspath(__file__), "--mode", mode, "--members", str(args.members),
-                                 "--years", str(args.years)], env=env)
+                for math in args.math.split(","):
+                    env = dict(os.environ)
+                    if occ != "auto":
+                        env["SIPNET_GPU_OCC"] = occ
+                    if lib:
+                        env["SIPNET_GPU_LIB"] = os.path.abspath(lib)
+                    subprocess.call([sys.executable, os.path.abspath(__file__), "--mode", mode, "--members", str(args.members),
+                                     "--years", str(args.years), "--math", math], env=env)
 
 
 if __name__ == "__main__":
