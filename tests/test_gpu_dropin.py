@@ -225,6 +225,63 @@ def test_site_list_runs_many_sites_in_one_launch(smoke_dir, tmp_path):
     assert subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--site-list", "sites.txt", "--restart-out", "x"], cwd=work).returncode == 8
 
 
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_ngpus() < 2", reason="needs two GPUs on the box")
+def test_many_member_launches_on_all_gpus_equal_one_gpu(smoke_dir, tmp_path):
+    """The driver fans a --site-list / --ensemble-params launch out over every visible GPU (sipnet_gpu_multi_*; the
+    seam is the reference's runModelOutput(), sipnet.c:1954-1990).  Every output file must equal, byte for byte, the
+    one written with --devices 1: whole sites per GPU for the site list (5 sites), one site's members split over the
+    GPUs for the ensemble (7 members)."""
+    import shutil
+    src = os.path.join(smoke_dir, "russell_2")
+    base = open(os.path.join(src, "sipnet.param")).read()
+
+    def make(work):
+        os.makedirs(work)
+        shutil.copy(os.path.join(src, "sipnet.in"), work)
+        sites = []
+        for i in range(5):
+            d = os.path.join(work, f"site{i}")
+            os.makedirs(d)
+            for fn in ("sipnet.clim", "events.in"):
+                shutil.copy(os.path.join(src, fn), d)
+            open(os.path.join(d, "sipnet.param"), "w").write(base.replace("aMax 53.2895432752984", f"aMax {40 + 3 * i}.5"))
+            sites.append(d)
+        open(os.path.join(work, "sites.txt"), "w").write("".join(f"{d}/sipnet\n" for d in sites))
+        ens = os.path.join(work, "ens")
+        os.makedirs(ens)
+        for fn in ("sipnet.clim", "events.in", "sipnet.param"):
+            shutil.copy(os.path.join(src, fn), ens)
+        members = []
+        for k in range(7):
+            p = os.path.join(ens, f"m{k}.param")
+            open(p, "w").write(base.replace("soilWHC 12", f"soilWHC {9 + 0.5 * k}"))
+            members.append(p)
+        open(os.path.join(ens, "members.txt"), "w").write("\n".join(members) + "\n")
+        return sites, ens
+
+    outs = {}
+    for tag, extra in (("one", ["--devices", "1"]), ("all", [])):
+        work = str(tmp_path / tag)
+        sites, ens = make(work)
+        r = subprocess.run([DRIVER, "-i", "sipnet.in", "--site-list", "sites.txt", *extra], cwd=work, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        if tag == "all":
+            assert f"on {min(_ngpus(), 5)} GPU(s)" in r.stdout, r.stdout
+        r = subprocess.run([DRIVER, "-i", "../sipnet.in", "-f", "sipnet", "-e", "events", "--ensemble-params", "members.txt", *extra],
+                           cwd=ens, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        files = [f"{d}/sipnet.out" for d in sites] + [f"{d}/events.out" for d in sites]
+        files += [f"{ens}/sipnet.out.{k}" for k in range(7)] + [f"{ens}/events.out.{k}" for k in range(7)]
+        outs[tag] = [open(f, "rb").read() for f in files]
+        assert all(len(b) > 1000 for b in outs[tag][:5])
+    assert outs["one"] == outs["all"]
+
+
 @pytest.mark.parametrize("case", SMOKE)
 def test_single_variable_outputs_byte_identical(smoke_dir, case):
     """--do-single-outputs: <prefix>.NEE / .NEE_cum / .GPP / .GPP_cum equal the reference's files (md5 from
