@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -230,7 +231,9 @@ class Ensemble:
         cfg = self._configure(sites, params, member_site, flags, outputs, math, device, out_steps_capacity, summary_cols,
                               quantiles, nee_sigma, max_event_records, block_threads, stream, ring_slots)
         self.handle = C.c_void_p()
+        t0 = time.perf_counter()
         rc = self.lib.sipnet_gpu_init(C.byref(cfg), C.byref(self.handle))
+        self.init_seconds = time.perf_counter() - t0           # the library call alone (not the ctypes marshalling)
         if rc != 0:
             self.handle = None
             raise SipnetGpuError(rc, (self.lib.sipnet_gpu_last_error() or b"").decode())

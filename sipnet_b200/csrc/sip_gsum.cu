@@ -307,6 +307,16 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   const int sh0 = shift_of(level - 1), sh1 = shift_of(level), bmask = bins_of(level) - 1;
   const double mu = S.mean;
   double q2 = 0.0;
+  // the slots' resolved prefixes in registers (compared with every element); unused slots never match
+  uint64_t top[kGsMaxStat];
+#pragma unroll
+  for (int s = 0; s < kGsMaxStat; ++s) top[s] = (pass && s < nslots) ? slotTop[s] : kGsNoKey;
+  // "are the slot's keys all equal?" is only worth asking where a slot is still large after the first refinement:
+  // a group of equal values (exact zeros) that holds a wanted order statistic
+  unsigned trackMask = 0;
+  if (pass && level >= 2)
+    for (int r2 = 0; r2 < 2 * a.nq; ++r2)
+      if (S.slotOf[r2] != 0xff && S.pop[r2] > 1024u) trackMask |= 1u << S.slotOf[r2];
   for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
     double x[kUnroll];
 #pragma unroll
@@ -324,23 +334,25 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
         }
         if (pass) {
           const uint64_t k = key_of(x[u]);
-          const uint64_t top = k >> sh0;
+          const uint64_t t = k >> sh0;
           int slot = -1;
-          for (int s = 0; s < nslots; ++s)
-            if (slotTop[s] == top) slot = s;
+#pragma unroll
+          for (int s = 0; s < kGsMaxStat; ++s)
+            if (top[s] == t) slot = s;
           if (slot >= 0) {
             code = slot * 256 + (int)((k >> sh1) & (uint64_t)bmask);
-            // are the slot's keys all equal?  one representative (first come) and the OR of the differences
-            unsigned long long rep = *(volatile unsigned long long *)&tieRep[slot];
-            if (rep == kGsNoKey) {
-              const unsigned long long old = atomicCAS(&tieRep[slot], (unsigned long long)kGsNoKey, (unsigned long long)k);
-              rep = old == kGsNoKey ? k : old;
-            }
-            const uint64_t d = k ^ rep;
-            if (d) {
-              const unsigned int lo = (unsigned int)d, hi = (unsigned int)(d >> 32);
-              if (lo & ~*(volatile unsigned int *)&tieLo[slot]) atomicOr(&tieLo[slot], lo);
-              if (hi & ~*(volatile unsigned int *)&tieHi[slot]) atomicOr(&tieHi[slot], hi);
+            if ((trackMask >> slot) & 1u) {  // one representative (first come) and the OR of the differences
+              unsigned long long rep = *(volatile unsigned long long *)&tieRep[slot];
+              if (rep == kGsNoKey) {
+                const unsigned long long old = atomicCAS(&tieRep[slot], (unsigned long long)kGsNoKey, (unsigned long long)k);
+                rep = old == kGsNoKey ? k : old;
+              }
+              const uint64_t d = k ^ rep;
+              if (d) {
+                const unsigned int lo = (unsigned int)d, hi = (unsigned int)(d >> 32);
+                if (lo & ~*(volatile unsigned int *)&tieLo[slot]) atomicOr(&tieLo[slot], lo);
+                if (hi & ~*(volatile unsigned int *)&tieHi[slot]) atomicOr(&tieHi[slot], hi);
+              }
             }
           }
         }
@@ -357,9 +369,10 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
     unsigned int *g = a.hist + r.row * kGsHistWords;
     for (int i = tid; i < nslots * 256; i += kThreads) g[i] = hist[i];
     if (tid < kGsMaxStat) {
-      GsTie t;
-      t.rep = tieRep[tid];
-      t.diff = ((uint64_t)tieHi[tid] << 32) | tieLo[tid];
+      GsTie t;  // a slot that was not watched reports "not all equal"
+      const bool watched = (trackMask >> tid) & 1u;
+      t.rep = watched ? tieRep[tid] : 0;
+      t.diff = watched ? (((uint64_t)tieHi[tid] << 32) | tieLo[tid]) : ~0ull;
       a.tieAll[((int64_t)a.rank * rows + r.row) * kGsMaxStat + tid] = t;
     }
   }
@@ -406,16 +419,32 @@ __global__ void __launch_bounds__(kThreads, 2) gs_emit_kernel(const GsArgs a) {
   }
   __syncthreads();
   if (nemit == 0) return;
-  const int nr = 2 * a.nq;
-  for (int i = tid; i < r.count; i += kThreads) {
-    const double x = r.p[i];
-    if (!finite_hi(x)) continue;
-    const uint64_t k = key_of(x);
-    for (int s = 0; s < nr; ++s) {
-      if (owner[s] != s) continue;
-      if ((k >> sh[s]) == top[s]) {
-        const unsigned int pos = atomicAdd(&fill[s], 1u);
-        if (pos < (unsigned)kGsEmit) dst[s * kGsEmit + pos] = k;
+  // the emit slots in registers: a key belongs to slot s when (key >> shv[s]) == tp[s]
+  uint64_t tp[kGsMaxStat];
+  int shv[kGsMaxStat];
+#pragma unroll
+  for (int s = 0; s < kGsMaxStat; ++s) {
+    const bool on = s < 2 * a.nq && owner[s] == s;
+    tp[s] = on ? top[s] : kGsNoKey;
+    shv[s] = on ? sh[s] : 0;
+  }
+  for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
+    double x[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = i0 + u * kThreads + tid;
+      x[u] = i < r.count ? r.p[i] : __longlong_as_double(0x7ff8000000000000ll);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!finite_hi(x[u])) continue;
+      const uint64_t k = key_of(x[u]);
+#pragma unroll
+      for (int s = 0; s < kGsMaxStat; ++s) {
+        if ((k >> shv[s]) == tp[s]) {
+          const unsigned int pos = atomicAdd(&fill[s], 1u);
+          if (pos < (unsigned)kGsEmit) dst[s * kGsEmit + pos] = k;
+        }
       }
     }
   }

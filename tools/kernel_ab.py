@@ -37,7 +37,7 @@ def child(args):
     else:  # full output, segmented
         kw = dict(outputs=A.OUT_FULL, out_steps_capacity=64)
     math = {"fast": A.MATH_FAST, "throughput": A.MATH_THROUGHPUT, "validation": A.MATH_VALIDATION}[args.math]
-    ens = api.Ensemble([site], params, None, flags, math=math, device=0, **kw)
+    ens = api.Ensemble([site], params, None, flags, math=math, device=0, block_threads=args.block, **kw)
     T = ens.max_steps
 
     def one():
@@ -62,7 +62,7 @@ def child(args):
     st = ens.status()
     ens.close()
     k = float(np.mean(ms))
-    print(json.dumps({"mode": args.mode, "math": args.math, "members": M, "occ": os.environ.get("SIPNET_GPU_OCC", "auto"),
+    print(json.dumps({"mode": args.mode, "math": args.math, "block": args.block, "members": M, "occ": os.environ.get("SIPNET_GPU_OCC", "auto"),
                       "lib": os.path.basename(os.environ.get("SIPNET_GPU_LIB", "default")), "kernel_ms": round(k, 3),
                       "member_steps_per_s": M * T / (k * 1e-3), "checksum": digest,
                       "replayed": int((st & A.ST_REPLAY).astype(bool).sum())}), flush=True)
@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--occ", default="2,3,4")
     ap.add_argument("--libs", default="")
     ap.add_argument("--mode", default="")
+    ap.add_argument("--block", type=int, default=0, help="block_threads (0 = library default)")
     ap.add_argument("--math", default="fast", help="fast | throughput | validation (comma list in the parent)")
     args = ap.parse_args()
     if args.mode:
@@ -91,7 +92,7 @@ def main():
                     if lib:
                         env["SIPNET_GPU_LIB"] = os.path.abspath(lib)
                     subprocess.call([sys.executable, os.path.abspath(__file__), "--mode", mode, "--members", str(args.members),
-                                     "--years", str(args.years), "--math", math], env=env)
+                                     "--years", str(args.years), "--math", math, "--block", str(args.block)], env=env)
 
 
 if __name__ == "__main__":
