@@ -165,6 +165,12 @@ __device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value
   mb.ringSum = sum;
 }
 
+// products and sums that must not be contracted into an FMA in ANY build (the throughput policy's translation units
+// are compiled with -fmad=true): the soil-water balance, where a half-ulp difference is amplified by cancellation
+__device__ __forceinline__ double nc_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double nc_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double nc_sub(double a, double b) { return __dsub_rn(a, b); }
+
 // ---- small helpers ---------------------------------------------------------------
 __device__ __forceinline__ bool has_biomass(const Member &mb) {  // hasSufficientBiomass, sipnet.c:1530-1536
   const double totWood = mb.wood + mb.delta;
@@ -234,6 +240,12 @@ struct Div {
     if (NM::kFast && invLenPow2 != 0.0) return a * invLenPow2;  // exact: length is a power of two
     return nm.divs(a, len, seedLen);
   }
+  // the soil-water balance's divisions (ThroughNum keeps them correctly rounded)
+  __device__ __forceinline__ double byLenW(double a) const {
+    if (NM::kFast && invLenPow2 != 0.0) return a * invLenPow2;  // exact: length is a power of two
+    return nm.divsw(a, len, seedLen);
+  }
+  __device__ __forceinline__ double byWhcW(double a) const { return nm.divsw(a, SIP_P(soilWHC), SIP_K(kSeedWhc)); }
   __device__ __forceinline__ double byLeafCN(double a) const { return nm.divs(a, SIP_P(leafCN), SIP_K(kSeedLeafCN)); }
   __device__ __forceinline__ double byWoodCN(double a) const { return nm.divs(a, SIP_P(woodCN), SIP_K(kSeedWoodCN)); }
   __device__ __forceinline__ double byFineCN(double a) const {
@@ -600,33 +612,33 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     }
   }
 
-  // calcSoilWaterFluxes, :963-1031
-  const double waterFrac = clip01(dv.byWhc(mb.water));  // getClippedWaterFrac, depeffects.c:11
+  // calcSoilWaterFluxes, :963-1031 (sums written with nc_*: same operations as `a + b * len`, never contracted)
+  const double waterFrac = clip01(dv.byWhcW(mb.water));  // getClippedWaterFrac, depeffects.c:11
   {
-    double netIn = netRain + r.snowMelt;
-    r.fastFlow = netIn * SIP_P(fastFlowFrac);
-    netIn -= r.fastFlow;
-    double left = mb.water + netIn * len - r.transpiration * len;
+    double netIn = nc_add(netRain, r.snowMelt);
+    r.fastFlow = nc_mul(netIn, SIP_P(fastFlowFrac));
+    netIn = nc_sub(netIn, r.fastFlow);
+    double left = nc_sub(nc_add(mb.water, nc_mul(netIn, len)), nc_mul(r.transpiration, len));
     if (mb.snow > 0) {
       r.evaporation = 0;
     } else {
-      const double rd = nm.div(SIP_P(rdConst), c.wspd);
-      const double rsoil = nm.exp(SIP_P(rSoilConst1) - SIP_P(rSoilConst2) * waterFrac);
-      r.evaporation = nm.div(c.evapK, rd + rsoil);
+      const double rd = nm.divw(SIP_P(rdConst), c.wspd);
+      const double rsoil = nm.exp(nc_sub(SIP_P(rSoilConst1), nc_mul(SIP_P(rSoilConst2), waterFrac)));
+      r.evaporation = nm.divw(c.evapK, nc_add(rd, rsoil));
       if (r.evaporation < 0) r.evaporation = 0;
-      if (left - (r.evaporation * len) < kTiny) {
-        r.evaporation = dv.byLen(left - kTiny);
+      if (nc_sub(left, nc_mul(r.evaporation, len)) < kTiny) {
+        r.evaporation = dv.byLenW(nc_sub(left, kTiny));
         left = 0;
       } else {
-        left -= (r.evaporation * len);
+        left = nc_sub(left, nc_mul(r.evaporation, len));
       }
     }
     if (left > whc) {
-      const double excess = left - whc;
+      const double excess = nc_sub(left, whc);
       if (fl.on(F_FLOODING)) {
-        r.drainage = fmin(excess * SIP_P(waterDrainFrac), dv.byLen(excess));
+        r.drainage = fmin(nc_mul(excess, SIP_P(waterDrainFrac)), dv.byLenW(excess));
       } else {
-        r.drainage = dv.byLen(excess);
+        r.drainage = dv.byLenW(excess);
       }
     } else {
       r.drainage = 0;
@@ -881,7 +893,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   }
   mb.coarse += r.eventCoarseRootC * len;
   mb.fine += r.eventFineRootC * len;
-  mb.water += r.eventSoilWater * len;
+  mb.water = nc_add(mb.water, nc_mul(r.eventSoilWater, len));
   if (fl.on(F_NITROGEN)) {
     mb.minN += r.eventMinN * len;
     mb.orgN += r.eventSoilOrgN * len;
@@ -897,7 +909,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     mb.delta += ((r.photosynthesis - ra) - alloc) * len;
     mb.wood += (r.woodCreation - r.woodLitter - r.leafOnCreationFromWood) * len;
     mb.leaf += (r.leafCreation + r.leafOnCreation - r.leafLitter) * len;
-    mb.water += (r.rain + r.snowMelt - r.immedEvap - r.fastFlow - r.evaporation - r.transpiration - r.drainage) * len;
+    mb.water = nc_add(mb.water, nc_mul(r.rain + r.snowMelt - r.immedEvap - r.fastFlow - r.evaporation - r.transpiration - r.drainage, len));
     mb.snow += (r.snowFall - r.snowMelt - r.sublimation) * len;
   }
 

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -120,6 +121,7 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, Ev
                        (long long)siteIndex);
   }
   int64_t e = 0;
+  double prevLen = -1.0, prevDecay = 0.0, prevInv = 0.0;  // step lengths repeat: their functions are reused
   for (int64_t t = 0; t < s.nsteps; ++t) {
     ClimRec &c = recs[(size_t)t];
     c.time = s.time[t];
@@ -140,7 +142,15 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, Ev
                        "site %lld: climate length (%f) on year %d day %d is non-positive", (long long)siteIndex, c.length,
                        c.year, c.day);
     minLen = std::min(minLen, c.length);
-    c.tillDecay = std::exp(-c.length * (1 / 30.0));  // events.c:816, events.h:58
+    if (c.length != prevLen) {
+      prevLen = c.length;
+      prevDecay = std::exp(-c.length * (1 / 30.0));  // events.c:816, events.h:58
+      int ex = 0;
+      const double mant = std::frexp(c.length, &ex);  // power of two <=> mantissa 0.5: then x / length == x * (1 / length)
+      prevInv = (mant == 0.5 && ex > -500 && ex < 500) ? 1.0 / c.length : 0.0;
+    }
+    c.tillDecay = prevDecay;
+    c.invLenPow2 = prevInv;
     {
       const libm::LogHL l = libm::pow_log(c.vpd);  // host evaluation of the same operations
       c.logVpdHi = l.hi;
@@ -151,11 +161,6 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, Ev
     c.precipRate = c.precip / c.length;
     c.sublK = ((1.3 * 1005.) / 66. * (1. / 2835000.) * 1000. * 1000. * (1. / 10000) * 86400.0) * (0.6 - c.vPress);
     c.evapK = ((1.3 * 1005.) / 66. * (1. / 2501000.) * 1000. * 1000. * (1. / 10000) * 86400.0) * c.vpdSoil;
-    {
-      int ex = 0;
-      const double mant = std::frexp(c.length, &ex);  // power of two <=> mantissa 0.5: then x / length == x * (1 / length)
-      c.invLenPow2 = (mant == 0.5 && ex > -500 && ex < 500) ? 1.0 / c.length : 0.0;
-    }
     c.evBegin = (int32_t)e;
     while (e < nev && s.events[e].year <= c.year && s.events[e].day <= c.day) {  // events.c:471
       const sipnet_gpu_event &ev = s.events[e];
@@ -205,6 +210,10 @@ static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, doub
     evOff[(size_t)s + 1] = evOff[(size_t)s] + site_event_count(st, eventsOn);
     obsOff[(size_t)s + 1] = obsOff[(size_t)s] + ((wantObs && st.nee_obs) ? st.nsteps : 0);
   }
+  const bool trace = getenv("SIPNET_GPU_TRACE_INIT") != nullptr;  // phase times of the site upload on stderr
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tTrace0 = now();
+  double tBuild = 0.0;
   ClimRec *dRec = nullptr;
   EventDev *dEv = nullptr;
   double *dObs = nullptr;
@@ -216,7 +225,7 @@ static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, doub
   h->siteAllocs.push_back(dObs);
 
   // batches of whole sites, about kBatchBytes of records each
-  const size_t kBatchBytes = (size_t)256 << 20;
+  const size_t kBatchBytes = (size_t)64 << 20;  // pinning the two staging buffers is part of init: keep them small
   std::vector<int64_t> batchBegin{0};
   {
     size_t acc = 0;
@@ -252,6 +261,7 @@ static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, doub
         cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) != cudaSuccess)
       rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "pinned staging allocation of %zu bytes failed", stageBytes);
   }
+  const double tPinned = now();
   for (size_t b = 0; rc == 0 && b + 1 < batchBegin.size(); ++b) {
     const int64_t s0 = batchBegin[b], s1 = batchBegin[b + 1];
     const int buf = (int)(b % (size_t)nbuf);
@@ -274,9 +284,11 @@ static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, doub
     };
     const unsigned nt = (unsigned)std::min<int64_t>(nthreads, s1 - s0);
     std::vector<std::thread> pool;
+    const double tb0 = now();
     for (unsigned i = 1; i < nt; ++i) pool.emplace_back(work);
     work();
     for (std::thread &t : pool) t.join();
+    tBuild += now() - tb0;
     for (int64_t s = s0; s < s1 && rc == 0; ++s)
       if (siteRc[(size_t)s]) rc = fail(siteRc[(size_t)s], "%s", siteErr[(size_t)s].c_str());
     if (rc) break;
@@ -287,10 +299,16 @@ static int upload_sites(sipnet_gpu_handle *h, const sipnet_gpu_config *cfg, doub
     if (e != cudaSuccess) rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "site upload failed: %s", cudaGetErrorString(e));
   }
   if (rc == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SIPNET_GPU_ERR_NO_DEVICE, "site upload failed");
+  const double tDone = now();
   for (int i = 0; i < 2; ++i) {
     if (copied[i]) cudaEventDestroy(copied[i]);
     if (stage[i]) cudaFreeHost(stage[i]);
   }
+  if (trace)
+    fprintf(stderr, "[sipnet_gpu] sites: %lld, records %.2f GB, %u threads, %zu batches: alloc+pin %.3f s, build %.3f s, "
+                    "build+upload %.3f s, unpin %.3f s\n",
+            (long long)S, (double)recOff[(size_t)S] * sizeof(ClimRec) / 1e9, nthreads, batchBegin.size() - 1, tPinned - tTrace0,
+            tBuild, tDone - tPinned, now() - tDone);
   if (rc) return rc;
   // observations go up straight from the caller's arrays
   int64_t firstLen = cfg->sites[0].nsteps;
