@@ -4,10 +4,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tools/multi_gpu_check.py [--members 8192] [--years 2]
 
-C4-shaped: one site, members sharded over ranks, ensemble mean/variance (ordered all_gather combine) and
-exact quantiles through ONE all-to-all time-transpose + local radix select.
-C5-shaped: NEE log-likelihood per draw, all_gather over NVLink.
-Rank 0 also integrates the whole ensemble alone and compares (moments to 1e-12, quantiles to 4e-16
+C4-shaped: one site, members sharded over ranks.  The product path -- sipnet_gpu_comm_summaries (C ABI, NCCL
+all-reduce of key histograms, no member value moves) -- is cross-checked against an INDEPENDENT route through
+torch.distributed (ordered all_gather combine of the moments; ONE all-to-all time-transpose + the one-GPU row
+select for the quantiles): quantiles must agree bit for bit.
+C5-shaped: NEE log-likelihood per draw, sipnet_gpu_comm_gather_loglik vs torch all_gather.
+Every rank also integrates the whole ensemble alone and compares with numpy (moments to 1e-12, quantiles to 4e-16
 relative -- same order statistics --, likelihoods bit for bit).  Prints one JSON line with timings."""
 import argparse
 import json
@@ -47,7 +49,13 @@ def main():
     qs = [0.05, 0.5, 0.95]
     T = site.nsteps
     ens = api.Ensemble([site], np.ascontiguousarray(P[:, mine]), None, synth.SYNTH_FLAGS,
-                       outputs=A.OUT_MOMENTS | A.OUT_LOGLIK, summary_cols=cols, nee_sigma=0.5, device=local)
+                       outputs=A.OUT_MOMENTS | A.OUT_QUANTILES | A.OUT_LOGLIK, summary_cols=cols, quantiles=qs, nee_sigma=0.5,
+                       device=local)
+    cid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        cid.copy_(torch.frombuffer(bytearray(api.unique_comm_id()), dtype=torch.uint8))
+    dist.broadcast(cid, src=0)
+    ens.join_team(world, rank, bytes(cid.cpu().numpy().tobytes()))
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     ens.run()
@@ -73,7 +81,20 @@ def main():
         quant.append((ta, tb, q))
     torch.cuda.synchronize()
     t_sum = time.perf_counter() - t0
+    # ---- the product path: the C ABI's team (after the reference route, which reads the handle's LOCAL moments)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ens.team_summaries()
+    ens.sync()
+    t_team = time.perf_counter() - t0
+    team_q, team_mean, team_var = ens.quantiles()[0], ens.mean()[0], ens.variance()[0]     # [ncols][nq][T], [ncols][T]
+    team_ll = ens.team_loglik()
     ok = True
+    ok &= bool(np.array_equal(team_ll, ll.cpu().numpy()))
+    ok &= bool(np.allclose(team_mean, mean, rtol=1e-13, atol=1e-300) and np.allclose(team_var, var, rtol=1e-9, atol=1e-24))
+    for i in range(len(cols)):
+        ta, tb, q = quant[i]
+        ok &= bool(np.array_equal(team_q[i][:, ta:tb], q.cpu().numpy(), equal_nan=True))            # bit for bit
     if not args.no_check:
         # every rank checks its share of the quantiles against rank-local numpy on a full single-GPU run
         full = api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL | A.OUT_LOGLIK, nee_sigma=0.5, device=local)
@@ -92,7 +113,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"check": "multi_gpu", "world": world, "members": M, "steps": T, "ok": bool(flag.item()),
-                          "run_s": t_run, "loglik_gather_s": t_ll, "moments_quantiles_s": t_sum,
+                          "run_s": t_run, "loglik_gather_s": t_ll, "all_to_all_route_s": t_sum, "team_summaries_s": t_team,
                           "member_steps_per_s": M * T / t_run}), flush=True)
     ens.close()
     dist.barrier()
