@@ -102,13 +102,15 @@ def test_multi_split_site_equals_one_gpu():
 
 @needs2
 def test_multi_whole_sites_equal_one_gpu():
-    sites, P, ms, flags = synth.config_c3(nsites=7, members_per_site=50, nyears=2)
+    # more sites than GPUs on any box: whole sites per device (fewer sites than devices would split them instead)
+    sites, P, ms, flags = synth.config_c3(nsites=11, members_per_site=40, nyears=2)
     kw = dict(outputs=A.OUT_FULL | A.OUT_MOMENTS | A.OUT_EVENTS, summary_cols=[A.O["nee"]], math=A.MATH_FAST,
               max_event_records=64)
     with api.Ensemble(sites, P, ms, flags, **kw) as ens:
         ens.run()
         ref = dict(out=ens.output(), mean=ens.mean(), var=ens.variance(), status=ens.status(), counts=ens.event_counts())
     with api.MultiEnsemble(sites, P, ms, flags, **kw) as me:
+        assert me.ndevices <= 11
         me.run()
         assert np.array_equal(me.output(), ref["out"], equal_nan=True)
         assert np.array_equal(me.mean(), ref["mean"], equal_nan=True)        # whole sites: the same local kernels
