@@ -293,6 +293,10 @@ enum sipnet_gpu_gather_what {
 #define SIPNET_GPU_ST_NONFINITE 0x20u     /* a pool became NaN/Inf */
 #define SIPNET_GPU_ST_BALANCE 0x80u       /* the mass-balance check found a non-zero deltaC or deltaN on some step (the
                                              reference's warning, balance.c:150-169; debug dump only) */
+/* the reference's informational messages / flux caps of limitations.c, once per run and member: */
+#define SIPNET_GPU_ST_LEAFON_LIMITED 0x100u /* leaf-on growth reduced by available C / N (limitations.c:46-62) */
+#define SIPNET_GPU_ST_N_LIMITED 0x200u      /* plant growth reduced by N limitation (limitations.c:85-114) */
+#define SIPNET_GPU_ST_MINN_LIMITED 0x400u   /* leaching + volatilisation capped by the mineral N pool (:119-130) */
 #define SIPNET_GPU_ST_REPLAY 0x40u        /* the optimistic kernel met an input outside its guards and the member
                                              was re-run by the general kernel (informational; results are exact) */
 

@@ -161,7 +161,10 @@ class Oracle(_Runner):
         done = C.c_int64(0)
         clim = (C.POINTER(C.c_double) * 11)(*[_dp(site.clim[k]) for k in A.CLIM_COLS])
         arr, n = site.event_array()
-        self.lib.sipnet_oracle_run_balance.restype = C.c_int
-        rc = self.lib.sipnet_oracle_run_balance(_ip(fl), _dp(p), C.c_int64(T), _ip(site.year), _ip(site.day), clim,
-                                                C.c_int64(n), C.cast(arr, C.POINTER(A.Event)), _dp(bal), C.byref(done))
+        self.lib.sipnet_oracle_run_diag.restype = C.c_int
+        info = C.c_uint32(0)
+        rc = self.lib.sipnet_oracle_run_diag(_ip(fl), _dp(p), C.c_int64(T), _ip(site.year), _ip(site.day), clim,
+                                             C.c_int64(n), C.cast(arr, C.POINTER(A.Event)), _dp(bal), C.byref(done),
+                                             C.byref(info))
+        self.last_info = int(info.value)         # SIPNET_GPU_ST_*_LIMITED bits of the run
         return rc, int(done.value), bal

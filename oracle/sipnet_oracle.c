@@ -91,6 +91,7 @@ typedef struct {
   int32_t max_recs, nrec;
   int64_t step;
   double balDeltaC, balDeltaN; /* balanceTracker.deltaC / deltaN of the last step, balance.h:46-47 */
+  uint32_t info;               /* SIPNET_GPU_ST_* bits of the reference's informational messages, whole run */
   int exit_code;
 } OrSim;
 
@@ -238,7 +239,7 @@ static void n_fix_and_uptake(OrSim *s) { /* nitrogen.c:156-168 */
 }
 
 /* ---- limitations.c:13-64 ---------------------------------------------------- */
-static void limit_leaf_on(const OrSim *s, double *flux) {
+static void limit_leaf_on(OrSim *s, double *flux) {
   double demandC = *flux * s->c.length;
   if (demandC < OR_TINY) {
     return;
@@ -255,6 +256,7 @@ static void limit_leaf_on(const OrSim *s, double *flux) {
   double lim = or_clip01(fmin(cLim, nLim));
   if (lim < 1) {
     *flux *= lim;
+    s->info |= SIPNET_GPU_ST_LEAFON_LIMITED; /* logInfo("Leaf on creation ... exceeds available ..."), limitations.c:48-61 */
   }
 }
 
@@ -761,6 +763,7 @@ static void step_fluxes(OrSim *s) {
         double red = pool / loss;
         r->nLeaching *= red;
         r->nVolatilization *= red;
+        s->info |= SIPNET_GPU_ST_MINN_LIMITED;
       }
     }
     /* checkNitrogenLimitation, limitations.c:69-114 */
@@ -773,6 +776,7 @@ static void step_fluxes(OrSim *s) {
         double demand = n_demand(s) * len;
         double uptakeFrac = 1 - n_fix_frac(s);
         double red = (avail / uptakeFrac + unclaimed) / demand;
+        s->info |= SIPNET_GPU_ST_N_LIMITED; /* logInfo("N limitation: ..."), limitations.c:98-102 */
         r->woodCreation *= red;
         r->leafCreation *= red;
         r->fineRootCreation *= red;
@@ -1290,9 +1294,18 @@ int sipnet_oracle_run(const int32_t *flags, const double *params, int64_t T, con
 int sipnet_oracle_run_balance(const int32_t *flags, const double *params, int64_t T, const int32_t *year,
                               const int32_t *day, const double *const *clim11, int64_t nev, const sipnet_gpu_event *ev,
                               double *balance, int64_t *steps_done) {
+  return sipnet_oracle_run_diag(flags, params, T, year, day, clim11, nev, ev, balance, steps_done, NULL);
+}
+
+/* The same with the informational status bits of the whole run (SIPNET_GPU_ST_LEAFON_LIMITED, _N_LIMITED,
+ * _MINN_LIMITED: the places where the reference prints a message or caps a flux, limitations.c). */
+int sipnet_oracle_run_diag(const int32_t *flags, const double *params, int64_t T, const int32_t *year,
+                           const int32_t *day, const double *const *clim11, int64_t nev, const sipnet_gpu_event *ev,
+                           double *balance, int64_t *steps_done, uint32_t *info) {
   OrSim *s = (OrSim *)malloc(sizeof(OrSim));
   if (!s) return SIPNET_GPU_ERR_INTERNAL;
   int rc = run_member(s, flags, params, 1, T, year, day, clim11, nev, ev, NULL, NULL, steps_done, NULL, NULL, 0, balance);
+  if (info) *info = s->info;
   free(s);
   return rc;
 }

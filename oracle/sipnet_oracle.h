@@ -53,6 +53,12 @@ int sipnet_oracle_run_balance(const int32_t *flags, const double *params, int64_
                               const double *const *clim11, int64_t nev,
                               const sipnet_gpu_event *ev, double *balance,
                               int64_t *steps_done);
+/* ... plus the informational status bits of the run (limitations.c messages). */
+int sipnet_oracle_run_diag(const int32_t *flags, const double *params, int64_t T,
+                           const int32_t *year, const int32_t *day,
+                           const double *const *clim11, int64_t nev,
+                           const sipnet_gpu_event *ev, double *balance,
+                           int64_t *steps_done, uint32_t *info);
 
 /*
  * Ensemble form used by the CPU baseline: run `nmembers` parameter vectors

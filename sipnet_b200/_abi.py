@@ -137,6 +137,7 @@ MATH_VALIDATION, MATH_FAST, MATH_THROUGHPUT = 0, 1, 2
 ST_BAD_ALLOCATION, ST_RING_OVERFLOW, ST_CLAMPED, ST_DIED, ST_EVREC_OVERFLOW, \
     ST_NONFINITE, ST_REPLAY = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 ST_BALANCE = 0x80
+ST_LEAFON_LIMITED, ST_N_LIMITED, ST_MINN_LIMITED = 0x100, 0x200, 0x400
 NBALANCE = 2
 
 ERR_NO_DEVICE, ERR_BAD_ARGUMENT = 100, 101

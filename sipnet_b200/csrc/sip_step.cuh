@@ -306,8 +306,7 @@ __device__ __forceinline__ double n_fix_and_uptake(const FL &fl, const DV &dv, c
 
 // checkLeafOnLimitation, limitations.c:13-64
 template <class FL, class DV>
-__device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, const Member &mb, double len,
-                                              double &flux) {
+__device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, Member &mb, double len, double &flux) {
   const auto &prm = dv.prm;
   const double demandC = flux * len;
   if (demandC < kTiny) return;
@@ -319,7 +318,10 @@ __device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, const 
     if (demandN > kTiny) nLim = dv.nm.div(mb.storN, demandN);
   }
   const double lim = clip01(fmin(cLim, nLim));
-  if (lim < 1) flux *= lim;
+  if (lim < 1) {
+    flux *= lim;
+    mb.status |= SIPNET_GPU_ST_LEAFON_LIMITED;  // the reference's logInfo, limitations.c:48-61
+  }
 }
 
 // calcRatio, common/util.c:72-75
@@ -838,6 +840,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         const double red = nm.div(pool, loss);
         r.nLeaching *= red;
         r.nVolatilization *= red;
+        mb.status |= SIPNET_GPU_ST_MINN_LIMITED;
       }
     }
     // checkNitrogenLimitation, limitations.c:69-114
@@ -850,6 +853,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         const double demand = n_demand(fl, dv, r) * len;
         const double uptakeFrac = 1 - n_fix_frac(dv, mb);
         const double red = nm.div(nm.div(avail, uptakeFrac) + unclaimed, demand);
+        mb.status |= SIPNET_GPU_ST_N_LIMITED;  // the reference's logInfo, limitations.c:98-102
         r.woodCreation *= red;
         r.leafCreation *= red;
         r.fineRootCreation *= red;

@@ -84,3 +84,28 @@ def test_gpu_balance_ensemble_and_segments(oracle):
         rc, done, bal = oracle.run_balance(synth.SYNTH_FLAGS, P[:, m], site)
         assert np.array_equal(got[:, :, m].T, bal), m
         assert bool(status[m] & A.ST_BALANCE) == bool((bal != 0).any()), m
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_gpu(), reason="needs a CUDA device")
+def test_gpu_informational_bits_equal_oracle(oracle):
+    """SIPNET_GPU_ST_LEAFON_LIMITED / _N_LIMITED / _MINN_LIMITED mark the members for which the reference would print
+    its limitation messages or cap the mineral-N losses (limitations.c:46-62, 85-114, 119-130), in every numerics."""
+    from sipnet_b200 import api
+    site = synth.synth_site(4, 3, "unequal", with_events=True)
+    P = synth.synth_params(64, stream=5)
+    P[A.P["nLeachingFrac"], 4:8] = 50.0                       # losses above the mineral N pool (and N limitation after it)
+    P[A.P["leafGrowth"], 20:24] = 0.0                         # no leaf-on flush: nothing to limit
+    bits = A.ST_LEAFON_LIMITED | A.ST_N_LIMITED | A.ST_MINN_LIMITED
+    want = []
+    for m in range(P.shape[1]):
+        oracle.run_balance(synth.SYNTH_FLAGS, P[:, m], site)
+        want.append(oracle.last_info & bits)
+    want = np.array(want, np.uint32)
+    for b in (A.ST_LEAFON_LIMITED, A.ST_N_LIMITED, A.ST_MINN_LIMITED):
+        assert (want & b).any() and not (want & b).all(), hex(b)
+    for math in (A.MATH_VALIDATION, A.MATH_FAST):
+        with api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_FULL, math=math) as ens:
+            ens.run()
+            got = ens.status() & bits
+        assert np.array_equal(got, want), math
