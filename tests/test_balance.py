@@ -94,7 +94,7 @@ def test_gpu_informational_bits_equal_oracle(oracle):
     from sipnet_b200 import api
     site = synth.synth_site(4, 3, "unequal", with_events=True)
     P = synth.synth_params(64, stream=5)
-    P[A.P["nLeachingFrac"], 4:8] = 50.0                       # losses above the mineral N pool (and N limitation after it)
+    P[A.P["nVolatilizationFrac"], 4:20] = 5.0                 # losses above the mineral N pool, N limitation after it
     P[A.P["leafGrowth"], 20:24] = 0.0                         # no leaf-on flush: nothing to limit
     bits = A.ST_LEAFON_LIMITED | A.ST_N_LIMITED | A.ST_MINN_LIMITED
     want = []
