@@ -244,6 +244,7 @@ __device__ void resolve_level(const GsArgs &a, GsRow &S, const unsigned int *his
 
 
 // ---- level l >= 1: resolve level l-1, then (rows still undecided) histogram the next key bits -------------------
+template <bool HI32>
 __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, const int level) {
   __shared__ unsigned int hist[kGsHistWords];
   __shared__ double red[kThreads];
@@ -307,10 +308,15 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   const int sh0 = shift_of(level - 1), sh1 = shift_of(level), bmask = bins_of(level) - 1;
   const double mu = S.mean;
   double q2 = 0.0;
-  // the slots' resolved prefixes in registers (compared with every element); unused slots never match
+  // the slots' resolved prefixes in registers (compared with every element); unused slots never match.  HI32 (levels
+  // 1 and 2): the resolved bits AND the next 8 all sit in the key's high word -- 32-bit compares and shifts only.
   uint64_t top[kGsMaxStat];
+  unsigned top32[kGsMaxStat];
 #pragma unroll
-  for (int s = 0; s < kGsMaxStat; ++s) top[s] = (pass && s < nslots) ? slotTop[s] : kGsNoKey;
+  for (int s = 0; s < kGsMaxStat; ++s) {
+    top[s] = (pass && s < nslots) ? slotTop[s] : kGsNoKey;
+    top32[s] = (pass && s < nslots) ? (unsigned)slotTop[s] : 0xffffffffu;  // a prefix of <= 19 bits is never all ones
+  }
   // "are the slot's keys all equal?" is only worth asking where a slot is still large after the first refinement:
   // a group of equal values (exact zeros) that holds a wanted order statistic
   unsigned trackMask = 0;
@@ -333,15 +339,28 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
           q2 += d * d;
         }
         if (pass) {
-          const uint64_t k = key_of(x[u]);
-          const uint64_t t = k >> sh0;
           int slot = -1;
+          int bin;
+          if (HI32) {
+            const unsigned hi = (unsigned)__double2hiint(x[u]);
+            const unsigned khi = hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);  // high word of key_of(x)
+            const unsigned t = khi >> (sh0 - 32);
 #pragma unroll
-          for (int s = 0; s < kGsMaxStat; ++s)
-            if (top[s] == t) slot = s;
+            for (int s = 0; s < kGsMaxStat; ++s)
+              if (top32[s] == t) slot = s;
+            bin = (int)((khi >> (sh1 - 32)) & (unsigned)bmask);
+          } else {
+            const uint64_t k = key_of(x[u]);
+            const uint64_t t = k >> sh0;
+#pragma unroll
+            for (int s = 0; s < kGsMaxStat; ++s)
+              if (top[s] == t) slot = s;
+            bin = (int)((k >> sh1) & (uint64_t)bmask);
+          }
           if (slot >= 0) {
-            code = slot * 256 + (int)((k >> sh1) & (uint64_t)bmask);
+            code = slot * 256 + bin;
             if ((trackMask >> slot) & 1u) {  // one representative (first come) and the OR of the differences
+              const uint64_t k = key_of(x[u]);
               unsigned long long rep = *(volatile unsigned long long *)&tieRep[slot];
               if (rep == kGsNoKey) {
                 const unsigned long long old = atomicCAS(&tieRep[slot], (unsigned long long)kGsNoKey, (unsigned long long)k);
@@ -349,15 +368,16 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
               }
               const uint64_t d = k ^ rep;
               if (d) {
-                const unsigned int lo = (unsigned int)d, hi = (unsigned int)(d >> 32);
+                const unsigned int lo = (unsigned int)d, hi2 = (unsigned int)(d >> 32);
                 if (lo & ~*(volatile unsigned int *)&tieLo[slot]) atomicOr(&tieLo[slot], lo);
-                if (hi & ~*(volatile unsigned int *)&tieHi[slot]) atomicOr(&tieHi[slot], hi);
+                if (hi2 & ~*(volatile unsigned int *)&tieHi[slot]) atomicOr(&tieHi[slot], hi2);
               }
             }
           }
         }
       }
-      if (pass) hist_add(hist, code);
+      // (warps in which no lane holds a candidate -- most of them from the second refinement on -- skip the update)
+      if (pass && __any_sync(0xffffffffu, code >= 0)) hist_add(hist, code);
     }
   }
   if (needSS) {
@@ -419,14 +439,19 @@ __global__ void __launch_bounds__(kThreads, 2) gs_emit_kernel(const GsArgs a) {
   }
   __syncthreads();
   if (nemit == 0) return;
-  // the emit slots in registers: a key belongs to slot s when (key >> shv[s]) == tp[s]
+  // the emit slots in registers: a key belongs to slot s when (key >> shv[s]) == tp[s].  When every slot was
+  // resolved within the key's high word (<= 32 bits: the usual case) the test is a 32-bit shift and compare.
   uint64_t tp[kGsMaxStat];
+  unsigned tp32[kGsMaxStat];
   int shv[kGsMaxStat];
+  bool hi32 = true;
 #pragma unroll
   for (int s = 0; s < kGsMaxStat; ++s) {
     const bool on = s < 2 * a.nq && owner[s] == s;
     tp[s] = on ? top[s] : kGsNoKey;
     shv[s] = on ? sh[s] : 0;
+    if (on && sh[s] < 32) hi32 = false;
+    tp32[s] = on ? (unsigned)top[s] : 0xffffffffu;
   }
   for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
     double x[kUnroll];
@@ -438,12 +463,25 @@ __global__ void __launch_bounds__(kThreads, 2) gs_emit_kernel(const GsArgs a) {
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (!finite_hi(x[u])) continue;
-      const uint64_t k = key_of(x[u]);
+      if (hi32) {  // block-uniform
+        const unsigned hi = (unsigned)__double2hiint(x[u]);
+        const unsigned khi = hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);
+        int hit = -1;
 #pragma unroll
-      for (int s = 0; s < kGsMaxStat; ++s) {
-        if ((k >> shv[s]) == tp[s]) {
-          const unsigned int pos = atomicAdd(&fill[s], 1u);
-          if (pos < (unsigned)kGsEmit) dst[s * kGsEmit + pos] = k;
+        for (int s = 0; s < kGsMaxStat; ++s)
+          if (shv[s] != 0 && (khi >> (shv[s] - 32)) == tp32[s]) hit = s;  // emit slots hold disjoint key ranges
+        if (hit >= 0) {
+          const unsigned int pos = atomicAdd(&fill[hit], 1u);
+          if (pos < (unsigned)kGsEmit) dst[hit * kGsEmit + pos] = key_of(x[u]);
+        }
+      } else {
+        const uint64_t k = key_of(x[u]);
+#pragma unroll
+        for (int s = 0; s < kGsMaxStat; ++s) {
+          if ((k >> shv[s]) == tp[s]) {
+            const unsigned int pos = atomicAdd(&fill[s], 1u);
+            if (pos < (unsigned)kGsEmit) dst[s * kGsEmit + pos] = k;
+          }
         }
       }
     }
@@ -526,7 +564,9 @@ cudaError_t launch_pass0(const GsArgs &a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 cudaError_t launch_level(const GsArgs &a, int level, cudaStream_t stream) {
-  gs_level_kernel<<<(unsigned)gs_rows(a), kThreads, 0, stream>>>(a, level);
+  // levels 1 and 2 resolve key bits 11..26: shift_of(level) >= 32
+  if (level <= 2) gs_level_kernel<true><<<(unsigned)gs_rows(a), kThreads, 0, stream>>>(a, level);
+  else gs_level_kernel<false><<<(unsigned)gs_rows(a), kThreads, 0, stream>>>(a, level);
   return cudaGetLastError();
 }
 cudaError_t launch_emit(const GsArgs &a, cudaStream_t stream) {
