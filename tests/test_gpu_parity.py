@@ -402,3 +402,27 @@ def test_random_flag_combinations_are_bit_identical(oracle):
                 continue
             assert rc == 0 and done == site.nsteps, (trial, m)
             assert np.array_equal(out[:, :, m].T, o_out, equal_nan=True), (trial, m, f)
+
+
+def test_full_size_ensemble_is_invariant_under_member_permutation_and_segmentation():
+    """Size-independent properties at BASELINE's per-GPU size (131 072 members; two years keep it quick): a member's
+    results do not depend on which block / lane / work item integrates it, nor on how the run is cut into segments.
+    (a) the ensemble in reversed member order gives the reversed state, bit for bit; (b) duplicated members give
+    duplicated results; (c) three run segments end in the state of one run."""
+    M = 131072
+    site = synth.synth_site(6, 2, "half-daily", with_events=True)
+    P = synth.synth_params(M // 2, stream=77)
+    P = np.concatenate([P, P], axis=1)                                   # every member twice
+    kw = dict(outputs=A.OUT_MOMENTS | A.OUT_LOGLIK, summary_cols=[A.O["nee"]], math=A.MATH_FAST, nee_sigma=0.5)
+    rng = np.random.default_rng(3)
+    site.nee_obs = np.where(rng.uniform(size=site.nsteps) < 0.2, np.nan, rng.normal(0, 1.5, site.nsteps))
+    with api.Ensemble([site], P, None, synth.SYNTH_FLAGS, **kw) as ens:
+        ens.run()
+        st, ll, mean = ens.state(), ens.loglik(), ens.mean()
+    assert np.array_equal(st[:, : M // 2], st[:, M // 2:], equal_nan=True) and np.array_equal(ll[: M // 2], ll[M // 2:])
+    with api.Ensemble([site], np.ascontiguousarray(P[:, ::-1]), None, synth.SYNTH_FLAGS, **kw) as ens:
+        for t0, t1 in ((0, 500), (500, 501), (501, site.nsteps)):
+            ens.run(t0, t1)
+        st2, ll2 = ens.state(), ens.loglik()
+    assert np.array_equal(st2[:, ::-1], st, equal_nan=True) and np.array_equal(ll2[::-1], ll)
+    assert np.isfinite(mean).all()
