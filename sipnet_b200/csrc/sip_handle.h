@@ -53,6 +53,7 @@ struct sipnet_gpu_handle {
   int32_t *recCountBk = nullptr;
   bool summariesValid = false;
   std::vector<sip::SiteDev> hostSites;
+  bool mixedBlocks = false;          // some block holds members of two sites
   sip::StepConsts kc = {};           // launch-lifetime constants of the step (device-evaluated at init)
 };
 

@@ -39,9 +39,17 @@ constexpr int kChunkSteps = 32;  // steps staged per TMA chunk (default): 32 * 1
 
 // Tuning policy of one instantiation: block size, resident blocks per SM asked of the compiler, steps per staged
 // forcing chunk.
-template <int BLOCK, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1), int CHUNK = kChunkSteps>
+// 128-member blocks may hold members of TWO sites (BlockDesc): two forcing streams are staged, each in chunks of half
+// the length, and a lane reads its own site's record.
+// MIX instantiations exist for 128-member blocks only and are launched only when some block of the handle is mixed:
+// the single-site variant keeps its longer chunks and block-uniform forcing reads (1 % faster on the C4 share).
+template <int BLOCK, bool MIX = false, int MIN_BLOCKS = (BLOCK == 128 ? SIP_MIN_BLOCKS_128 : 1),
+          int CHUNK = (MIX ? kChunkSteps / 2 : kChunkSteps)>
 struct Tune {
+  static_assert(!MIX || BLOCK == 128, "mixed blocks are a 128-member feature");
   static constexpr int kBlock = BLOCK, kMinBlocks = MIN_BLOCKS, kChunk = CHUNK;
+  static constexpr bool kMix = MIX;
+  static constexpr int kStreams = kMix ? 2 : 1;
 };
 
 // ---- mbarrier / bulk-copy PTX wrappers (sm_90+; SASS: SYNCS / UBLKCP) ------------
@@ -250,6 +258,10 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   const int tid = threadIdx.x;
   const BlockDesc bd = a.blocks[blk];
   const SiteDev site = a.sites[bd.site];
+  // second site of a mixed block (block-uniform); `second` = this lane belongs to it
+  const bool mixed = TN::kMix && bd.count0 < bd.count;
+  const SiteDev siteB = mixed ? a.sites[bd.site1] : site;
+  const bool second = TN::kMix && tid >= bd.count0;
   const int64_t m = (int64_t)bd.member0 + tid;
   bool active = tid < bd.count;
   if (REPLAY) {
@@ -260,7 +272,12 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   }
 
   const int64_t t0 = itemBegin;
-  const int64_t t1 = itemEnd < site.nsteps ? itemEnd : site.nsteps;
+  const int64_t t1A = itemEnd < site.nsteps ? itemEnd : site.nsteps;
+  const int64_t t1B = itemEnd < siteB.nsteps ? itemEnd : siteB.nsteps;
+  const int64_t t1 = t1A > t1B ? t1A : t1B;          // the block's range
+  const int64_t myT1 = second ? t1B : t1A;           // this lane's site may end earlier
+  const EventDev *myEvents = second ? siteB.events : site.events;
+  const double *myObs = second ? siteB.neeObs : site.neeObs;
 
   // parameter tile: coalesced global reads, column-per-thread shared layout (each thread reads only its column)
   for (int k = 0; k < kNParamDev; ++k) {
@@ -269,12 +286,15 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   }
   const DirectTile prm{tile + tid, BLOCK};
 
-  auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, min(cs + kChunkSteps, t1)) as chunk `serial`
-    const int64_t n = (t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps;
-    const uint32_t bytes = (uint32_t)(n * sizeof(ClimRec));
+  auto issue = [&](int64_t cs, int serial) {  // stage steps [cs, cs + kChunkSteps) of the block's site(s) as chunk `serial`
     const int buf = serial & 1;
-    mbar_expect_tx(&bars[buf], bytes);
-    bulk_g2s(climBuf + buf * kChunkSteps, site.clim + cs, bytes, &bars[buf]);
+    const int64_t nA = t1A - cs < kChunkSteps ? t1A - cs : kChunkSteps;
+    const int64_t nB = mixed ? (t1B - cs < kChunkSteps ? t1B - cs : kChunkSteps) : 0;
+    const uint32_t bytesA = nA > 0 ? (uint32_t)(nA * sizeof(ClimRec)) : 0u;
+    const uint32_t bytesB = nB > 0 ? (uint32_t)(nB * sizeof(ClimRec)) : 0u;
+    mbar_expect_tx(&bars[buf], bytesA + bytesB);
+    if (bytesA) bulk_g2s(climBuf + buf * kChunkSteps, site.clim + cs, bytesA, &bars[buf]);
+    if (bytesB) bulk_g2s(climBuf + (2 + buf) * kChunkSteps, siteB.clim + cs, bytesB, &bars[buf]);
   };
   if (tid == 0 && t1 > t0) issue(t0, sc);
 
@@ -298,7 +318,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
       active = false;
       // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
       const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-      const int64_t o0 = t0 - a.stepBegin, o1 = t1 - a.stepBegin;
+      const int64_t o0 = t0 - a.stepBegin, o1 = myT1 - a.stepBegin;
       if (a.out != nullptr)
         for (int c = 0; c < SIPNET_GPU_NOUT; ++c)
           if (a.colSlot[c] >= 0)
@@ -333,7 +353,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     rec.recs = a.recs != nullptr ? a.recs + m * (int64_t)a.maxRecs : nullptr;
   }
   Emitter<FULL> emit{&a, a.out != nullptr ? a.out + m : nullptr, a.dbg != nullptr ? a.dbg + m : nullptr, 0,
-                     site.neeObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
+                     myObs, 0, 0.0, 0.0, nullptr, a.outSteps * a.ld * (int64_t)sizeof(double)};
   if (active && a.loglik != nullptr) {  // continue the member's running sums (same addition order as one long run)
     emit.ll = carried_load<DYN>(&a.loglik[m]);
     emit.lln = carried_load<DYN>(&a.loglikN[m]);
@@ -342,14 +362,14 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   for (int64_t cs = t0; cs < t1; cs += kChunkSteps, ++sc) {
     if (tid == 0 && cs + kChunkSteps < t1) issue(cs + kChunkSteps, sc + 1);  // that buffer was released by the barrier below
     mbar_wait(&bars[sc & 1], (uint32_t)((sc >> 1) & 1));
-    const ClimRec *cbuf = climBuf + (sc & 1) * kChunkSteps;
-    const int n = (int)((t1 - cs) < kChunkSteps ? (t1 - cs) : kChunkSteps);
+    const ClimRec *cbuf = climBuf + ((second ? 2 : 0) + (sc & 1)) * kChunkSteps;  // this lane's site's records
+    const int n = (int)((myT1 - cs) < kChunkSteps ? (myT1 - cs) : kChunkSteps);   // <= 0 once its site has ended
     if (active) {
       for (int i = 0; i < n; ++i) {
         const int64_t t = cs + i;
         emit.begin(t - a.stepBegin, t);
         rec.step = (int32_t)t;
-        step<FL, DEBUG>(fl, nm, prm, cbuf[i], site.events, mb, ext, rg, rec, emit, kc);
+        step<FL, DEBUG>(fl, nm, prm, cbuf[i], myEvents, mb, ext, rg, rec, emit, kc);
       }
     }
     __syncthreads();  // everyone is done reading this buffer before it is refilled
@@ -357,7 +377,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   if (active) {
     if (NM::kFast && nm.bad) mb.status |= kStNeedsReplay;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
-    if (a.loglik != nullptr && site.neeObs != nullptr) {  // running sums continue across segments in step order
+    if (a.loglik != nullptr && myObs != nullptr) {  // running sums continue across segments in step order
       a.loglik[m] = emit.ll;
       a.loglikN[m] = emit.lln;
     }
@@ -371,15 +391,15 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
 // so the predecessor was claimed earlier by a running CTA that waits for nothing later -- no deadlock.
 template <class TN>
 __host__ __device__ constexpr size_t fixed_smem_bytes() {  // forcing ring + libm tables + mbarriers
-  return 2 * (size_t)TN::kChunk * sizeof(ClimRec) + kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
+  return (size_t)TN::kStreams * 2 * TN::kChunk * sizeof(ClimRec) + kLibmTabWords * sizeof(uint64_t) + 2 * sizeof(uint64_t);
 }
 
 template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool DYN, class TN = Tune<BLOCK>>
 __global__ void __launch_bounds__(BLOCK, TN::kMinBlocks) run_kernel(const __grid_constant__ RunArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [forcing ring 2 x kChunk][libm tables][mbarriers][parameter tile]
-  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw);                     // [2][kChunk]
-  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + 2 * TN::kChunk);   // [kLibmTabWords]
+  ClimRec *climBuf = reinterpret_cast<ClimRec *>(smem_raw);                     // [kStreams][2][kChunk]
+  uint64_t *libmTab = reinterpret_cast<uint64_t *>(climBuf + TN::kStreams * 2 * TN::kChunk);  // [kLibmTabWords]
   uint64_t *bars = libmTab + kLibmTabWords;                                     // [2]
   double *tile = reinterpret_cast<double *>(bars + 2);                          // direct: [kNTileRows][BLOCK]
 
@@ -447,9 +467,9 @@ inline int dynamic_max_waves() {
   return v;
 }
 
-template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL>
+template <class FL, bool DEBUG, class NM, int BLOCK, bool REPLAY, bool FULL, bool MIX = false>
 static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream) {
-  using TN = Tune<BLOCK>;
+  using TN = Tune<BLOCK, MIX>;
   const size_t smem = fixed_smem_bytes<TN>() + sizeof(double) * kNTileRows * BLOCK;
   auto kern = run_kernel<FL, DEBUG, NM, BLOCK, REPLAY, FULL, false, TN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -484,6 +504,11 @@ static cudaError_t launch_one(const RunArgs &a, int nblocks, cudaStream_t stream
 
 template <class FL, int BLOCK, class NM = FastNum>
 static cudaError_t launch_fast(const RunArgs &a, int nblocks, bool full, cudaStream_t stream) {
+  if constexpr (BLOCK == 128) {
+    if (a.mixedBlocks)  // some block holds members of two sites
+      return full ? launch_one<FL, false, NM, BLOCK, false, true, true>(a, nblocks, stream)
+                  : launch_one<FL, false, NM, BLOCK, false, false, true>(a, nblocks, stream);
+  }
   return full ? launch_one<FL, false, NM, BLOCK, false, true>(a, nblocks, stream)
               : launch_one<FL, false, NM, BLOCK, false, false>(a, nblocks, stream);
 }

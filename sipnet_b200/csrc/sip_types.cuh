@@ -130,8 +130,12 @@ struct SiteDev {
   int32_t member0, memberCount;
 };
 
+// One block of consecutive members.  They belong to `site`; with 128-member blocks the tail of a site may share its
+// block with the head of the next site that has members (`site1`): lanes [0, count0) are `site`, lanes
+// [count0, count) are `site1`.  A site of 100 members would otherwise leave 28 of every 128 lanes idle.
 struct BlockDesc {
-  int32_t site, member0, count, pad;
+  int32_t site, member0, count, site1;
+  int32_t count0, pad0, pad1, pad2;
 };
 
 // launch-lifetime constants of the step: log_inline(2.0) and the division seeds (sip_num.cuh FastNum::seed) of the
@@ -183,6 +187,7 @@ struct RunArgs {
   unsigned long long *workCounter;  // next work item
   unsigned int *progress;           // [nblocks] sub-ranges completed per block descriptor
   int32_t nblocks, itemSteps;
+  int32_t mixedBlocks;  // some block descriptor holds members of two sites (the MIX kernel variants)
 };
 
 }  // namespace sip

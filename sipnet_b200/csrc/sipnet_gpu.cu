@@ -510,10 +510,34 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     }
   }
   std::vector<BlockDesc> blocks;
-  for (int64_t s = 0; s < cfg->nsites; ++s) {
-    const SiteDev &sd = h->hostSites[(size_t)s];
-    for (int32_t off = 0; off < sd.memberCount; off += h->blockThreads)
-      blocks.push_back(BlockDesc{(int32_t)s, sd.member0 + off, std::min(h->blockThreads, sd.memberCount - off), 0});
+  {
+    const int32_t B = h->blockThreads;
+    const bool mix = B == 128 && getenv("SIPNET_GPU_NO_MIXED_BLOCKS") == nullptr;  // (A/B switch for measurements)
+    std::vector<int64_t> live;  // sites that have members, in member order
+    for (int64_t s = 0; s < cfg->nsites; ++s)
+      if (h->hostSites[(size_t)s].memberCount > 0) live.push_back(s);
+    int32_t taken = 0;  // members of the current site already placed in the previous (mixed) block
+    for (size_t i = 0; i < live.size(); ++i) {
+      const SiteDev &sd = h->hostSites[(size_t)live[i]];
+      int32_t off = taken;
+      taken = 0;
+      for (; off < sd.memberCount; off += B) {
+        BlockDesc bd{};
+        bd.site = bd.site1 = (int32_t)live[i];
+        bd.member0 = sd.member0 + off;
+        bd.count = bd.count0 = std::min(B, sd.memberCount - off);
+        if (mix && bd.count < B && i + 1 < live.size()) {  // the site's tail shares its block with the next site's head
+          const SiteDev &nx = h->hostSites[(size_t)live[i + 1]];
+          if (nx.member0 == bd.member0 + bd.count) {
+            taken = std::min(B - bd.count, nx.memberCount);
+            bd.site1 = (int32_t)live[i + 1];
+            bd.count += taken;
+            h->mixedBlocks = true;
+          }
+        }
+        blocks.push_back(bd);
+      }
+    }
   }
   h->nblocks = (int)blocks.size();
 
@@ -735,6 +759,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
   a.ringCap = h->ringCap;
   a.flags = h->flags;
   a.kc = h->kc;
+  a.mixedBlocks = h->mixedBlocks ? 1 : 0;
   a.invSigma = 1.0 / h->sigma;
   a.logNorm = -std::log(h->sigma) - 0.5 * std::log(2.0 * M_PI);
   memcpy(a.colSlot, h->colSlot, sizeof a.colSlot);

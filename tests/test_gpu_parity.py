@@ -426,3 +426,46 @@ def test_full_size_ensemble_is_invariant_under_member_permutation_and_segmentati
         st2, ll2 = ens.state(), ens.loglik()
     assert np.array_equal(st2[:, ::-1], st, equal_nan=True) and np.array_equal(ll2[::-1], ll)
     assert np.isfinite(mean).all()
+
+
+@pytest.mark.parametrize("math", [A.MATH_VALIDATION, A.MATH_FAST])
+def test_mixed_site_blocks_are_bit_identical(oracle, math):
+    """128-member blocks share a block between the tail of one site and the head of the next (BlockDesc): sites with
+    different forcing, event schedules, record counts (ragged: the second site of a block may end first or last),
+    member counts that leave tails of every size, a site small enough to be swallowed whole, likelihoods against
+    per-site observations, event records, segments.  Every member against the oracle, and the whole run against
+    32-member blocks (one site per block)."""
+    lens = [2, 1, 2, 1, 2]
+    counts = [100, 37, 5, 150, 28]
+    sites = [synth.synth_site(30 + i, lens[i], ["half-daily", "unequal"][i % 2], with_events=True) for i in range(5)]
+    rng = np.random.default_rng(11)
+    for s_ in sites:
+        s_.nee_obs = np.where(rng.uniform(size=s_.nsteps) < 0.3, np.nan, rng.normal(0, 1.5, s_.nsteps))
+    ms = np.repeat(np.arange(5, dtype=np.int32), counts)
+    P = synth.synth_params(int(ms.size), stream=31)
+    kw = dict(outputs=A.OUT_FULL | A.OUT_LOGLIK | A.OUT_EVENTS, math=math, nee_sigma=0.5, max_event_records=256)
+
+    def run(block, segments):
+        with api.Ensemble(sites, P, ms, synth.SYNTH_FLAGS, block_threads=block, out_steps_capacity=0, **kw) as ens:
+            outs = []
+            T = ens.max_steps
+            cuts = [0, T] if not segments else [0, 300, 301, 1000, T]
+            for a_, b_ in zip(cuts[:-1], cuts[1:]):
+                ens.run(a_, b_)
+                outs.append(ens.output())
+            return dict(out=np.concatenate(outs, axis=1), ll=ens.loglik(), state=ens.state(), status=ens.status(),
+                        counts=ens.event_counts(), recs=ens.event_records())
+
+    wide, narrow, seg = run(128, False), run(32, False), run(128, True)
+    for other in (narrow, seg):
+        assert np.array_equal(wide["out"], other["out"], equal_nan=True)
+        assert np.array_equal(wide["ll"], other["ll"]) and np.array_equal(wide["state"], other["state"], equal_nan=True)
+        assert np.array_equal(wide["counts"], other["counts"]) and np.array_equal(wide["status"], other["status"])
+    for m in list(range(0, ms.size, 7)) + [99, 100, 136, 137, 141, 142, 291, 292, ms.size - 1]:
+        site = sites[ms[m]]
+        rc, done, o_out, _, o_recs = oracle.run(synth.SYNTH_FLAGS, P[:, m], site, want_debug=False, max_event_records=256)
+        assert rc == 0
+        assert np.array_equal(wide["out"][:, :site.nsteps, m].T, o_out, equal_nan=True), m
+        assert np.isnan(wide["out"][:, site.nsteps:, m]).all()
+        assert [(r.step, r.type, r.variant, r.nval, tuple(r.val)) for r in wide["recs"][m]] == \
+               [(r.step, r.type, r.variant, r.nval, tuple(r.val)) for r in o_recs], m

@@ -37,9 +37,9 @@ def test_only_sm_100a_code_is_shipped(res_usage):
 def test_step_kernel_variants_exist_and_fit_two_blocks_per_sm(res_usage):
     _, usage = res_usage
     runs = kernels(usage, "run_kernel")
-    # 3 flag policies x 2 block sizes x {all columns, summary columns} x {static, dynamic}, for the optimistic and the
-    # throughput numerics, + 3 x 2 general
-    assert len(kernels(runs, "FastNum")) == 24 and len(kernels(runs, "ThroughNum")) == 24 and len(kernels(runs, "ExactNum")) == 6
+    # 3 flag policies x {32, 128, 128 with two sites per block} x {all columns, summary columns} x {static, dynamic},
+    # for the optimistic and the throughput numerics, + 3 x 2 general
+    assert len(kernels(runs, "FastNum")) == 36 and len(kernels(runs, "ThroughNum")) == 36 and len(kernels(runs, "ExactNum")) == 6
     for name, u in runs.items():
         assert u["reg"] <= 255
         if "Li128E" in name:
