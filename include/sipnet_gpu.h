@@ -431,7 +431,11 @@ int sipnet_gpu_rows_summary(int device, const double *d_rows, int64_t nrows, int
 
 /* Validation hook: evaluate the device exp (op 0: out = exp(x)) or pow (op 1: out = pow(x, y))
  * on host arrays of n doubles, so the device libm can be compared bit for bit with the
- * reference's host libm (glibc) -- see sipnet_b200/csrc/sip_libm.cuh. */
+ * reference's host libm (glibc) -- see sipnet_b200/csrc/sip_libm.cuh.
+ * ops 2..5 evaluate the optimistic policy of the production kernel (sip_num.cuh FastNum): 2 = exp(x),
+ * 3 = pow(x, y), 4 = pow(x, y) through the cached log of x, 5 = x / y.  An input outside the policy's guards
+ * (the member would be replayed by the general kernel) yields SIPNET_GPU_EVAL_FLAGGED instead of a value. */
+#define SIPNET_GPU_EVAL_FLAGGED 0x7ff8bad0bad0bad0ull
 int sipnet_gpu_eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n);
 
 /* ---- multi-GPU ---------------------------------------------------------------------------------------

@@ -202,16 +202,21 @@ def flags_array(flags: dict) -> np.ndarray:
     return np.array([int(merged[n]) for n in A.FLAG_NAMES], dtype=np.int32)
 
 
+EVAL_FLAGGED = 0x7ff8bad0bad0bad0     # sipnet_gpu.h SIPNET_GPU_EVAL_FLAGGED
+_EVAL_OPS = {"exp": 0, "pow": 1, "fast_exp": 2, "fast_pow": 3, "fast_powc": 4, "fast_div": 5}
+
+
 def device_libm(op: str, x: np.ndarray, y: Optional[np.ndarray] = None, device: int = 0) -> np.ndarray:
-    """Evaluate the DEVICE exp/pow (glibc-exact restatement) on arrays (validation hook)."""
+    """Evaluate the DEVICE exp/pow (glibc-exact restatement) on arrays (validation hook).  The fast_* ops run the
+    production kernel's optimistic policy; inputs outside its guards come back as the bit pattern EVAL_FLAGGED."""
     lib = load_library()
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     yp = None
-    if op == "pow":
+    if op not in ("exp", "fast_exp"):
         y = np.ascontiguousarray(y, dtype=np.float64)
         yp = y.ctypes.data
-    rc = lib.sipnet_gpu_eval_libm(device, 0 if op == "exp" else 1, x.ctypes.data, yp, out.ctypes.data, x.size)
+    rc = lib.sipnet_gpu_eval_libm(device, _EVAL_OPS[op], x.ctypes.data, yp, out.ctypes.data, x.size)
     if rc != 0:
         raise SipnetGpuError(rc, (lib.sipnet_gpu_last_error() or b"").decode())
     return out

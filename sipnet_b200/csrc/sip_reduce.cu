@@ -16,6 +16,7 @@
 #include <cstdint>
 
 #include "sip_libm.cuh"
+#include "sip_num.cuh"
 #include "sip_types.cuh"
 
 namespace sip {
@@ -567,11 +568,33 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
   return e;
 }
 
-// ---- validation hook: device exp / pow on arrays ------------------------------------------
+// ---- validation hook: device exp / pow / division on arrays ---------------------------------
+// ops 0, 1: the general restatement (libm::exp, libm::pow).  ops 2..5: the optimistic policy of the production
+// kernel (FastNum: exp, pow with a varying base, pow with a cached log of the base, a / b); an input outside its
+// guards yields kFlagged instead of a value -- "FastNum never has to be right outside its guards, only to notice".
+constexpr unsigned long long kFlagged = 0x7ff8bad0bad0bad0ull;
 __global__ void eval_libm_kernel(int op, const double *x, const double *y, double *out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = op == 0 ? libm::exp(x[i]) : libm::pow(x[i], y[i]);
+  if (op < 2) {
+    out[i] = op == 0 ? libm::exp(x[i]) : libm::pow(x[i], y[i]);
+    return;
+  }
+  FastNum nm;
+  nm.expTab = libm::d_exp_tab;
+  nm.powlogTab = libm::d_powlog_tab;
+  double v;
+  if (op == 2) {
+    v = nm.exp(x[i]);
+  } else if (op == 3) {
+    v = nm.pow(x[i], y[i]);
+  } else if (op == 4) {
+    const libm::LogHL l = libm::pow_log(x[i]);
+    v = nm.powc(x[i], l.hi, l.lo, y[i]);
+  } else {
+    v = nm.div(x[i], y[i]);
+  }
+  out[i] = nm.bad ? __longlong_as_double((long long)kFlagged) : v;
 }
 
 cudaError_t eval_libm(int device, int op, const double *x, const double *y, double *out, int64_t n) {

@@ -534,9 +534,12 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     double eff[7];
     // the seven layers are independent: each stage is issued for all layers before the next one
 #pragma unroll
-    for (int layer = 0; layer <= 6; ++layer) {
+    for (int layer = 6; layer >= 0; --layer) {
       const double cumLai = lai * ((double)layer / 6);
-      eff[layer] = nm.exp(-1.0 * att * cumLai);
+      // optimistic policy, top of the canopy: cumLai = lai * 0 = +0 and exp(-att * +0) = exp(+-0) = 1 for finite
+      // att and lai -- and layer 6's guard (|att * lai| < 512) has just flagged the member if either is not
+      if (NM::kFast && layer == 0) eff[layer] = 1.0;
+      else eff[layer] = nm.exp(-1.0 * att * cumLai);
     }
 #pragma unroll
     for (int layer = 0; layer <= 6; ++layer) {
