@@ -120,9 +120,9 @@ __global__ void init_state_kernel(const double *params, int64_t ld, int64_t nmem
     } else if (fl.on(F_SOIL_PHENOL)) {
       didGrowth = c.tsoil >= P(SIPNET_P_soilTempLeafOn);
     } else if (P(SIPNET_P_leafOnDay) > 0) {
-      didGrowth = ((double)c.day + c.time / 24.0) >= P(SIPNET_P_leafOnDay);
+      didGrowth = c.dayFrac >= P(SIPNET_P_leafOnDay);
     }
-    if (P(SIPNET_P_leafOffDay) > 0) didFall = (c.day + c.time / 24.0) >= P(SIPNET_P_leafOffDay);
+    if (P(SIPNET_P_leafOffDay) > 0) didFall = c.dayFrac >= P(SIPNET_P_leafOffDay);
     if (didFall && !didGrowth) didGrowth = 1;
   }
   S(SIPNET_S_didLeafGrowth) = didGrowth;

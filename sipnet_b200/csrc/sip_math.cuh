@@ -1,12 +1,8 @@
 // sip_math.cuh -- numeric leaves of the integrator.
 //
-// Two arithmetic builds of the same kernels (selected by -DSIP_FAST_MATH and the
-// matching -fmad switch in the Makefile):
-//   validation (default): -fmad=false, IEEE division; every expression keeps the
-//     reference's shape so the only difference from the reference binary
-//     (gcc -O0, x86-64 SSE2, glibc libm) is the last-ulp behaviour of pow/exp.
-//   fast: -fmad=true, same expressions (contraction allowed) with
-//     transcendental calls restructured (see sip_pow_q10 etc.).
+// Every kernel on the model path is compiled with -fmad=false and keeps the reference's expression shapes; exp and
+// pow are the glibc-exact restatements of sip_libm.cuh.  (The throughput policy's translation units, sip_run_thr_*.cu,
+// are the one exception: -fmad=true, see sip_num.cuh ThroughNum.)
 #pragma once
 #include <cmath>
 
@@ -14,8 +10,14 @@
 
 namespace sip {
 
-__device__ __forceinline__ double clip01(double x) {  // unitClip, reference common/util.h:38
-  return fmin(fmax(x, 0.0), 1.0);
+// fmax(x, 0.0) and fmin(x, 1.0) against a CONSTANT: one compare and one select give exactly what CUDA's fmax / fmin
+// return for every input (x = NaN -> the constant; x = -0 -> +0 for max0, kept for min1), where the two-variable
+// library forms cost eight instructions each on sm_100a (no DMNMX).
+__device__ __forceinline__ double max0(double x) { return x > 0.0 ? x : 0.0; }
+__device__ __forceinline__ double min1(double x) { return x < 1.0 ? x : 1.0; }
+
+__device__ __forceinline__ double clip01(double x) {  // unitClip, reference common/util.h:38: fmin(fmax(x, 0.0), 1.0)
+  return min1(max0(x));
 }
 
 __device__ __forceinline__ double safe_ratio(double num, double den) {  // calcRatio, common/util.c:72-75

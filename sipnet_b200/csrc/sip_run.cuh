@@ -99,7 +99,7 @@ struct Emitter {
   __device__ __forceinline__ void begin(int64_t tl, int64_t ts) {
     tLocal = tl;
     tSite = ts;
-    if (FULL) cur = reinterpret_cast<char *>(outp + tl * a->ld);
+    if (FULL || outp != nullptr) cur = reinterpret_cast<char *>(outp + tl * a->ld);
   }
   // value(col) is the step's column -> value switch (sip_step.cuh)
   template <class F>
@@ -111,10 +111,10 @@ struct Emitter {
         cur += colStride;
       }
     } else if (outp != nullptr) {
-      double *p = outp + tLocal * a->ld;
+      char *p = cur;
       for (int s = 0; s < a->nOutCols; ++s) {
-        __stcs(p, value((int)a->slotCol[s]));
-        p += a->outSteps * a->ld;
+        __stcs(reinterpret_cast<double *>(p), value((int)a->slotCol[s]));
+        p += colStride;
       }
     }
   }

@@ -178,12 +178,16 @@ __device__ __forceinline__ bool has_biomass(const Member &mb) {  // hasSufficien
   return mb.wood > kTiny && totWood > kTiny && totRoot > kTiny;
 }
 
-__device__ __forceinline__ void clamp_stock(double &v, double floorv, uint32_t &status) {
-  // ensureNonNegative, sipnet.c:1346-1356
-  if (v < floorv) {
-    if (fabs(v) > kEps) status |= SIPNET_GPU_ST_CLAMPED;  // the reference's warning (informational)
-    v = 0.;
-  }
+// ensureNonNegative, sipnet.c:1346-1356: a stock below its floor is set to zero; a clamped amount above EPS is what
+// the reference warns about (informational status bit, collected in one predicate and folded into the status once)
+__device__ __forceinline__ void clamp_stock(double &v, bool &clamped) {  // floor 0: v < 0 and |v| > EPS <=> v < -EPS
+  clamped = clamped | (v < -kEps);
+  v = v < 0.0 ? 0.0 : v;
+}
+__device__ __forceinline__ void clamp_stock(double &v, double floorv, bool &clamped) {
+  const bool low = v < floorv;
+  clamped = clamped | (low & (fabs(v) > kEps));
+  v = low ? 0.0 : v;
 }
 
 // record sink for events.out rows (events.c:379-402)
@@ -260,14 +264,14 @@ __device__ __forceinline__ double n_leafon_from_c(const DV &dv, double c) {  // 
   // c is the leaf-on flux: zero on all but one step a year.  fmax(0.0, (+-0)/a - (+-0)/b) is +0 exactly,
   // so the two divisions are skipped (same bits).
   if (c == 0.0) return 0.0;
-  return fmax(0.0, dv.byLeafCN(c) - dv.byWoodCN(c));
+  return max0(dv.byLeafCN(c) - dv.byWoodCN(c));
 }
 template <class FL, class DV>
 __device__ __forceinline__ double n_demand(const FL &fl, const DV &dv, const Rates &r) {  // nitrogen.c:91-106
   if (!fl.on(F_NITROGEN)) return 0.0;
   const double d = dv.byWoodCN(r.woodCreation) + dv.byLeafCN(r.leafCreation) + dv.byFineCN(r.fineRootCreation) +
                    dv.byWoodCN(r.coarseRootCreation);
-  return fmax(0.0, d);
+  return max0(d);
 }
 __device__ __forceinline__ double n_non_uptake(const Rates &r) {  // nitrogen.c:124-126
   return r.nMin - r.nVolatilization - r.nLeaching;
@@ -277,7 +281,7 @@ __device__ __forceinline__ double n_unclaimed_storage(const DV &dv, const Member
                                                       double len) {  // nitrogen.c:129-136
   const double cflux = r.leafOnCreation + r.eventLeafOnCreation;
   const double nflux = n_leafon_from_c(dv, cflux);
-  return fmax(0.0, mb.storN - nflux * len);
+  return max0(mb.storN - nflux * len);
 }
 template <class DV>
 __device__ __forceinline__ double n_fix_frac(const DV &dv, const Member &mb) {  // nitrogen.c:139-153
@@ -297,7 +301,7 @@ __device__ __forceinline__ double n_fix_and_uptake(const FL &fl, const DV &dv, c
                                                    double len) {  // nitrogen.c:156-168
   const double demand = n_demand(fl, dv, r);
   const double storage = dv.byLen(n_unclaimed_storage(dv, mb, r, len));
-  const double rem = fmax(0.0, demand - storage);
+  const double rem = max0(demand - storage);
   const double ff = n_fix_frac(dv, mb);
   r.nFixation = ff * rem;
   r.nUptake = (1 - ff) * rem;
@@ -525,9 +529,9 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // kPsnTRangeSqSlot holds pow((psnTMax - psnTMin) / 2.0, 2), evaluated once per member by the setup kernel
   double dTemp = nm.divs((SIP_P(psnTMax) - c.tair) * (c.tair - SIP_P(psnTMin)), SIP_K(kPsnTRangeSqSlot),
                          SIP_K(kSeedPsnTRangeSq));
-  dTemp = fmax(dTemp, 0.0);
+  dTemp = max0(dTemp);
   double dVpd = 1.0 - SIP_P(dVpdSlope) * vpdPow;
-  dVpd = fmax(dVpd, 0.0);
+  dVpd = max0(dVpd);
   double dLight;
   if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
     const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = SIP_K(kSeedHalfSatPar);
@@ -688,8 +692,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       } else if (fl.on(F_SOIL_PHENOL)) {
         past = c.tsoil >= SIP_P(soilTempLeafOn);
       } else if (SIP_P(leafOnDay) > 0) {
-        const double now = (double)c.day + nm.divs(c.time, 24.0, kc.seed24);
-        past = now >= SIP_P(leafOnDay);
+        past = c.dayFrac >= SIP_P(leafOnDay);  // (double)day + time / 24.0, from the host
       } else {
         past = false;
       }
@@ -704,7 +707,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     }
     if (!mb.didFall) {
       bool past = false;  // pastLeafFall, :733-742
-      if (SIP_P(leafOffDay) > 0) past = (c.day + nm.divs(c.time, 24.0, kc.seed24)) >= SIP_P(leafOffDay);
+      if (SIP_P(leafOffDay) > 0) past = c.dayFrac >= SIP_P(leafOffDay);
       if (past) {
         const double off = dv.byLen(mb.leaf * SIP_P(fracLeafFall));
         r.leafLitter += off;
@@ -982,18 +985,22 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   }
 
   // ensureNonNegativeStocks, sipnet.c:1368-1397
-  clamp_stock(mb.wood, 0, mb.status);
-  clamp_stock(mb.leaf, 0, mb.status);
-  if (fl.on(F_LITTER_POOL)) clamp_stock(mb.litter, 0, mb.status);
-  clamp_stock(mb.soil, 0, mb.status);
-  clamp_stock(mb.coarse, 0, mb.status);
-  clamp_stock(mb.fine, 0, mb.status);
-  clamp_stock(mb.water, 0, mb.status);
-  clamp_stock(mb.snow, kTiny, mb.status);
-  clamp_stock(mb.minN, 0, mb.status);
-  clamp_stock(mb.orgN, 0, mb.status);
-  clamp_stock(mb.litN, 0, mb.status);
-  clamp_stock(mb.storN, 0, mb.status);
+  {
+    bool clamped = false;
+    clamp_stock(mb.wood, clamped);
+    clamp_stock(mb.leaf, clamped);
+    if (fl.on(F_LITTER_POOL)) clamp_stock(mb.litter, clamped);
+    clamp_stock(mb.soil, clamped);
+    clamp_stock(mb.coarse, clamped);
+    clamp_stock(mb.fine, clamped);
+    clamp_stock(mb.water, clamped);
+    clamp_stock(mb.snow, kTiny, clamped);
+    clamp_stock(mb.minN, clamped);
+    clamp_stock(mb.orgN, clamped);
+    clamp_stock(mb.litN, clamped);
+    clamp_stock(mb.storN, clamped);
+    if (clamped) mb.status |= SIPNET_GPU_ST_CLAMPED;
+  }
 
   double balDeltaC = 0.0, balDeltaN = 0.0;
   if (DEBUG) {  // updateBalanceTrackerPostClamp + checkBalance, balance.c:45-148
@@ -1086,6 +1093,9 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // column -> value; with a compile-time column (all 32 kept) the switch folds away, with a run-time column (only
   // the summary columns are kept) it is one uniform jump per stored value instead of 32 tests per step
   const auto column = [&](int col) -> double {
+    // the usual summary columns first: one uniform test each instead of the switch's compare tree
+    if (col == SIPNET_O_nee) return t.nee;
+    if (col == SIPNET_O_gpp) return t.gpp;
     switch (col) {
       case SIPNET_O_plantWoodC: return mb.wood + mb.delta;
       case SIPNET_O_plantLeafC: return mb.leaf;

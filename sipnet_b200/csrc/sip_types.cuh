@@ -96,7 +96,9 @@ enum : uint32_t {
 // One climate step as staged to shared memory: 20 doubles + 4 ints = 176 bytes
 // (multiple of 16 so a chunk is a legal cp.async.bulk size).
 struct alignas(16) ClimRec {
-  double time, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
+  // dayFrac = (double)day + time / 24.0: the step's position in the year as pastLeafGrowth / pastLeafFall form it
+  // (sipnet.c:720,739), evaluated on the host with the same two IEEE operations; `time` itself is not needed here
+  double dayFrac, length, tair, tsoil, par, precip, vpd, vpdSoil, vPress, wspd, gdd;
   // exp(-length * (1 / 30.0)) evaluated on the host with the host libm: the
   // tillage decay factor of updateEventTrackers() (events.c:816) depends on the
   // step length only, so it is hoisted out of the member loop.

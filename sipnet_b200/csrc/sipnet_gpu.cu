@@ -124,7 +124,6 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, Ev
   double prevLen = -1.0, prevDecay = 0.0, prevInv = 0.0;  // step lengths repeat: their functions are reused
   for (int64_t t = 0; t < s.nsteps; ++t) {
     ClimRec &c = recs[(size_t)t];
-    c.time = s.time[t];
     c.length = s.length[t];
     c.tair = s.tair[t];
     c.tsoil = s.tsoil[t];
@@ -137,6 +136,7 @@ static int build_site(const sipnet_gpu_site &s, bool eventsOn, ClimRec *recs, Ev
     c.gdd = s.gdd[t];
     c.year = s.year[t];
     c.day = s.day[t];
+    c.dayFrac = (double)c.day + s.time[t] / 24.0;
     if (!(c.length > 0))  // events.c:460-465
       return site_fail(err, SIPNET_GPU_ERR_BAD_PARAMETER_VALUE,
                        "site %lld: climate length (%f) on year %d day %d is non-positive", (long long)siteIndex, c.length,
