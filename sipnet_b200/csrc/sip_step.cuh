@@ -175,7 +175,7 @@ __device__ __forceinline__ double nc_sub(double a, double b) { return __dsub_rn(
 __device__ __forceinline__ bool has_biomass(const Member &mb) {  // hasSufficientBiomass, sipnet.c:1530-1536
   const double totWood = mb.wood + mb.delta;
   const double totRoot = mb.fine + mb.coarse;
-  return mb.wood > kTiny && totWood > kTiny && totRoot > kTiny;
+  return (mb.wood > kTiny) & (totWood > kTiny) & (totRoot > kTiny);  // three chained compares, no branches
 }
 
 // ensureNonNegative, sipnet.c:1346-1356: a stock below its floor is set to zero; a clamped amount above EPS is what
