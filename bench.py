@@ -262,11 +262,29 @@ class Dist:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
         torch.cuda.set_device(self.local)
+        self.affinity = self._bind_to_gpu_node()
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
+
+    def _bind_to_gpu_node(self) -> str:
+        """Run this rank (and first-touch its pinned buffers) on the CPU cores NVML lists as local to its GPU, so that
+        eight ranks' device<->host copies do not all cross one socket."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return f"nvml: {len(cpus)} cores local to GPU {self.local}"
+        except Exception as exc:  # no NVML / not permitted: stay where the launcher put us
+            return f"unchanged ({type(exc).__name__})"
+        return "unchanged"
 
     def barrier(self):
         if self.dist is not None:
@@ -508,20 +526,25 @@ def section_c5(args, D: Dist, site):
 
 
 def section_c2(args, D: Dist, lib, site):
-    """C2 (BASELINE.json configs[1]): 4096 members, FULL per-step output; device-resident and host-delivered."""
+    """C2 (BASELINE.json configs[1]): 4096 members, FULL per-step output; device-resident and host-delivered.
+    With N ranks every GPU runs its own C2 (replicas: the full-output mode has no exchange step); the host-delivered
+    figure is the aggregate over the ranks, and a plain device->pinned-host copy of the same bytes, issued by all
+    ranks at once, is timed beside it as the box's ceiling for this mode."""
     from sipnet_b200 import _abi as A, api, synth
+    torch = D.torch
     M, T = 4096, site.nsteps
-    params = synth.synth_params(M, stream=0)
+    params = synth.synth_params(M, stream=D.rank)
     ens = api.Ensemble([site], params, None, dict(synth.SYNTH_FLAGS), outputs=A.OUT_FULL, math=A.MATH_FAST, device=D.local)
     for _ in range(2):
         ens.reset()
         ens.run(0, T)
     ens.sync()
+    D.barrier()
     ens.timer_start()
     for _ in range(5):
         ens.reset()
         ens.run(0, T)
-    dev_ms = ens.timer_stop_ms() / 5
+    dev_ms = D.max(ens.timer_stop_ms() / 5)
     kern_ms = ens.last_run_ms()
     out_bytes = A.NOUT * T * M * 8
     par_bytes = A.NPARAMS * M * 8
@@ -529,18 +552,39 @@ def section_c2(args, D: Dist, lib, site):
     C.memmove(hpar, params.ctypes.data, par_bytes)
     ens.set_params(hpar, M)
     ens.run_to_host(hout, 0, T, nbytes=out_bytes)
+    D.barrier()
     ens.timer_start()
     for _ in range(3):
         ens.set_params(hpar, M)
         ens.run_to_host(hout, 0, T, nbytes=out_bytes)
-    e2e_ms = ens.timer_stop_ms() / 3
+    e2e_ms = D.max(ens.timer_stop_ms() / 3)
+    # the ceiling: one plain copy of the same bytes, device -> the same pinned buffer, all ranks at once
+    src = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+    dst = torch.frombuffer((C.c_ubyte * out_bytes).from_address(hout), dtype=torch.uint8)
+    dst.copy_(src)
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src)
+    e1.record()
+    torch.cuda.synchronize()
+    probe_ms = D.max(e0.elapsed_time(e1) / 3)
+    del src, dst
     lib.sipnet_gpu_host_free(hout)
     lib.sipnet_gpu_host_free(hpar)
     ens.close()
-    return {"workload": "C2: 1 site x 4096 members x 10 yr half-daily, full per-step output (32 doubles per member-step)",
-            "value": M * T / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms, "kernel_ms": kern_ms,
-            "e2e": {"value": M * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": par_bytes, "d2h_bytes_per_step": out_bytes},
+    W = D.world
+    return {"workload": "C2: 1 site x 4096 members x 10 yr half-daily, full per-step output (32 doubles per member-step)"
+                        + (f", one replica per GPU x {W}" if W > 1 else ""),
+            "value": W * M * T / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms, "kernel_ms": kern_ms,
+            "e2e": {"value": W * M * T / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": par_bytes, "d2h_bytes_per_step": out_bytes,
+                    "d2h_gb_s_all_ranks": W * out_bytes / (e2e_ms * 1e-3) / 1e9},
+            "d2h_probe": {"gb_s_all_ranks": W * out_bytes / (probe_ms * 1e-3) / 1e9, "ms": probe_ms,
+                          "what": "plain device -> pinned host copy of the same bytes, all ranks at once (the box's "
+                                  "ceiling for host-delivered full output)"},
+            "cpu_affinity": D.affinity,
             "note": "4096 members = 128 warps on 592 warp schedulers: latency-bound by construction (round-1 headline)"}
 
 
@@ -556,7 +600,7 @@ def run_ours(args):
     r = section_c4(args, D, lib, site, fp64_peak_tflops)
     thr = None if args.no_extras else section_throughput_policy(args, D, site)
     c5 = None if args.no_extras else section_c5(args, D, site)
-    c2 = section_c2(args, D, lib, site) if (D.world == 1 and not args.no_extras) else None
+    c2 = None if args.no_extras else section_c2(args, D, lib, site)
 
     if D.rank == 0:
         M, T, world = r["M"], r["T"], D.world

@@ -280,8 +280,20 @@ enum sipnet_gpu_gather_what {
   SIPNET_GPU_GATHER_LOGLIK_N = 11, /* double [M]: number of observations that entered the likelihood */
   SIPNET_GPU_GATHER_RING_VALUES = 12,  /* double [ring_slots][M]: MeanTracker.values, slot-major (runmean.h) */
   SIPNET_GPU_GATHER_RING_WEIGHTS = 13, /* double [ring_slots][M]: MeanTracker.weights */
-  SIPNET_GPU_GATHER_BALANCE = 14       /* double [SIPNET_GPU_NBALANCE][n][M]: deltaC, deltaN of the mass-balance check
+  SIPNET_GPU_GATHER_BALANCE = 14,      /* double [SIPNET_GPU_NBALANCE][n][M]: deltaC, deltaN of the mass-balance check
                                           (needs SIPNET_GPU_OUT_DEBUG) */
+  SIPNET_GPU_GATHER_COUNTERS = 15      /* uint32 [SIPNET_GPU_NCOUNTERS][M]: how often, since init / reset, the reference
+                                          would have printed each of its informational messages for the member
+                                          (SIPNET_GPU_CNT_* order; needs SIPNET_GPU_OUT_DEBUG) */
+};
+
+/* rows of SIPNET_GPU_GATHER_COUNTERS: the status bits say WHETHER, these say HOW OFTEN (validation dump only) */
+enum sipnet_gpu_counter {
+  SIPNET_GPU_CNT_LEAFON_LIMITED = 0, /* logInfo of checkLeafOnLimitation, limitations.c:48-61 (once per limited step) */
+  SIPNET_GPU_CNT_N_LIMITED,          /* logInfo of checkNitrogenLimitation, limitations.c:98-102 */
+  SIPNET_GPU_CNT_MINN_LIMITED,       /* mineral-N loss cap applied, limitations.c:119-130 (silent in the reference) */
+  SIPNET_GPU_CNT_CLAMPED,            /* logWarning of ensureNonNegative, sipnet.c:1346-1356 (once per clamped stock) */
+  SIPNET_GPU_NCOUNTERS
 };
 
 /* per-member status bits (instead of the reference's exit()) */

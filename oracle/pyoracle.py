@@ -167,4 +167,7 @@ class Oracle(_Runner):
                                              C.c_int64(n), C.cast(arr, C.POINTER(A.Event)), _dp(bal), C.byref(done),
                                              C.byref(info))
         self.last_info = int(info.value)         # SIPNET_GPU_ST_*_LIMITED bits of the run
+        cnt = (C.c_uint32 * A.NCOUNTERS)()
+        self.lib.sipnet_oracle_last_counts(cnt)
+        self.last_counts = np.array(list(cnt), np.uint32)   # how often each message occurred (CNT_* order)
         return rc, int(done.value), bal

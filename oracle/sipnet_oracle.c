@@ -92,6 +92,7 @@ typedef struct {
   int64_t step;
   double balDeltaC, balDeltaN; /* balanceTracker.deltaC / deltaN of the last step, balance.h:46-47 */
   uint32_t info;               /* SIPNET_GPU_ST_* bits of the reference's informational messages, whole run */
+  uint32_t counts[SIPNET_GPU_NCOUNTERS]; /* how often each of them occurred (SIPNET_GPU_CNT_*) */
   int exit_code;
 } OrSim;
 
@@ -256,6 +257,7 @@ static void limit_leaf_on(OrSim *s, double *flux) {
   double lim = or_clip01(fmin(cLim, nLim));
   if (lim < 1) {
     *flux *= lim;
+    s->counts[SIPNET_GPU_CNT_LEAFON_LIMITED]++;
     s->info |= SIPNET_GPU_ST_LEAFON_LIMITED; /* logInfo("Leaf on creation ... exceeds available ..."), limitations.c:48-61 */
   }
 }
@@ -763,6 +765,7 @@ static void step_fluxes(OrSim *s) {
         double red = pool / loss;
         r->nLeaching *= red;
         r->nVolatilization *= red;
+        s->counts[SIPNET_GPU_CNT_MINN_LIMITED]++;
         s->info |= SIPNET_GPU_ST_MINN_LIMITED;
       }
     }
@@ -776,6 +779,7 @@ static void step_fluxes(OrSim *s) {
         double demand = n_demand(s) * len;
         double uptakeFrac = 1 - n_fix_frac(s);
         double red = (avail / uptakeFrac + unclaimed) / demand;
+        s->counts[SIPNET_GPU_CNT_N_LIMITED]++;
         s->info |= SIPNET_GPU_ST_N_LIMITED; /* logInfo("N limitation: ..."), limitations.c:98-102 */
         r->woodCreation *= red;
         r->leafCreation *= red;
@@ -804,8 +808,9 @@ static int enough_biomass(const OrSim *s) {
   return s->e.plantWoodC > OR_TINY && wood > OR_TINY && root > OR_TINY;
 }
 
-static void clamp_stock(double *v, double floor_) { /* ensureNonNegative, sipnet.c:1346-1356 */
+static void clamp_stock(OrSim *s, double *v, double floor_) { /* ensureNonNegative, sipnet.c:1346-1356 */
   if (*v < floor_) {
+    if (fabs(*v) > 1e-8) s->counts[SIPNET_GPU_CNT_CLAMPED]++; /* the logWarning (EPS, balance.h:6) */
     *v = 0.;
   }
 }
@@ -940,20 +945,20 @@ static void step_pools(OrSim *s) {
   }
 
   /* ensureNonNegativeStocks, sipnet.c:1368-1397 */
-  clamp_stock(&e->plantWoodC, 0);
-  clamp_stock(&e->plantLeafC, 0);
+  clamp_stock(s, &e->plantWoodC, 0);
+  clamp_stock(s, &e->plantLeafC, 0);
   if (s->f.litterPool) {
-    clamp_stock(&e->litterC, 0);
+    clamp_stock(s, &e->litterC, 0);
   }
-  clamp_stock(&e->soilC, 0);
-  clamp_stock(&e->coarseRootC, 0);
-  clamp_stock(&e->fineRootC, 0);
-  clamp_stock(&e->soilWater, 0);
-  clamp_stock(&e->snow, OR_TINY);
-  clamp_stock(&e->minN, 0);
-  clamp_stock(&e->soilOrgN, 0);
-  clamp_stock(&e->litterN, 0);
-  clamp_stock(&e->plantStorageN, 0);
+  clamp_stock(s, &e->soilC, 0);
+  clamp_stock(s, &e->coarseRootC, 0);
+  clamp_stock(s, &e->fineRootC, 0);
+  clamp_stock(s, &e->soilWater, 0);
+  clamp_stock(s, &e->snow, OR_TINY);
+  clamp_stock(s, &e->minN, 0);
+  clamp_stock(s, &e->soilOrgN, 0);
+  clamp_stock(s, &e->litterN, 0);
+  clamp_stock(s, &e->plantStorageN, 0);
 
   /* updateBalanceTrackerPostClamp, balance.c:45-104 */
   mass_totals(s, &finalC, &finalN);
@@ -1297,6 +1302,10 @@ int sipnet_oracle_run_balance(const int32_t *flags, const double *params, int64_
   return sipnet_oracle_run_diag(flags, params, T, year, day, clim11, nev, ev, balance, steps_done, NULL);
 }
 
+static __thread uint32_t g_last_counts[SIPNET_GPU_NCOUNTERS];
+/* occurrence counts of the last sipnet_oracle_run_diag / _run_balance call on this thread (SIPNET_GPU_CNT_* order) */
+void sipnet_oracle_last_counts(uint32_t *out) { memcpy(out, g_last_counts, sizeof(g_last_counts)); }
+
 /* The same with the informational status bits of the whole run (SIPNET_GPU_ST_LEAFON_LIMITED, _N_LIMITED,
  * _MINN_LIMITED: the places where the reference prints a message or caps a flux, limitations.c). */
 int sipnet_oracle_run_diag(const int32_t *flags, const double *params, int64_t T, const int32_t *year,
@@ -1306,6 +1315,7 @@ int sipnet_oracle_run_diag(const int32_t *flags, const double *params, int64_t T
   if (!s) return SIPNET_GPU_ERR_INTERNAL;
   int rc = run_member(s, flags, params, 1, T, year, day, clim11, nev, ev, NULL, NULL, steps_done, NULL, NULL, 0, balance);
   if (info) *info = s->info;
+  memcpy(g_last_counts, s->counts, sizeof(g_last_counts));
   free(s);
   return rc;
 }

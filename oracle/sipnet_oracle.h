@@ -60,6 +60,9 @@ int sipnet_oracle_run_diag(const int32_t *flags, const double *params, int64_t T
                            const sipnet_gpu_event *ev, double *balance,
                            int64_t *steps_done, uint32_t *info);
 
+/* occurrence counts (SIPNET_GPU_CNT_* order) of the last _run_diag / _run_balance call on this thread */
+void sipnet_oracle_last_counts(uint32_t *out);
+
 /*
  * Ensemble form used by the CPU baseline: run `nmembers` parameter vectors
  * (SoA [80][ld]) on one site with `nthreads` POSIX threads; only the 32

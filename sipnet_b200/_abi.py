@@ -132,13 +132,14 @@ MATH_VALIDATION, MATH_FAST, MATH_THROUGHPUT = 0, 1, 2
 
 (GATHER_FULL, GATHER_DEBUG, GATHER_LOGLIK, GATHER_STATUS, GATHER_STATE,
  GATHER_MEAN, GATHER_VARIANCE, GATHER_QUANTILES, GATHER_EVENT_COUNTS,
- GATHER_EVENT_RECORDS, GATHER_LOGLIK_N, GATHER_RING_VALUES, GATHER_RING_WEIGHTS, GATHER_BALANCE) = range(1, 15)
+ GATHER_EVENT_RECORDS, GATHER_LOGLIK_N, GATHER_RING_VALUES, GATHER_RING_WEIGHTS, GATHER_BALANCE, GATHER_COUNTERS) = range(1, 16)
 
 ST_BAD_ALLOCATION, ST_RING_OVERFLOW, ST_CLAMPED, ST_DIED, ST_EVREC_OVERFLOW, \
     ST_NONFINITE, ST_REPLAY = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 ST_BALANCE = 0x80
 ST_LEAFON_LIMITED, ST_N_LIMITED, ST_MINN_LIMITED = 0x100, 0x200, 0x400
 NBALANCE = 2
+(CNT_LEAFON_LIMITED, CNT_N_LIMITED, CNT_MINN_LIMITED, CNT_CLAMPED, NCOUNTERS) = range(5)   # sipnet_gpu_counter
 
 ERR_NO_DEVICE, ERR_BAD_ARGUMENT = 100, 101
 EVREC_NVAL = 10

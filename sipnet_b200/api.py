@@ -349,6 +349,11 @@ class Ensemble:
         """[2][n][M]: deltaC, deltaN of the reference's mass-balance check (balance.c:129-148); needs OUT_DEBUG."""
         return self._gather(A.GATHER_BALANCE, np.float64, (A.NBALANCE, self.nrun, self.nmembers))
 
+    def counters(self) -> np.ndarray:
+        """[NCOUNTERS][members] uint32: how often the reference would have printed each informational message
+        (CNT_* order) since init / reset; validation dump (OUT_DEBUG) only."""
+        return self._gather(A.GATHER_COUNTERS, np.uint32, (A.NCOUNTERS, self.nmembers))
+
     def loglik(self) -> np.ndarray:
         return self._gather(A.GATHER_LOGLIK, np.float64, (self.nmembers,))
 

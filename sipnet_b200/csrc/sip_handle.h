@@ -37,6 +37,7 @@ struct sipnet_gpu_handle {
   // device memory
   double *params = nullptr, *state = nullptr, *ringV = nullptr, *ringW = nullptr;
   uint32_t *status = nullptr;
+  uint32_t *counters = nullptr;  // [SIPNET_GPU_NCOUNTERS][ld], with the debug dump only
   int32_t *memberSite = nullptr;
   sip::BlockDesc *blocks = nullptr;
   sip::SiteDev *sites = nullptr;

@@ -314,6 +314,8 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     }
     load_member<DYN>(a, REPLAY ? a.stateBackup : a.state, REPLAY ? a.statusBackup : a.status, m, mb, ext, DEBUG);
     if (REPLAY) mb.status = (mb.status & ~kStNeedsReplay) | SIPNET_GPU_ST_REPLAY;  // sticky, informational
+    if (DEBUG && a.counters != nullptr)
+      for (int k = 0; k < SIPNET_GPU_NCOUNTERS; ++k) ext.cnt[k] = carried_load<DYN>(&a.counters[(int64_t)k * a.ld + m]);
     if (mb.status & SIPNET_GPU_ST_BAD_ALLOCATION) {  // reference would have exited (sipnet.c:1117-1122)
       active = false;
       // the member is not integrated: its outputs of this range are NaN (summaries skip non-finite members)
@@ -377,6 +379,8 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
   if (active) {
     if (NM::kFast && nm.bad) mb.status |= kStNeedsReplay;  // outside the optimistic guards: general kernel re-runs it
     store_member(a, m, mb, ext, DEBUG);
+    if (DEBUG && a.counters != nullptr)
+      for (int k = 0; k < SIPNET_GPU_NCOUNTERS; ++k) a.counters[(int64_t)k * a.ld + m] = ext.cnt[k];
     if (a.loglik != nullptr && myObs != nullptr) {  // running sums continue across segments in step order
       a.loglik[m] = emit.ll;
       a.loglikN[m] = emit.lln;

@@ -92,6 +92,7 @@ struct Member {
 struct MemberExt {
   double yGpp, yRtot, yRa, yRh, yNpp, yNee, yLitter, tGpp, tRtot, tRa, tRh, tNpp;
   double harvRemoved, harvTransferred;  // eventTrackers of the last step (checkpoint payload only)
+  uint32_t cnt[SIPNET_GPU_NCOUNTERS];   // occurrences of the reference's informational messages (SIPNET_GPU_CNT_*)
 };
 
 // ---- mean-NPP ring in HBM: slot s of member m at v[s * ld + m] -----------------
@@ -310,7 +311,8 @@ __device__ __forceinline__ double n_fix_and_uptake(const FL &fl, const DV &dv, c
 
 // checkLeafOnLimitation, limitations.c:13-64
 template <class FL, class DV>
-__device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, Member &mb, double len, double &flux) {
+__device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, Member &mb, double len, double &flux,
+                                              uint32_t *count) {  // count: the validation dump's message counter, or null
   const auto &prm = dv.prm;
   const double demandC = flux * len;
   if (demandC < kTiny) return;
@@ -325,6 +327,7 @@ __device__ __forceinline__ void limit_leaf_on(const FL &fl, const DV &dv, Member
   if (lim < 1) {
     flux *= lim;
     mb.status |= SIPNET_GPU_ST_LEAFON_LIMITED;  // the reference's logInfo, limitations.c:48-61
+    if (count != nullptr) ++*count;
   }
 }
 
@@ -483,7 +486,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       } break;
       case SIPNET_EV_LEAFON: {  // :686-705
         double flux = dv.byLen(SIP_P(leafGrowth));
-        limit_leaf_on(fl, dv, mb, len, flux);
+        limit_leaf_on(fl, dv, mb, len, flux, DEBUG ? &ext.cnt[SIPNET_GPU_CNT_LEAFON_LIMITED] : nullptr);
         r.eventLeafOnCreation += flux;
         const double src = mb.wood + mb.coarse;
         if (src > kTiny) r.eventLeafOnCreationFromWood += nm.div(flux * mb.wood, src);
@@ -698,7 +701,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       }
       if (past) {
         double on = dv.byLen(SIP_P(leafGrowth));
-        limit_leaf_on(fl, dv, mb, len, on);
+        limit_leaf_on(fl, dv, mb, len, on, DEBUG ? &ext.cnt[SIPNET_GPU_CNT_LEAFON_LIMITED] : nullptr);
         r.leafOnCreation += on;
         const double src = mb.wood + mb.coarse;
         if (src > kTiny) r.leafOnCreationFromWood += nm.div(on * mb.wood, src);
@@ -847,6 +850,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         r.nLeaching *= red;
         r.nVolatilization *= red;
         mb.status |= SIPNET_GPU_ST_MINN_LIMITED;
+        if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_MINN_LIMITED];
       }
     }
     // checkNitrogenLimitation, limitations.c:69-114
@@ -860,6 +864,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         const double uptakeFrac = 1 - n_fix_frac(dv, mb);
         const double red = nm.div(nm.div(avail, uptakeFrac) + unclaimed, demand);
         mb.status |= SIPNET_GPU_ST_N_LIMITED;  // the reference's logInfo, limitations.c:98-102
+        if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_N_LIMITED];
         r.woodCreation *= red;
         r.leafCreation *= red;
         r.fineRootCreation *= red;
@@ -987,18 +992,25 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // ensureNonNegativeStocks, sipnet.c:1368-1397
   {
     bool clamped = false;
-    clamp_stock(mb.wood, clamped);
-    clamp_stock(mb.leaf, clamped);
-    if (fl.on(F_LITTER_POOL)) clamp_stock(mb.litter, clamped);
-    clamp_stock(mb.soil, clamped);
-    clamp_stock(mb.coarse, clamped);
-    clamp_stock(mb.fine, clamped);
-    clamp_stock(mb.water, clamped);
-    clamp_stock(mb.snow, kTiny, clamped);
-    clamp_stock(mb.minN, clamped);
-    clamp_stock(mb.orgN, clamped);
-    clamp_stock(mb.litN, clamped);
-    clamp_stock(mb.storN, clamped);
+    const auto clamp = [&](double &v, double floorv) {
+      bool one = false;
+      if (floorv == 0.0) clamp_stock(v, one);
+      else clamp_stock(v, floorv, one);
+      clamped = clamped | one;
+      if (DEBUG) ext.cnt[SIPNET_GPU_CNT_CLAMPED] += one ? 1u : 0u;  // one warning per clamped stock
+    };
+    clamp(mb.wood, 0);
+    clamp(mb.leaf, 0);
+    if (fl.on(F_LITTER_POOL)) clamp(mb.litter, 0);
+    clamp(mb.soil, 0);
+    clamp(mb.coarse, 0);
+    clamp(mb.fine, 0);
+    clamp(mb.water, 0);
+    clamp(mb.snow, kTiny);
+    clamp(mb.minN, 0);
+    clamp(mb.orgN, 0);
+    clamp(mb.litN, 0);
+    clamp(mb.storN, 0);
     if (clamped) mb.status |= SIPNET_GPU_ST_CLAMPED;
   }
 

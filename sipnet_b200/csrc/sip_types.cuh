@@ -157,6 +157,7 @@ struct RunArgs {
   double *ringV;
   double *ringW;
   uint32_t *status;
+  uint32_t *counters;  // [SIPNET_GPU_NCOUNTERS][ld] or null (DEBUG instantiation only)
   // segment-start copies used when a member is replayed by the general kernel
   const double *stateBackup;
   const double *ringVBackup;

@@ -341,7 +341,7 @@ static void free_handle(sipnet_gpu_handle *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void *ptrs[] = {h->params, h->state, h->ringV, h->ringW, h->status, h->memberSite, h->blocks, h->sites, h->out,
-                  h->dbg,    h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant,
+                  h->dbg,    h->counters, h->loglik, h->loglikN, h->recs, h->recCount, h->mean, h->var, h->quant,
                   h->stateBk, h->ringVBk, h->ringWBk, h->loglikBk, h->loglikNBk, h->statusBk,
                   h->recCountBk, h->sched};
   for (void *p : ptrs)
@@ -365,6 +365,7 @@ static int run_init_state(sipnet_gpu_handle *h) {
   // rings start zeroed so that never-written slots read the same after a reset as after init
   CUDA_OK(cudaMemsetAsync(h->ringV, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
   CUDA_OK(cudaMemsetAsync(h->ringW, 0, (size_t)h->ringCap * h->ld * sizeof(double), h->stream));
+  if (h->counters) CUDA_OK(cudaMemsetAsync(h->counters, 0, (size_t)SIPNET_GPU_NCOUNTERS * h->ld * sizeof(uint32_t), h->stream));
   cudaError_t e = k1::launch_init_state(h->params, h->ld, h->nmembers, h->memberSite, h->sites, h->flags, h->state,
                                         h->ringV, h->ringW, h->status, h->loglik, h->loglikN, h->recCount, h->stream);
   h->launches++;
@@ -574,6 +575,7 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
   }
   if (h->ncols > 0) INIT_CUDA(dalloc(&h->out, (size_t)h->ncols * h->outCap * h->ld));
   if (cfg->outputs & SIPNET_GPU_OUT_DEBUG) INIT_CUDA(dalloc(&h->dbg, (size_t)(SIPNET_GPU_NDEBUG + SIPNET_GPU_NBALANCE) * h->outCap * h->ld));
+  if (cfg->outputs & SIPNET_GPU_OUT_DEBUG) INIT_CUDA(dalloc(&h->counters, (size_t)SIPNET_GPU_NCOUNTERS * h->ld));
   if (cfg->outputs & SIPNET_GPU_OUT_LOGLIK) {
     INIT_CUDA(dalloc(&h->loglik, (size_t)h->ld));
     INIT_CUDA(dalloc(&h->loglikN, (size_t)h->ld));
@@ -744,6 +746,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
   a.ringV = h->ringV;
   a.ringW = h->ringW;
   a.status = h->status;
+  a.counters = h->counters;
   a.blocks = h->blocks;
   a.sites = h->sites;
   a.stepBegin = step_begin;
@@ -911,6 +914,7 @@ extern "C" size_t sipnet_gpu_gather_bytes(const sipnet_gpu_handle *h, int what) 
     case SIPNET_GPU_GATHER_LOGLIK:
     case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglik ? M * 8 : 0;
     case SIPNET_GPU_GATHER_STATUS: return M * 4;
+    case SIPNET_GPU_GATHER_COUNTERS: return h->counters ? (size_t)SIPNET_GPU_NCOUNTERS * M * 4 : 0;
     case SIPNET_GPU_GATHER_STATE: return (size_t)SIPNET_GPU_NSTATE * M * 8;
     case SIPNET_GPU_GATHER_RING_VALUES:
     case SIPNET_GPU_GATHER_RING_WEIGHTS: return (size_t)h->ringCap * M * 8;
@@ -947,6 +951,7 @@ extern "C" int sipnet_gpu_gather(sipnet_gpu_handle *h, int what, void *dst, size
     case SIPNET_GPU_GATHER_LOGLIK: return copy_rows(h, dst, h->loglik, 1, 8);
     case SIPNET_GPU_GATHER_LOGLIK_N: return copy_rows(h, dst, h->loglikN, 1, 8);
     case SIPNET_GPU_GATHER_STATUS: return copy_rows(h, dst, h->status, 1, 4);
+    case SIPNET_GPU_GATHER_COUNTERS: return copy_rows(h, dst, h->counters, SIPNET_GPU_NCOUNTERS, 4);
     case SIPNET_GPU_GATHER_STATE: return copy_rows(h, dst, h->state, SIPNET_GPU_NSTATE, 8);
     case SIPNET_GPU_GATHER_RING_VALUES: return copy_rows(h, dst, h->ringV, (size_t)h->ringCap, 8);
     case SIPNET_GPU_GATHER_RING_WEIGHTS: return copy_rows(h, dst, h->ringW, (size_t)h->ringCap, 8);
@@ -996,6 +1001,7 @@ extern "C" void *sipnet_gpu_device_ptr(sipnet_gpu_handle *h, int what) {
     case SIPNET_GPU_GATHER_LOGLIK: return h->loglik;
     case SIPNET_GPU_GATHER_LOGLIK_N: return h->loglikN;
     case SIPNET_GPU_GATHER_STATUS: return h->status;
+    case SIPNET_GPU_GATHER_COUNTERS: return h->counters;
     case SIPNET_GPU_GATHER_STATE: return h->state;
     case SIPNET_GPU_GATHER_MEAN: return ensure_summaries(h) ? nullptr : h->mean;
     case SIPNET_GPU_GATHER_VARIANCE: return ensure_summaries(h) ? nullptr : h->var;

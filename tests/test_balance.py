@@ -109,3 +109,36 @@ def test_gpu_informational_bits_equal_oracle(oracle):
             ens.run()
             got = ens.status() & bits
         assert np.array_equal(got, want), math
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_gpu(), reason="needs a CUDA device")
+def test_gpu_message_counters_equal_oracle(oracle):
+    """SIPNET_GPU_GATHER_COUNTERS (validation dump): how OFTEN the reference would have printed each informational
+    message -- leaf-on limitation (limitations.c:48-61), N limitation (:98-102), the mineral-N cap (:119-130), the
+    non-negative-stock warning (sipnet.c:1346-1356, once per clamped stock) -- per member, continued across segments
+    and cleared by a reset."""
+    from sipnet_b200 import api
+    site = synth.synth_site(4, 3, "unequal", with_events=True)
+    P = synth.synth_params(48, stream=5)
+    P[A.P["nVolatilizationFrac"], 4:20] = 5.0
+    P[A.P["leafGrowth"], 20:24] = 0.0
+    P[A.P["baseSoilResp"], 24:30] *= 40.0                      # soil carbon runs out: clamp warnings
+    want = []
+    for m in range(P.shape[1]):
+        oracle.run_balance(synth.SYNTH_FLAGS, P[:, m], site)
+        want.append(oracle.last_counts.copy())
+    want = np.array(want, np.uint32).T                          # [NCOUNTERS][members]
+    for k in range(A.NCOUNTERS):
+        assert want[k].max() > 1, f"counter {k} is never above one on this ensemble: pick harder parameters"
+    with api.Ensemble([site], P, None, synth.SYNTH_FLAGS, outputs=A.OUT_DEBUG, out_steps_capacity=500) as ens:
+        for t0 in range(0, site.nsteps, 500):
+            ens.run(t0, min(site.nsteps, t0 + 500))
+        got = ens.counters()
+        status = ens.status()
+        assert np.array_equal(got, want)
+        assert np.array_equal(got[A.CNT_CLAMPED] > 0, (status & A.ST_CLAMPED) != 0)
+        assert np.array_equal(got[A.CNT_N_LIMITED] > 0, (status & A.ST_N_LIMITED) != 0)
+        ens.reset()
+        ens.run(0, 500)
+        assert (ens.counters() <= want).all() and not np.array_equal(ens.counters(), want)

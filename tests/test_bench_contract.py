@@ -58,6 +58,7 @@ def test_our_arm_line():
     assert line["oracle_spot_check"]["bit_identical_to_oracle"] is True
     assert line["c5"]["comm_nranks"] == 1 and line["c5"]["value"] > 0
     assert line["c2"]["e2e"]["d2h_bytes_per_step"] == 32 * T * 4096 * 8
+    assert line["c2"]["d2h_probe"]["gb_s_all_ranks"] >= line["c2"]["e2e"]["d2h_gb_s_all_ranks"] > 0   # the ceiling beside it
 
 
 def test_both_arms_share_one_config_object():
