@@ -111,11 +111,12 @@ struct Emitter {
         cur += colStride;
       }
     } else if (outp != nullptr) {
-      char *p = cur;
-      for (int s = 0; s < a->nOutCols; ++s) {
-        __stcs(reinterpret_cast<double *>(p), value((int)a->slotCol[s]));
-        p += colStride;
-      }
+      // NEE and GPP, the usual summary columns: a launch-uniform test and a store each (the column is a compile-time
+      // constant, so value() folds to the variable); any other kept column goes through the column switch
+      if (a->neeOff >= 0) __stcs(reinterpret_cast<double *>(cur + a->neeOff), value(SIPNET_O_nee));
+      if (a->gppOff >= 0) __stcs(reinterpret_cast<double *>(cur + a->gppOff), value(SIPNET_O_gpp));
+      for (int s = 0; s < a->nSlowCols; ++s)
+        __stcs(reinterpret_cast<double *>(cur + a->slowOff[s]), value((int)a->slowCol[s]));
     }
   }
   __device__ __forceinline__ void dbg(int k, double v) const {

@@ -1105,9 +1105,6 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // column -> value; with a compile-time column (all 32 kept) the switch folds away, with a run-time column (only
   // the summary columns are kept) it is one uniform jump per stored value instead of 32 tests per step
   const auto column = [&](int col) -> double {
-    // the usual summary columns first: one uniform test each instead of the switch's compare tree
-    if (col == SIPNET_O_nee) return t.nee;
-    if (col == SIPNET_O_gpp) return t.gpp;
     switch (col) {
       case SIPNET_O_plantWoodC: return mb.wood + mb.delta;
       case SIPNET_O_plantLeafC: return mb.leaf;

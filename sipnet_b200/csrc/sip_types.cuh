@@ -185,6 +185,12 @@ struct RunArgs {
   int8_t colSlot[SIPNET_GPU_NOUT];  // output column -> slot in `out`, or -1
   int8_t slotCol[SIPNET_GPU_NOUT];  // slot -> output column (first nOutCols entries)
   int32_t nOutCols;
+  // the usual summary columns are stored without going through the column switch: byte offset of the NEE / GPP slot
+  // from the step's first column (-1 = not kept); the other kept columns follow as (column, byte offset) pairs
+  int64_t neeOff, gppOff;
+  int32_t nSlowCols;
+  int8_t slowCol[SIPNET_GPU_NOUT];
+  int64_t slowOff[SIPNET_GPU_NOUT];
   // dynamic scheduling of (block descriptor, sub-range of steps) work items over a persistent grid; a null
   // workCounter means one CTA per block descriptor over the whole range (sip_kernels.cu: run_kernel)
   unsigned long long *workCounter;  // next work item

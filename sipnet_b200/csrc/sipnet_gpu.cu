@@ -771,6 +771,20 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
       a.slotCol[h->colSlot[c]] = (int8_t)c;
       a.nOutCols = std::max<int32_t>(a.nOutCols, h->colSlot[c] + 1);
     }
+  a.neeOff = a.gppOff = -1;
+  a.nSlowCols = 0;
+  for (int c = 0; c < SIPNET_GPU_NOUT; ++c) {
+    if (h->colSlot[c] < 0) continue;
+    const int64_t off = (int64_t)h->colSlot[c] * a.outSteps * h->ld * (int64_t)sizeof(double);
+    if (c == SIPNET_O_nee) {
+      a.neeOff = off;
+    } else if (c == SIPNET_O_gpp) {
+      a.gppOff = off;
+    } else {
+      a.slowCol[a.nSlowCols] = (int8_t)c;
+      a.slowOff[a.nSlowCols++] = off;
+    }
+  }
 
   if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
     if (outbuf) CUDA_OK(cudaMemsetAsync(outbuf, 0xFF, (size_t)h->ncols * a.outSteps * h->ld * sizeof(double), h->stream));
