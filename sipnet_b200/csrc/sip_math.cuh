@@ -13,8 +13,15 @@ namespace sip {
 // fmax(x, 0.0) and fmin(x, 1.0) against a CONSTANT: one compare and one select give exactly what CUDA's fmax / fmin
 // return for every input (x = NaN -> the constant; x = -0 -> +0 for max0, kept for min1), where the two-variable
 // library forms cost eight instructions each on sm_100a (no DMNMX).
-__device__ __forceinline__ double max0(double x) { return x > 0.0 ? x : 0.0; }
-__device__ __forceinline__ double min1(double x) { return x < 1.0 ? x : 1.0; }
+// (written on the two 32-bit halves: nvcc turns `x > 0.0 ? x : 0.0` back into its nine-instruction fmax sequence)
+__device__ __forceinline__ double max0(double x) {
+  const bool keep = x > 0.0;
+  return __hiloint2double(keep ? __double2hiint(x) : 0, keep ? __double2loint(x) : 0);
+}
+__device__ __forceinline__ double min1(double x) {
+  const bool keep = x < 1.0;
+  return __hiloint2double(keep ? __double2hiint(x) : 0x3ff00000, keep ? __double2loint(x) : 0);
+}
 
 __device__ __forceinline__ double clip01(double x) {  // unitClip, reference common/util.h:38: fmin(fmax(x, 0.0), 1.0)
   return min1(max0(x));

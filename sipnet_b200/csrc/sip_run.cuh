@@ -99,7 +99,7 @@ struct Emitter {
   __device__ __forceinline__ void begin(int64_t tl, int64_t ts) {
     tLocal = tl;
     tSite = ts;
-    if (FULL || outp != nullptr) cur = reinterpret_cast<char *>(outp + tl * a->ld);
+    if (FULL || a->out != nullptr) cur = reinterpret_cast<char *>(outp + tl * a->ld);  // (launch-uniform tests)
   }
   // value(col) is the step's column -> value switch (sip_step.cuh)
   template <class F>
@@ -110,7 +110,7 @@ struct Emitter {
         __stcs(reinterpret_cast<double *>(cur), value(c));
         cur += colStride;
       }
-    } else if (outp != nullptr) {
+    } else if (a->out != nullptr) {
       // NEE and GPP, the usual summary columns: a launch-uniform test and a store each (the column is a compile-time
       // constant, so value() folds to the variable); any other kept column goes through the column switch
       if (a->neeOff >= 0) __stcs(reinterpret_cast<double *>(cur + a->neeOff), value(SIPNET_O_nee));
