@@ -117,29 +117,42 @@ struct RingRefT {
 #endif
 };
 
+// The ring's oldest entry (what the next push evicts first), loaded AHEAD of ring_push: the ring lives in HBM and its
+// loads are L2 round trips; issued inside ring_push, the eviction loop's exit test waits for them with nothing else
+// of the step left to issue.  The step loads it right after the canopy integral (register pressure has dropped, more
+// than half of the step still lies ahead) and ring_push uses it for its first eviction.
+struct RingHead {
+  double w, v;
+};
 template <class RG>
-__device__ __forceinline__ void ring_reset(Member &mb, const RG &rg, double v) {  // runmean.c:44-51
+__device__ __forceinline__ RingHead ring_head(const Member &mb, const RG &rg) {
+  return RingHead{rg.wgt(mb.ringStart), rg.val(mb.ringStart)};
+}
+
+template <class RG>
+__device__ __forceinline__ void ring_reset(Member &mb, const RG &rg, double v, RingHead &head) {  // runmean.c:44-51
   mb.ringStart = mb.ringLast = 0;
   rg.set_val(0, v);
   rg.set_wgt(0, kMeanNppDays);
   mb.ringSum = v * kMeanNppDays;
+  head = RingHead{kMeanNppDays, v};  // slot 0 is the oldest entry now
 }
 
-// (Loading the ring's oldest entry one step ahead of its use -- the load sits at the end of the step -- was measured:
-// no change on the filled GPU, and the four extra registers cost the C2 kernel a spill.  Left as it is.)
 template <class RG>
-__device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value, double weight) {
+__device__ __forceinline__ void ring_push(Member &mb, const RG &rg, double value, double weight, RingHead head) {
   // addValueToMeanTracker, runmean.c:61-115 (weight <= 0 is rejected at init: events.c:460)
   if (weight >= kMeanNppDays) {
-    ring_reset(mb, rg, value);
+    ring_reset(mb, rg, value, head);
     return;
   }
   double left = weight;
   int i = mb.ringStart;
   double sum = mb.ringSum;
+  bool first = true;
   while (left > 0) {
-    const double wi = rg.wgt(i);
-    const double vi = rg.val(i);
+    const double wi = first ? head.w : rg.wgt(i);
+    const double vi = first ? head.v : rg.val(i);
+    first = false;
     if (wi > left) {
       rg.set_wgt(i, wi - left);
       sum -= left * vi;
@@ -566,6 +579,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   } else {
     dLight = 0;
   }
+  RingHead ringHead = ring_head(mb, rg);  // consumed by ring_push at the end of the step
   const double conv = SIP_K(kConvBase) * lai * 86400.0;
   const double potPsn = grossAMax * dTemp * dVpd * dLight * conv;
   const double baseFolResp = respPerGram * conv;
@@ -982,7 +996,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     mb.fine = 0.0;
     mb.delta = 0.0;
     if (fl.on(F_NITROGEN)) mb.storN = 0.0;
-    ring_reset(mb, rg, 0.0);
+    ring_reset(mb, rg, 0.0, ringHead);
     if (fl.on(F_EVENTS)) {
       const double v[4] = {harvRemoved, harvTransferred, totWood, totRoot};
       rec.add(mb, SIPNET_EV_PLANTDEATH, 0, 4, v);
@@ -1146,7 +1160,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   // ---------------- updateMeanTrackers, sipnet.c:1546-1570 -----------------------------------
   if (alive) {
     const double npp = r.photosynthesis - r.rVeg - r.rCoarseRoot - r.rFineRoot;
-    ring_push(mb, rg, npp, len);
+    ring_push(mb, rg, npp, len, ringHead);
   }
 
   if (DEBUG) {  // debug-log field order, debug_log.c:51-170
