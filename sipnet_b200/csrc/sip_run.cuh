@@ -101,6 +101,12 @@ struct Emitter {
     tSite = ts;
     if (FULL || a->out != nullptr) cur = reinterpret_cast<char *>(outp + tl * a->ld);  // (launch-uniform tests)
   }
+  // the following step of the same chunk: one row further (in FULL mode outputs() has walked cur through the columns)
+  __device__ __forceinline__ void next() {
+    ++tLocal;
+    ++tSite;
+    cur += a->ld * (int64_t)sizeof(double) - (FULL ? SIPNET_GPU_NOUT * colStride : 0);
+  }
   // value(col) is the step's column -> value switch (sip_step.cuh)
   template <class F>
   __device__ __forceinline__ void outputs(const F &value) {
@@ -349,7 +355,7 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     if (fl.on(F_CSAT)) nm.divisor_check(SIP_P(soilCSaturation));
   }
   const StepConsts &kc = a.kc;
-  const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, a.ld, a.ringCap};
+  const RingRefT<DYN> rg{a.ringV + m, a.ringW + m, (unsigned)a.ld, a.ringCap};
   RecSinkT<DYN> rec{nullptr, nullptr, a.maxRecs, 0};
   if (a.recCount != nullptr && active) {
     rec.count = a.recCount + m;
@@ -370,7 +376,8 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     if (active) {
       for (int i = 0; i < n; ++i) {
         const int64_t t = cs + i;
-        emit.begin(t - a.stepBegin, t);
+        if (i == 0) emit.begin(t - a.stepBegin, t);
+        else emit.next();
         rec.step = (int32_t)t;
         step<FL, DEBUG>(fl, nm, prm, cbuf[i], myEvents, mb, ext, rg, rec, emit, kc);
       }

@@ -100,21 +100,15 @@ template <bool COHERENT>
 struct RingRefT {
   double *v;
   double *w;
-  int64_t ld;
+  unsigned ld;  // slots are ld doubles apart; cap * ld < 2^32 (checked at init), so a slot's offset is one 32-bit product
   int cap;
+  __device__ __forceinline__ size_t off(int s) const { return (size_t)((unsigned)s * ld); }
   // L2-coherent accesses: with dynamic scheduling consecutive sub-ranges of a member may run on different SMs
   // within ONE launch, so ring slots must not be served from a stale L1 line
-#ifdef SIP_RING_L1  // measurement variant: default (L1-allocating) accesses
-  __device__ __forceinline__ double val(int s) const { return v[(int64_t)s * ld]; }
-  __device__ __forceinline__ double wgt(int s) const { return w[(int64_t)s * ld]; }
-  __device__ __forceinline__ void set_val(int s, double x) const { v[(int64_t)s * ld] = x; }
-  __device__ __forceinline__ void set_wgt(int s, double x) const { w[(int64_t)s * ld] = x; }
-#else
-  __device__ __forceinline__ double val(int s) const { return carried_load<COHERENT>(v + (int64_t)s * ld); }
-  __device__ __forceinline__ double wgt(int s) const { return carried_load<COHERENT>(w + (int64_t)s * ld); }
-  __device__ __forceinline__ void set_val(int s, double x) const { carried_store<COHERENT>(v + (int64_t)s * ld, x); }
-  __device__ __forceinline__ void set_wgt(int s, double x) const { carried_store<COHERENT>(w + (int64_t)s * ld, x); }
-#endif
+  __device__ __forceinline__ double val(int s) const { return carried_load<COHERENT>(v + off(s)); }
+  __device__ __forceinline__ double wgt(int s) const { return carried_load<COHERENT>(w + off(s)); }
+  __device__ __forceinline__ void set_val(int s, double x) const { carried_store<COHERENT>(v + off(s), x); }
+  __device__ __forceinline__ void set_wgt(int s, double x) const { carried_store<COHERENT>(w + off(s), x); }
 };
 
 // The ring's oldest entry (what the next push evicts first), loaded AHEAD of ring_push: the ring lives in HBM and its

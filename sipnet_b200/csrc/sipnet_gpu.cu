@@ -478,6 +478,11 @@ extern "C" int sipnet_gpu_init(const sipnet_gpu_config *cfg, sipnet_gpu_handle *
     // reference would not, the reference's own count reproduces its ring layout slot for slot
     if (cfg->ring_slots != 0) h->ringCap = cfg->ring_slots;
   }
+  if ((uint64_t)h->ringCap * (uint64_t)h->ld >= (1ull << 32)) {  // the kernel forms ring offsets as 32-bit products
+    free_handle(h);
+    return fail(SIPNET_GPU_ERR_BAD_ARGUMENT, "%lld members x %d ring slots exceed the 2^32 ring entries one handle addresses",
+                (long long)cfg->nmembers, h->ringCap);
+  }
 
   // ---- members, blocks ----
   {
