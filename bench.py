@@ -46,7 +46,8 @@ if ROOT not in sys.path:
 
 METRIC = "ensemble member-timesteps/sec"
 UNIT = "member-timesteps/s"
-FLOP_PER_MEMBER_STEP = 3200.0   # SURVEY 8d / BASELINE.md 4: ~630 FP64 ops + ~19 libm calls (algorithmic figure)
+FLOP_PER_MEMBER_STEP = 3200.0   # SURVEY 8d / BASELINE.md 4: ~630 FP64 ops + ~19 libm calls (an estimate; kept for continuity)
+FP64_INST_PER_MEMBER_STEP_FALLBACK = 800.0   # executed FP64-pipe instructions per member-step if the facts file is missing
 MEMBERS_PER_GPU = 131072        # C4: 1M members / 8 GPUs
 C5_DRAWS_PER_GPU = 32768        # C5: 256k draws / 8 GPUs
 QUANTILES = [0.05, 0.5, 0.95]
@@ -617,27 +618,33 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         rate_kernel = M * T / (r["kern_ms"] * 1e-3)              # member-steps/s of one GPU inside the step kernel
-        fp64_ach = rate_kernel * FLOP_PER_MEMBER_STEP / 1e12
+        # FP64 roofline of the step kernel.  Basis: the FP64-pipe instructions the kernel executes per
+        # member-step (DFMA + DADD + DMUL + DSETP, from this round's ncu capture), each counted as one pipe slot = one
+        # FMA = 2 flop, against the pipe's issue rate -- 16 lanes per SM sub-partition and clock at the SM clock sampled
+        # during the timed region.  This is what ncu reports as sm__inst_executed_pipe_fp64 (% of peak).
+        e = float(facts.get("fp64_pipe_inst_per_member_step") or FP64_INST_PER_MEMBER_STEP_FALLBACK)
+        sm_hz = 1e6 * float(r["clocks"].get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        pipe_rate = 148 * 4 * 16 * sm_hz                           # thread-level FP64 instructions per second
+        fp64_ach = rate_kernel * e * 2.0 / 1e12
+        fp64_peak = pipe_rate * 2.0 / 1e12
         roof = {"bound": "fp64", "kernel": "sip::k1::run_kernel", "kernel_ms": r["kern_ms"],
-                "achieved": fp64_ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                "frac": fp64_ach / fp64_peak_tflops if fp64_peak_tflops > 0 else None,
-                "algorithmic": f"{FLOP_PER_MEMBER_STEP:.0f} FP64 flop/member-step (SURVEY 8d) x {M * T} member-steps per launch",
-                "peak_source": "FP64 FMA rate measured live (sipnet_gpu_measure_fp64_peak, 8 DFMA chains per thread); "
-                               "MEASURED_PEAKS.json holds no FP64 figure"}
-        e = facts.get("fp64_pipe_inst_per_member_step")
-        if e:
-            # executed FP64-pipe instructions per second over the pipe's issue rate -- 16 lanes per SM sub-partition and
-            # clock, i.e. one warp instruction per two clocks, at the SM clock sampled during the timed region -- which
-            # is what ncu reports as sm__inst_executed_pipe_fp64 (% of peak).  The live DFMA probe (`peak`) reaches 91 %
-            # of that rate, so the same count against the probe reads ~1.1x higher; both are given.
-            sm_hz = 1e6 * float(r["clocks"].get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
-            pipe_rate = 148 * 4 * 16 * sm_hz                       # thread-level FP64 instructions per second
-            roof["frac_executed"] = e * rate_kernel / pipe_rate
-            roof["frac_executed_vs_probe"] = e * rate_kernel / (fp64_peak_tflops * 1e12 / 2.0) if fp64_peak_tflops > 0 else None
-            roof["executed"] = {"fp64_pipe_inst_per_member_step": e, "all_inst_per_member_step": facts.get("inst_per_member_step"),
-                                "pipe_rate_inst_per_s": pipe_rate, "sm_mhz": sm_hz / 1e6,
-                                "ncu_fp64_pipe_pct": facts.get("ncu_fp64_pipe_pct"), "ncu_issue_active_pct": facts.get("ncu_issue_active_pct"),
-                                "source": facts.get("source")}
+                "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+                "algorithmic": f"{e:.0f} FP64-pipe instructions/member-step (= {2 * e:.0f} FMA-equivalent flop) x {M * T} "
+                               f"member-steps per launch",
+                "peak_source": "FP64 pipe issue rate: 148 SMs x 4 sub-partitions x 16 lanes x 2 flop x the SM clock sampled "
+                               "in the timed region (MEASURED_PEAKS.json holds no FP64 figure); a live DFMA probe is "
+                               "reported beside it",
+                "frac_executed": fp64_ach / fp64_peak,
+                "probe": {"tflops": fp64_peak_tflops, "frac_vs_probe": fp64_ach / fp64_peak_tflops if fp64_peak_tflops > 0 else None,
+                          "what": "sipnet_gpu_measure_fp64_peak: 8 independent DFMA chains per thread, this GPU, this run"},
+                "executed": {"fp64_pipe_inst_per_member_step": e, "all_inst_per_member_step": facts.get("inst_per_member_step"),
+                             "pipe_rate_inst_per_s": pipe_rate, "sm_mhz": sm_hz / 1e6,
+                             "ncu_fp64_pipe_pct": facts.get("ncu_fp64_pipe_pct"), "ncu_issue_active_pct": facts.get("ncu_issue_active_pct"),
+                             "source": facts.get("source")},
+                # SURVEY 8(d)'s estimate, kept for continuity with round 1: it prices a pow at CUDA libm's 150-200
+                # instructions; the glibc-exact restatement needs a quarter of that, so this basis is NOT a roofline
+                "survey_basis": {"flop_per_member_step": FLOP_PER_MEMBER_STEP, "tflops": rate_kernel * FLOP_PER_MEMBER_STEP / 1e12,
+                                 "note": "overstates the executed FP64 work about 2x; not used for frac"}}
         # summary columns written by the step kernel (2 x 8 B per member-step) against HBM
         hbm_ach = rate_kernel * 16.0 / 1e9
         roof["traffic"] = facts.get("dram_bytes_per_launch")
