@@ -116,6 +116,9 @@ struct Emitter {
         __stcs(reinterpret_cast<double *>(cur), value(c));
         cur += colStride;
       }
+    } else if (a->onlyNeeGpp) {  // the usual summary request: one launch-uniform test, two stores
+      __stcs(reinterpret_cast<double *>(cur + a->neeOff), value(SIPNET_O_nee));
+      __stcs(reinterpret_cast<double *>(cur + a->gppOff), value(SIPNET_O_gpp));
     } else if (a->out != nullptr) {
       // NEE and GPP, the usual summary columns: a launch-uniform test and a store each (the column is a compile-time
       // constant, so value() folds to the variable); any other kept column goes through the column switch

@@ -392,20 +392,20 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
                                      Member &mb, MemberExt &ext, const RG &rg, const RS &rec, Emit &emit,
                                      const StepConsts &kc) {
   const double len = c.length;
-  double seedLen = 0.0;
-  if constexpr (NM::kFast) {
-    if (c.invLenPow2 == 0.0) {  // block-uniform: the step length is not a power of two
-      seedLen = nm.seed(len);
-      nm.divisor_check(len);
-    }
-  }
-  const Div<NM, PT> dv{nm, prm, len, seedLen, c.invLenPow2};
+  Div<NM, PT> dv{nm, prm, len, 0.0, c.invLenPow2};  // (the reciprocal seed of an odd step length is set below)
   const double oldSoilWater = mb.water;  // sipnet.c:1821
   Rates r = {};                          // resetFluxes, sipnet.c:1222
   bool alive = has_biomass(mb);          // initPlantSurvivalTracker, sipnet.c:1538
   double harvRemoved = 0, harvTransferred = 0;  // events.c:468-469
 
   // ---------------- processEvents, events.c:471-741 (events pre-bound to this step) ----
+  // a step length that is not a power of two (its reciprocal seed is needed) or events on this step: both are
+  // block-uniform and unusual, one test covers them
+  if ((NM::kFast & (c.invLenPow2 == 0.0)) | (c.evBegin < c.evEnd)) {
+  if (NM::kFast && c.invLenPow2 == 0.0) {
+    dv.seedLen = nm.seed(len);
+    nm.divisor_check(len);
+  }
   for (int e = c.evBegin; e < c.evEnd; ++e) {
     const EventDev ev = events[e];
     switch (ev.type) {
@@ -540,6 +540,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
         break;  // PLANTDEATH is ignored (events.c:729-734); unknown types are rejected at init
     }
   }
+  }
 
   // ---------------- calculateFluxes, sipnet.c:1256-1336 -------------------------------
   const double whc = SIP_P(soilWHC);
@@ -548,7 +549,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   const double woodTot = mb.wood + mb.delta;                                   // getTotalWoodC
 
   double dLight;
-  if (lai > 0 && c.par > 0) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
+  if ((lai > 0) & (c.par > 0)) {  // calcLightEff, :517-570 (Simpson, 6 layers, coefficients 1,4,2,4,2,4,2 then -last)
     const double att = SIP_P(attenuation), hsp = SIP_P(halfSatPar), seedHsp = SIP_K(kSeedHalfSatPar);
     double eff[7];
     // the seven layers are independent: each stage is issued for all layers before the next one
@@ -818,7 +819,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     // pow(+0, e) = +0 for every finite e > 0 (e_pow.c zero branch): skip the evaluation in that (common) case.
     const double te = SIP_P(anaerobicTransExp);
     double mm;
-    if (__double_as_longlong(anaerobicIdx) == 0ll && te > 0.0 && te < 1e300) {
+    if ((__double_as_longlong(anaerobicIdx) == 0ll) & (te > 0.0) & (te < 1e300)) {
       mm = 0.0;
     } else {
       mm = nm.pow(anaerobicIdx, te);
@@ -883,35 +884,40 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     }
     nDemand = n_fix_and_uptake(fl, dv, mb, r, len);  // nitrogen.c:156-168
 
-    // checkMineralNLimitation, limitations.c:119-130
+    // checkMineralNLimitation, limitations.c:119-130, then checkNitrogenLimitation, limitations.c:69-114
     {
       const double pool = mb.minN + (r.nMin + r.eventMinN) * len;
       const double loss = (r.nLeaching + r.nVolatilization) * len;
-      if (loss > kTiny && loss > pool) {
-        const double red = nm.div(pool, loss);
-        r.nLeaching *= red;
-        r.nVolatilization *= red;
-        mb.status |= SIPNET_GPU_ST_MINN_LIMITED;
-        if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_MINN_LIMITED];
-      }
-    }
-    // checkNitrogenLimitation, limitations.c:69-114
-    {
-      const double uptakeDemand = r.nUptake * len;
-      const double nonUptake = n_non_uptake(r) * len;
-      const double avail = mb.minN + nonUptake;
-      if (uptakeDemand > kTiny && uptakeDemand > avail) {
-        const double unclaimed = n_unclaimed_storage(dv, mb, r, len);
-        const double demand = n_demand(fl, dv, r) * len;
-        const double uptakeFrac = 1 - n_fix_frac(dv, mb);
-        const double red = nm.div(nm.div(avail, uptakeFrac) + unclaimed, demand);
-        mb.status |= SIPNET_GPU_ST_N_LIMITED;  // the reference's logInfo, limitations.c:98-102
-        if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_N_LIMITED];
-        r.woodCreation *= red;
-        r.leafCreation *= red;
-        r.fineRootCreation *= red;
-        r.coarseRootCreation *= red;
-        nDemand = n_fix_and_uptake(fl, dv, mb, r, len);
+      const bool lossLimited = (loss > kTiny) & (loss > pool);
+      // both tests behind one: the second one's inputs only change when the first one acts, so evaluated up front it
+      // is the real test whenever the first is false -- and when the first is true the block is entered anyway
+      const double uptakeDemand0 = r.nUptake * len;
+      const bool uptakeMaybe = (uptakeDemand0 > kTiny) & (uptakeDemand0 > mb.minN + n_non_uptake(r) * len);
+      if (lossLimited | uptakeMaybe)
+      {
+        if (lossLimited) {
+          const double red = nm.div(pool, loss);
+          r.nLeaching *= red;
+          r.nVolatilization *= red;
+          mb.status |= SIPNET_GPU_ST_MINN_LIMITED;
+          if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_MINN_LIMITED];
+        }
+        const double uptakeDemand = r.nUptake * len;
+        const double nonUptake = n_non_uptake(r) * len;
+        const double avail = mb.minN + nonUptake;
+        if (uptakeDemand > kTiny && uptakeDemand > avail) {
+          const double unclaimed = n_unclaimed_storage(dv, mb, r, len);
+          const double demand = n_demand(fl, dv, r) * len;
+          const double uptakeFrac = 1 - n_fix_frac(dv, mb);
+          const double red = nm.div(nm.div(avail, uptakeFrac) + unclaimed, demand);
+          mb.status |= SIPNET_GPU_ST_N_LIMITED;  // the reference's logInfo, limitations.c:98-102
+          if (DEBUG) ++ext.cnt[SIPNET_GPU_CNT_N_LIMITED];
+          r.woodCreation *= red;
+          r.leafCreation *= red;
+          r.fineRootCreation *= red;
+          r.coarseRootCreation *= red;
+          nDemand = n_fix_and_uptake(fl, dv, mb, r, len);
+        }
       }
     }
   }
@@ -1002,6 +1008,15 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
 
   // checkForMortality, sipnet.c:1688-1767
   const bool hasBio = has_biomass(mb);
+  // updateEventTrackers, events.c:811-822: the tillage modifier is last read by the fluxes above, so its decay can sit
+  // here, behind the same "anything unusual on this step?" test as the mortality check
+  const bool tilled = mb.dTill > 0;
+  if ((alive == hasBio) & !tilled) {
+  } else {
+  if (tilled) {
+    mb.dTill *= c.tillDecay;
+    if (mb.dTill < 0.01) mb.dTill = 0.0;
+  }
   if (alive == hasBio) {  // the usual step: nothing changes (one test)
   } else if (!alive) {
     alive = true;
@@ -1033,6 +1048,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     }
   }
 
+  }
   // ensureNonNegativeStocks, sipnet.c:1368-1397
   {
     bool clamped = false;
@@ -1055,7 +1071,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
     clamp(mb.orgN, 0);
     clamp(mb.litN, 0);
     clamp(mb.storN, 0);
-    if (clamped) mb.status |= SIPNET_GPU_ST_CLAMPED;
+    mb.status |= clamped ? SIPNET_GPU_ST_CLAMPED : 0u;
   }
 
   double balDeltaC = 0.0, balDeltaN = 0.0;
@@ -1229,10 +1245,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
   }
 
   // ---------------- updateEventTrackers, events.c:811-822 -------------------------------------
-  if (mb.dTill > 0) {
-    mb.dTill *= c.tillDecay;
-    if (mb.dTill < 0.01) mb.dTill = 0.0;
-  }
+
 }
 
 }  // namespace sip

@@ -188,6 +188,7 @@ struct RunArgs {
   // the usual summary columns are stored without going through the column switch: byte offset of the NEE / GPP slot
   // from the step's first column (-1 = not kept); the other kept columns follow as (column, byte offset) pairs
   int64_t neeOff, gppOff;
+  int32_t onlyNeeGpp;  // exactly NEE and GPP are kept: the step stores them behind ONE launch-uniform test
   int32_t nSlowCols;
   int8_t slowCol[SIPNET_GPU_NOUT];
   int64_t slowOff[SIPNET_GPU_NOUT];

@@ -789,6 +789,7 @@ static int run_segment(sipnet_gpu_handle *h, int64_t step_begin, int64_t step_en
       a.slowCol[a.nSlowCols] = (int8_t)c;
       a.slowOff[a.nSlowCols++] = off;
     }
+  a.onlyNeeGpp = (a.out != nullptr && a.neeOff >= 0 && a.gppOff >= 0 && a.nSlowCols == 0) ? 1 : 0;
   }
 
   if (h->sitesDiffer) {  // steps past a shorter site's end are never written: make them NaN
