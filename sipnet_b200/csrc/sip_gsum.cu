@@ -6,6 +6,8 @@
 // The reference has no ensemble code: definitions as in sip_reduce.cu; tests compare with numpy.
 #include "sip_gsum.cuh"
 
+#include <type_traits>
+
 namespace sip {
 namespace gs {
 
@@ -323,6 +325,10 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
   if (pass && level >= 2)
     for (int r2 = 0; r2 < 2 * a.nq; ++r2)
       if (S.slotOf[r2] != 0xff && S.pop[r2] > 1024u) trackMask |= 1u << S.slotOf[r2];
+  // The scan of the row, instantiated for the number of slots an element has to be matched against: most rows have one
+  // or two bins in play, and eight compare + select pairs per element are most of what the later levels execute.
+  const auto scan = [&](auto nsTag) {
+  constexpr int NS = decltype(nsTag)::value;
   for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
     double x[kUnroll];
 #pragma unroll
@@ -346,14 +352,14 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
             const unsigned khi = hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);  // high word of key_of(x)
             const unsigned t = khi >> (sh0 - 32);
 #pragma unroll
-            for (int s = 0; s < kGsMaxStat; ++s)
+            for (int s = 0; s < NS; ++s)
               if (top32[s] == t) slot = s;
             bin = (int)((khi >> (sh1 - 32)) & (unsigned)bmask);
           } else {
             const uint64_t k = key_of(x[u]);
             const uint64_t t = k >> sh0;
 #pragma unroll
-            for (int s = 0; s < kGsMaxStat; ++s)
+            for (int s = 0; s < NS; ++s)
               if (top[s] == t) slot = s;
             bin = (int)((k >> sh1) & (uint64_t)bmask);
           }
@@ -380,6 +386,11 @@ __global__ void __launch_bounds__(kThreads, 2) gs_level_kernel(const GsArgs a, c
       if (pass && __any_sync(0xffffffffu, code >= 0)) hist_add(hist, code);
     }
   }
+  };
+  if (nslots <= 1) scan(std::integral_constant<int, 1>{});
+  else if (nslots <= 2) scan(std::integral_constant<int, 2>{});
+  else if (nslots <= 4) scan(std::integral_constant<int, 4>{});
+  else scan(std::integral_constant<int, kGsMaxStat>{});
   if (needSS) {
     const double ss = block_sum(q2, red);
     if (tid == 0) a.q2All[(int64_t)a.rank * rows + r.row] = ss;
@@ -439,53 +450,79 @@ __global__ void __launch_bounds__(kThreads, 2) gs_emit_kernel(const GsArgs a) {
   }
   __syncthreads();
   if (nemit == 0) return;
-  // the emit slots in registers: a key belongs to slot s when (key >> shv[s]) == tp[s].  When every slot was
-  // resolved within the key's high word (<= 32 bits: the usual case) the test is a 32-bit shift and compare.
+  // the ACTIVE emit slots in registers, compacted (most rows have one to three): a key belongs to slot at[j] when
+  // (key >> shv[j]) == tp[j].  When every slot was resolved within the key's high word (<= 32 bits: the usual case)
+  // the test is a 32-bit shift and compare.  The scan is instantiated for the number of active slots.
   uint64_t tp[kGsMaxStat];
   unsigned tp32[kGsMaxStat];
-  int shv[kGsMaxStat];
+  int shv[kGsMaxStat], at[kGsMaxStat];
   bool hi32 = true;
+  {
+    int j = 0;
 #pragma unroll
-  for (int s = 0; s < kGsMaxStat; ++s) {
-    const bool on = s < 2 * a.nq && owner[s] == s;
-    tp[s] = on ? top[s] : kGsNoKey;
-    shv[s] = on ? sh[s] : 0;
-    if (on && sh[s] < 32) hi32 = false;
-    tp32[s] = on ? (unsigned)top[s] : 0xffffffffu;
-  }
-  for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
-    double x[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int i = i0 + u * kThreads + tid;
-      x[u] = i < r.count ? r.p[i] : __longlong_as_double(0x7ff8000000000000ll);
+    for (int s = 0; s < kGsMaxStat; ++s) {
+      tp[s] = kGsNoKey;
+      tp32[s] = 0xffffffffu;
+      shv[s] = 32;
+      at[s] = 0;
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (!finite_hi(x[u])) continue;
-      if (hi32) {  // block-uniform
-        const unsigned hi = (unsigned)__double2hiint(x[u]);
-        const unsigned khi = hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);
-        int hit = -1;
+    for (int s = 0; s < kGsMaxStat; ++s) {
+      const bool on = s < 2 * a.nq && owner[s] == s;
+      if (on) {
 #pragma unroll
-        for (int s = 0; s < kGsMaxStat; ++s)
-          if (shv[s] != 0 && (khi >> (shv[s] - 32)) == tp32[s]) hit = s;  // emit slots hold disjoint key ranges
-        if (hit >= 0) {
-          const unsigned int pos = atomicAdd(&fill[hit], 1u);
-          if (pos < (unsigned)kGsEmit) dst[hit * kGsEmit + pos] = key_of(x[u]);
-        }
-      } else {
-        const uint64_t k = key_of(x[u]);
+        for (int jj = 0; jj < kGsMaxStat; ++jj)
+          if (jj == j) {
+            tp[jj] = top[s];
+            tp32[jj] = (unsigned)top[s];
+            shv[jj] = sh[s];
+            at[jj] = s;
+          }
+        if (sh[s] < 32) hi32 = false;
+        ++j;
+      }
+    }
+  }
+  const auto scan = [&](auto neTag) {
+    constexpr int NE = decltype(neTag)::value;
+    for (int i0 = 0; i0 < r.count; i0 += kUnroll * kThreads) {
+      double x[kUnroll];
 #pragma unroll
-        for (int s = 0; s < kGsMaxStat; ++s) {
-          if ((k >> shv[s]) == tp[s]) {
-            const unsigned int pos = atomicAdd(&fill[s], 1u);
-            if (pos < (unsigned)kGsEmit) dst[s * kGsEmit + pos] = k;
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = i0 + u * kThreads + tid;
+        x[u] = i < r.count ? r.p[i] : __longlong_as_double(0x7ff8000000000000ll);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (!finite_hi(x[u])) continue;
+        if (hi32) {  // block-uniform
+          const unsigned hi = (unsigned)__double2hiint(x[u]);
+          const unsigned khi = hi ^ ((unsigned)((int)hi >> 31) | 0x80000000u);
+          int hit = -1;
+#pragma unroll
+          for (int j = 0; j < NE; ++j)
+            if ((khi >> (shv[j] - 32)) == tp32[j]) hit = at[j];  // emit slots hold disjoint key ranges
+          if (hit >= 0) {
+            const unsigned int pos = atomicAdd(&fill[hit], 1u);
+            if (pos < (unsigned)kGsEmit) dst[hit * kGsEmit + pos] = key_of(x[u]);
+          }
+        } else {
+          const uint64_t k = key_of(x[u]);
+#pragma unroll
+          for (int j = 0; j < NE; ++j) {
+            if ((k >> shv[j]) == tp[j]) {
+              const unsigned int pos = atomicAdd(&fill[at[j]], 1u);
+              if (pos < (unsigned)kGsEmit) dst[at[j] * kGsEmit + pos] = k;
+            }
           }
         }
       }
     }
-  }
+  };
+  if (nemit <= 1) scan(std::integral_constant<int, 1>{});
+  else if (nemit <= 2) scan(std::integral_constant<int, 2>{});
+  else if (nemit <= 4) scan(std::integral_constant<int, 4>{});
+  else scan(std::integral_constant<int, kGsMaxStat>{});
 }
 
 // ---- finish: order statistics from the gathered keys, quantiles, moments ----------------------------------------
