@@ -377,12 +377,12 @@ __device__ __forceinline__ void run_item(const RunArgs &a, const FL &fl, int64_t
     const ClimRec *cbuf = climBuf + ((second ? 2 : 0) + (sc & 1)) * kChunkSteps;  // this lane's site's records
     const int n = (int)((myT1 - cs) < kChunkSteps ? (myT1 - cs) : kChunkSteps);   // <= 0 once its site has ended
     if (active) {
+      emit.begin(cs - a.stepBegin, cs);
+      rec.step = (int32_t)cs;
       for (int i = 0; i < n; ++i) {
-        const int64_t t = cs + i;
-        if (i == 0) emit.begin(t - a.stepBegin, t);
-        else emit.next();
-        rec.step = (int32_t)t;
         step<FL, DEBUG>(fl, nm, prm, cbuf[i], myEvents, mb, ext, rg, rec, emit, kc);
+        emit.next();  // (one past the chunk's last row after the last step: never dereferenced)
+        ++rec.step;
       }
     }
     __syncthreads();  // everyone is done reading this buffer before it is refilled

@@ -751,8 +751,7 @@ __device__ __forceinline__ void step(const FL &fl, NM &nm, const PT &prm, const 
       }
     }
     if (!mb.didFall) {
-      bool past = false;  // pastLeafFall, :733-742
-      if (SIP_P(leafOffDay) > 0) past = c.dayFrac >= SIP_P(leafOffDay);
+      const bool past = (SIP_P(leafOffDay) > 0) & (c.dayFrac >= SIP_P(leafOffDay));  // pastLeafFall, :733-742
       if (past) {
         const double off = dv.byLen(mb.leaf * SIP_P(fracLeafFall));
         r.leafLitter += off;
