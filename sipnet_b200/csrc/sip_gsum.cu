@@ -206,6 +206,7 @@ __device__ void resolve_level(const GsArgs &a, GsRow &S, const unsigned int *his
     const unsigned long long k = S.k[warp];
     const unsigned owner = __ballot_sync(0xffffffffu, incl > k);
     const int who = __ffs(owner) - 1;  // first lane whose inclusive count exceeds k (exists: k < population)
+    __syncwarp();  // every lane has read S.k[warp] before lane `who` overwrites it (the branch above is warp-uniform)
     if (lane == who) {
       unsigned long long acc = incl - mine;
       int bin = lane * per;
