@@ -85,6 +85,24 @@ void sip_site_view(const sip_site_data *site, sipnet_gpu_site *view); /* borrow 
 void sip_write_header(FILE *out);                                                         /* outputHeader() */
 void sip_write_state_row(FILE *out, int year, int day, double time, const double *out32, int64_t stride);
                                                                                           /* outputState(); out32[c*stride] */
+/* The same row into memory, without printf for the usual values (byte-identical; anything near a rounding boundary,
+ * huge or non-finite goes through snprintf), and the plain printf statements it must reproduce (tests). */
+#define SIP_STATE_ROW_MAX 12288 /* 35 fields of at most ~320 characters ("%f" of DBL_MAX) */
+size_t sip_format_state_row(char *dst, int year, int day, double time, const double *out32, int64_t stride);
+size_t sip_format_state_row_printf(char *dst, int year, int day, double time, const double *out32, int64_t stride);
+/* the rows of up to SIP_STATE_BLOCK_MAX members that are neighbours in the gathered [col][step][member] array */
+#define SIP_STATE_BLOCK_MAX 8
+int sip_write_state_block(FILE *const *files, int count, const int64_t *nsteps, const int32_t *const *year,
+                          const int32_t *const *day, const double *const *time, const double *out32, int64_t colStride,
+                          int64_t stepStride);
+/* The main output files of ALL members of a launch from the gathered [col][T][M] array: member m's file is
+ * paths + m * SIP_STATE_PATH_MAX (NUL-terminated), it gets nsteps[m] rows dated year[m][t] / day[m][t] / time[m][t].
+ * Blocks of members are formatted on nthreads host threads (0: SIPNET_GPU_WRITER_THREADS or every online core). */
+#define SIP_STATE_PATH_MAX (SIP_NAME_MAX + 32)
+#define SIP_STATE_THREADS_MAX 64
+int sip_write_state_files(const char *paths, int64_t M, const int64_t *nsteps, const int32_t *const *year,
+                          const int32_t *const *day, const double *const *time, int64_t T, const double *out32,
+                          int printHeader, int nthreads);
 void sip_write_events_header(FILE *out);                                                  /* openEventOutFile() header */
 int sip_write_event_row(FILE *out, int year, int day, const sipnet_gpu_event_record *rec); /* doWriteEventOut() */
 const char *sip_event_type_name(int type);                                                /* eventTypeToString() */

@@ -275,23 +275,44 @@ int main(int argc, char **argv) {
             fclose(sf);
           }
         }
-        if (!ctx.doMainOutput) continue;
-        FILE *o = out;
-        if (!o) {
-          char name[SIP_NAME_MAX + 32];
-          if (job->memberList[0])
-            snprintf(name, sizeof name, "%s.out.%lld", job->prefix, (long long)k);
-          else
-            snprintf(name, sizeof name, "%s.out", job->prefix);
-          o = fopen(name, "w");
-          if (!o) return die(SIPNET_GPU_ERR_FILE_OPEN, "cannot open a main output file");
-        }
-        if (ctx.printHeader) sip_write_header(o);
-        for (int64_t t = 0; t < job->data.nsteps; ++t)
-          sip_write_state_row(o, job->data.year[t], job->data.day[t], job->data.time[t],
-                              buf + (size_t)t * (size_t)M + (size_t)m, (int64_t)T * M);
-        fclose(o);
       }
+    }
+    if (ctx.doMainOutput && out) { /* one member, the file the reference opens up front */
+      if (ctx.printHeader) sip_write_header(out);
+      for (int64_t t = 0; t < jobs[0].data.nsteps; ++t)
+        sip_write_state_row(out, jobs[0].data.year[t], jobs[0].data.day[t], jobs[0].data.time[t], buf + (size_t)t * (size_t)M,
+                            (int64_t)T * M);
+      fclose(out);
+    } else if (ctx.doMainOutput) {
+      /* every member's <prefix>.out[.k], formatted on all host cores (sip_write_state_files) */
+      char *paths = (char *)malloc((size_t)M * SIP_STATE_PATH_MAX);
+      int64_t *nsteps = (int64_t *)malloc((size_t)M * sizeof *nsteps);
+      const int32_t **years = (const int32_t **)malloc((size_t)M * sizeof *years);
+      const int32_t **days = (const int32_t **)malloc((size_t)M * sizeof *days);
+      const double **times = (const double **)malloc((size_t)M * sizeof *times);
+      if (!paths || !nsteps || !years || !days || !times) return die(SIPNET_GPU_ERR_INTERNAL, "memory allocation failure");
+      for (int64_t s = 0; s < njobs; ++s) {
+        const site_job *job = &jobs[s];
+        for (int64_t k = 0; k < job->nmembers; ++k) {
+          const int64_t m = job->member0 + k;
+          char *name = paths + (size_t)m * SIP_STATE_PATH_MAX;
+          if (job->memberList[0])
+            snprintf(name, SIP_STATE_PATH_MAX, "%s.out.%lld", job->prefix, (long long)k);
+          else
+            snprintf(name, SIP_STATE_PATH_MAX, "%s.out", job->prefix);
+          nsteps[m] = job->data.nsteps;
+          years[m] = job->data.year;
+          days[m] = job->data.day;
+          times[m] = job->data.time;
+        }
+      }
+      if ((rc = sip_write_state_files(paths, M, nsteps, years, days, times, T, buf, ctx.printHeader, 0)))
+        return die(rc, sip_host_error());
+      free(paths);
+      free(nsteps);
+      free(years);
+      free(days);
+      free(times);
     }
     free(buf);
   }
