@@ -20,7 +20,7 @@
 
 #include "sip_host.h"
 
-static char g_err[1024];
+static _Thread_local char g_err[1024]; /* per thread: the readers and writers run on worker threads in many-site launches */
 const char *sip_host_error(void) { return g_err; }
 int sip_fail(int code, const char *fmt, ...) {
   va_list ap;

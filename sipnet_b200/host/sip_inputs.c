@@ -131,12 +131,14 @@ int sip_read_params(const char *path, const sipnet_gpu_flags *f, int quiet, doub
       char copy[256];
       strcpy(copy, line);
       int nf = 0;
-      for (char *t = strtok(copy, " \t\n\r"); t; t = strtok(NULL, " \t\n\r")) ++nf;
+      char *sv = NULL; /* strtok_r: sites are read on several threads in many-site launches */
+      for (char *t = strtok_r(copy, " \t\n\r", &sv); t; t = strtok_r(NULL, " \t\n\r", &sv)) ++nf;
       if (nf > 2) sip_info(quiet, "extra columns in .param file are being ignored (found %d columns)\n", nf);
       formatChecked = 1;
     }
-    char *name = strtok(line, " \t\n\r");
-    char *val = strtok(NULL, " \t\n\r");
+    char *sv = NULL;
+    char *name = strtok_r(line, " \t\n\r", &sv);
+    char *val = strtok_r(NULL, " \t\n\r", &sv);
     if (!name || !val) {
       rc = sip_fail(SIPNET_GPU_ERR_INPUT_FILE, "reading parameter file: missing value for %s", name ? name : "?");
       break;
@@ -231,8 +233,8 @@ int sip_read_clim(const char *path, int gddFlag, int quiet, sip_site_data *s) {
   /* 12 columns, or the legacy 14 (location first, soilWetness last), sipnet.c:157-178 */
   int nf = 0;
   {
-    char *copy = strdup(first);
-    for (char *t = strtok(copy, " \t\n\r"); t; t = strtok(NULL, " \t\n\r")) ++nf;
+    char *copy = strdup(first), *sv = NULL;
+    for (char *t = strtok_r(copy, " \t\n\r", &sv); t; t = strtok_r(NULL, " \t\n\r", &sv)) ++nf;
     free(copy);
   }
   int legacy;

@@ -264,7 +264,7 @@ static void *writer_main(void *argp) {
     if (rc == 0) {
       rc = sip_write_state_block(files, count, wp->nsteps + m0, wp->year + m0, wp->day + m0, wp->time + m0, wp->buf + m0,
                                  wp->T * wp->M, wp->M);
-      if (rc) bad = wp->paths + (size_t)m0 * SIP_STATE_PATH_MAX;
+      if (rc) bad = wp->paths + (size_t)m0 * SIP_STATE_PATH_MAX; /* (the block's first member names it) */
     }
     for (int k = 0; k < count; ++k)
       if (files[k] && fclose(files[k]) != 0 && rc == 0) {

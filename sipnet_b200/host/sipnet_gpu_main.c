@@ -21,9 +21,11 @@
  */
 #define _GNU_SOURCE
 #include <libgen.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "sip_host.h"
 
@@ -94,6 +96,108 @@ static int read_site_list(const char *path, site_job **jobs, int64_t *njobs) {
   return 0;
 }
 
+/* ---- inputs of a many-site launch on all host cores: initModel() + initEvents() per site ----
+ * (10 000 ten-year sites are 73 million .clim lines: two minutes on one thread next to a one-second run.)
+ * Sites are handed out in order; the first failing site IN ORDER decides the exit code, like a sequential pass:
+ * after a failure no NEW site is started, the ones before it were all started already. */
+typedef struct {
+  site_job *jobs;
+  int64_t njobs, M;
+  const sip_context *ctx;
+  double *params; /* [80][M] */
+  int32_t *memberSite;
+  sipnet_gpu_site *views;
+  int *rcs;            /* [njobs] */
+  char (*msgs)[512];   /* [njobs] */
+  int64_t next;
+  int failed;
+  pthread_mutex_t lock;
+} loader_pool;
+
+static int load_site(loader_pool *lp, int64_t s) {
+  site_job *job = &lp->jobs[s];
+  const sip_context *ctx = lp->ctx;
+  const int64_t M = lp->M;
+  char name[SIP_NAME_MAX + 16];
+  int rc;
+  for (int64_t k = 0; k < job->nmembers; ++k) {
+    double one[SIPNET_GPU_NPARAMS];
+    const int64_t m = job->member0 + k;
+    if ((rc = sip_read_params(job->paramFiles[k], &ctx->flags, ctx->quiet || m > 0, one))) return rc;
+    for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) lp->params[(size_t)p * (size_t)M + (size_t)m] = one[p];
+    lp->memberSite[m] = (int32_t)s;
+  }
+  snprintf(name, sizeof name, "%s.clim", job->prefix);
+  if ((rc = sip_read_clim(name, ctx->flags.gdd, ctx->quiet || s > 0, &job->data))) return rc;
+  if (ctx->flags.events) {
+    double first[SIPNET_GPU_NPARAMS];
+    for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) first[p] = lp->params[(size_t)p * (size_t)M + (size_t)job->member0];
+    snprintf(name, sizeof name, "%s.in", job->eventsPrefix);
+    if ((rc = sip_read_events(name, &ctx->flags, first, ctx->quiet || s > 0, &job->data))) return rc;
+  }
+  sip_site_view(&job->data, &lp->views[s]);
+  return 0;
+}
+
+static void *loader_main(void *argp) {
+  loader_pool *lp = (loader_pool *)argp;
+  for (;;) {
+    pthread_mutex_lock(&lp->lock);
+    const int64_t s = (lp->failed || lp->next >= lp->njobs) ? -1 : lp->next++;
+    pthread_mutex_unlock(&lp->lock);
+    if (s < 0) break;
+    const int rc = load_site(lp, s);
+    if (rc) {
+      snprintf(lp->msgs[s], sizeof lp->msgs[s], "%s", sip_host_error()); /* (this thread's message) */
+      pthread_mutex_lock(&lp->lock);
+      lp->rcs[s] = rc;
+      lp->failed = 1;
+      pthread_mutex_unlock(&lp->lock);
+    }
+  }
+  return NULL;
+}
+
+/* returns 0, or the exit code of the first failing site with its message in *msg (static storage) */
+static int load_sites(site_job *jobs, int64_t njobs, int64_t M, const sip_context *ctx, double *params, int32_t *memberSite,
+                      sipnet_gpu_site *views, const char **msg) {
+  static char firstMsg[512];
+  loader_pool lp;
+  memset(&lp, 0, sizeof lp);
+  lp.jobs = jobs, lp.njobs = njobs, lp.M = M, lp.ctx = ctx, lp.params = params, lp.memberSite = memberSite, lp.views = views;
+  lp.rcs = (int *)calloc((size_t)njobs, sizeof *lp.rcs);
+  lp.msgs = (char(*)[512])calloc((size_t)njobs, sizeof *lp.msgs);
+  if (!lp.rcs || !lp.msgs) {
+    *msg = "memory allocation failure";
+    return SIPNET_GPU_ERR_INTERNAL;
+  }
+  pthread_mutex_init(&lp.lock, NULL);
+  long want = sysconf(_SC_NPROCESSORS_ONLN);
+  const char *env = getenv("SIPNET_GPU_READER_THREADS");
+  if (env && atoi(env) > 0) want = atoi(env);
+  if (want > 64) want = 64;
+  if ((int64_t)want > njobs) want = (long)njobs;
+  pthread_t threads[64];
+  int started = 0;
+  for (long i = 1; i < want; ++i) { /* this thread is a worker too; a thread that cannot be started is simply absent */
+    if (pthread_create(&threads[started], NULL, loader_main, &lp) != 0) break;
+    ++started;
+  }
+  loader_main(&lp);
+  for (int i = 0; i < started; ++i) pthread_join(threads[i], NULL);
+  pthread_mutex_destroy(&lp.lock);
+  int rc = 0;
+  for (int64_t s = 0; s < njobs && rc == 0; ++s)
+    if (lp.rcs[s]) {
+      rc = lp.rcs[s];
+      snprintf(firstMsg, sizeof firstMsg, "%s", lp.msgs[s]);
+      *msg = firstMsg;
+    }
+  free(lp.rcs);
+  free(lp.msgs);
+  return rc;
+}
+
 int main(int argc, char **argv) {
   sip_context ctx;
   sip_context_init(&ctx);
@@ -151,25 +255,39 @@ int main(int argc, char **argv) {
   double *params = (double *)calloc((size_t)SIPNET_GPU_NPARAMS * (size_t)M, sizeof(double)); /* [80][M] */
   int32_t *memberSite = (int32_t *)malloc((size_t)M * sizeof *memberSite);
   sipnet_gpu_site *views = (sipnet_gpu_site *)calloc((size_t)njobs, sizeof *views);
+  {
+    const char *msg = "";
+    if ((rc = load_sites(jobs, njobs, M, &ctx, params, memberSite, views, &msg))) return die(rc, msg);
+  }
+  if (getenv("SIPNET_GPU_TRACE_INPUTS")) { /* FNV-1a over everything the loaders produced (stderr; tests compare thread counts) */
+    uint64_t hsh = 1469598103934665603ull;
+#define SIP_MIX(ptr, nbytes)                                                   \
+    for (size_t i_ = 0; i_ < (size_t)(nbytes); ++i_) hsh = (hsh ^ ((const unsigned char *)(ptr))[i_]) * 1099511628211ull
+    SIP_MIX(params, sizeof(double) * SIPNET_GPU_NPARAMS * (size_t)M);
+    SIP_MIX(memberSite, sizeof(int32_t) * (size_t)M);
+    for (int64_t s = 0; s < njobs; ++s) {
+      const sip_site_data *d = &jobs[s].data;
+      const double *cols[] = {d->time, d->length, d->tair, d->tsoil, d->par, d->precip, d->vpd, d->vpdSoil, d->vPress, d->wspd, d->gdd};
+      SIP_MIX(&d->nsteps, sizeof d->nsteps);
+      SIP_MIX(d->year, sizeof(int32_t) * (size_t)d->nsteps);
+      SIP_MIX(d->day, sizeof(int32_t) * (size_t)d->nsteps);
+      for (size_t c = 0; c < sizeof cols / sizeof cols[0]; ++c)
+        if (cols[c]) SIP_MIX(cols[c], sizeof(double) * (size_t)d->nsteps);
+      SIP_MIX(&d->nevents, sizeof d->nevents);
+      for (int64_t e = 0; e < d->nevents; ++e) { /* field by field: the struct has padding */
+        SIP_MIX(&d->events[e].year, sizeof d->events[e].year);
+        SIP_MIX(&d->events[e].day, sizeof d->events[e].day);
+        SIP_MIX(&d->events[e].type, sizeof d->events[e].type);
+        SIP_MIX(&d->events[e].method, sizeof d->events[e].method);
+        SIP_MIX(d->events[e].p, sizeof d->events[e].p);
+      }
+    }
+#undef SIP_MIX
+    fprintf(stderr, "[TRACE  ] inputs: %lld site(s), %lld member(s), checksum %016llx\n", (long long)njobs, (long long)M,
+            (unsigned long long)hsh);
+  }
   for (int64_t s = 0; s < njobs; ++s) {
-    site_job *job = &jobs[s];
-    char name[SIP_NAME_MAX + 16];
-    for (int64_t k = 0; k < job->nmembers; ++k) {
-      double one[SIPNET_GPU_NPARAMS];
-      const int64_t m = job->member0 + k;
-      if ((rc = sip_read_params(job->paramFiles[k], &ctx.flags, ctx.quiet || m > 0, one))) return die(rc, sip_host_error());
-      for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) params[(size_t)p * (size_t)M + (size_t)m] = one[p];
-      memberSite[m] = (int32_t)s;
-    }
-    snprintf(name, sizeof name, "%s.clim", job->prefix);
-    if ((rc = sip_read_clim(name, ctx.flags.gdd, ctx.quiet || s > 0, &job->data))) return die(rc, sip_host_error());
-    if (ctx.flags.events) {
-      double first[SIPNET_GPU_NPARAMS];
-      for (int p = 0; p < SIPNET_GPU_NPARAMS; ++p) first[p] = params[(size_t)p * (size_t)M + (size_t)job->member0];
-      snprintf(name, sizeof name, "%s.in", job->eventsPrefix);
-      if ((rc = sip_read_events(name, &ctx.flags, first, ctx.quiet || s > 0, &job->data))) return die(rc, sip_host_error());
-    }
-    sip_site_view(&job->data, &views[s]);
+    const site_job *job = &jobs[s];
     if (job->data.nsteps > Tmax) Tmax = job->data.nsteps;
     if (job->data.nevents > maxEvents) maxEvents = job->data.nevents;
     if (job->data.nsteps > 0) {

@@ -189,3 +189,57 @@ def test_readers_agree_with_live_reference(lib, refshim, smoke_dir):
         for k in A.CLIM_COLS:
             assert np.array_equal(mine[k], ref.clim[k])
         assert np.array_equal(refshim.read_params(os.path.join(d, "sipnet.param"), g.flags), g.params)
+
+
+def test_driver_loads_many_sites_identically_on_any_thread_count(smoke_dir, tmp_path):
+    """The drop-in driver reads the sites of a --site-list launch on several host threads (the readers are
+    re-entrant).  SIPNET_GPU_TRACE_INPUTS prints a checksum of everything loaded: it must not depend on the thread
+    count, and the first failing site in list order decides the exit code.  Without a GPU the driver stops at
+    sipnet_gpu_init (exit 100), after the inputs: that is all this test needs."""
+    import shutil
+    import subprocess
+    if not os.path.exists(DRIVER):
+        pytest.skip("sipnet_gpu driver not built")
+    src = os.path.join(smoke_dir, "russell_2")
+    work = str(tmp_path / "multi")
+    os.makedirs(work)
+    shutil.copy(os.path.join(src, "sipnet.in"), work)
+    clim = open(os.path.join(src, "sipnet.clim")).read().splitlines()
+    base = open(os.path.join(src, "sipnet.param")).read()
+    sites = []
+    for n in range(10):
+        d = os.path.join(work, f"site{n}")
+        os.makedirs(d)
+        open(os.path.join(d, "sipnet.clim"), "w").write("\n".join(clim[: 400 + 150 * n]) + "\n")   # ragged lengths
+        open(os.path.join(d, "sipnet.param"), "w").write(base.replace("soilWHC 12", f"soilWHC {9 + n}.5"))
+        shutil.copy(os.path.join(src, "events.in"), d)
+        sites.append(d)
+    members = []
+    for k in range(3):
+        p = os.path.join(sites[4], f"m{k}.param")
+        open(p, "w").write(base.replace("aMax 53.2895432752984", f"aMax {40 + k}.0"))
+        members.append(p)
+    open(os.path.join(sites[4], "members.txt"), "w").write("\n".join(members) + "\n")
+    with open(os.path.join(work, "sites.txt"), "w") as f:
+        for n, d in enumerate(sites):
+            f.write(f"{d}/sipnet {d}/events {d}/members.txt\n" if n == 4 else f"{d}/sipnet\n")
+
+    def run(threads):
+        env = dict(os.environ, SIPNET_GPU_TRACE_INPUTS="1", SIPNET_GPU_READER_THREADS=str(threads),
+                   CUDA_VISIBLE_DEVICES="")                     # stop at init on a GPU box too
+        r = subprocess.run([DRIVER, "-i", "sipnet.in", "--quiet", "--no-do-main-output", "--site-list", "sites.txt"], cwd=work,
+                           capture_output=True, text=True, env=env)
+        trace = [l for l in r.stderr.splitlines() if l.startswith("[TRACE  ] inputs:")]
+        return r.returncode, trace, r.stdout
+
+    rc1, t1, _ = run(1)
+    assert rc1 == 100 and len(t1) == 1 and "10 site(s), 12 member(s)" in t1[0], (rc1, t1)
+    for threads in (2, 4, 7):
+        for _ in range(3):
+            assert run(threads) == (rc1, t1, run(1)[2])
+    # two broken sites: the first one in list order decides, whatever the thread count
+    open(os.path.join(sites[6], "sipnet.clim"), "w").write("\n".join(clim[:50] + ["2016 x y z"] + clim[50:90]) + "\n")
+    os.remove(os.path.join(sites[2], "sipnet.param"))
+    for threads in (1, 4, 7):
+        rc, trace, out = run(threads)
+        assert rc == 6 and not trace and "site2/sipnet.param" in out, (threads, rc, out)
