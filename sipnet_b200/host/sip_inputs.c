@@ -216,6 +216,94 @@ static int site_reserve(sip_site_data *s, int64_t cap) {
   return 0;
 }
 
+/* ---- fast path of the .clim reader ---------------------------------------------------------------------------
+ * readClimData() reads the file with fscanf("%d %d %lf ... %lf") -- a token stream in which line ends are just
+ * white space.  Ten-year half-daily sites are 7 306 records of 12 numbers, a 10 000-site launch 73 million records,
+ * and glibc's scanf needs ~150 ns per number.  A record that sits on ONE line as exactly 12 plainly written numbers
+ * (the only way the files are ever written) is converted directly; at the first line that is anything else -- fewer
+ * or more tokens, a token scanf would split or reject, "nan", hex floats, an over-long line -- the file is
+ * repositioned to the start of that line and the fscanf loop carries on from there, so every irregular file is read
+ * exactly as before.
+ * Numbers: "%d" of [+-]digits (at most 9) is that integer; "%lf" of [+-]digits[.digits][e[+-]digits] is strtod's
+ * correctly rounded value, which for at most 15 significant digits and a decimal exponent within +-22 is ONE
+ * correctly rounded multiplication or division of two exactly representable numbers (Clinger's fast path);
+ * everything else goes through strtod itself. */
+static const double kExact10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+static int is_blank_char(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+/* [+-]digits{1,9} followed by white space; returns the end of the token or NULL */
+static const char *plain_int(const char *p, int *out) {
+  int neg = 0, n = 0;
+  long v = 0;
+  if (*p == '+' || *p == '-') neg = (*p++ == '-');
+  while (*p >= '0' && *p <= '9' && n < 10) v = v * 10 + (*p++ - '0'), ++n;
+  if (n == 0 || n > 9 || !is_blank_char(*p)) return NULL;
+  *out = (int)(neg ? -v : v);
+  return p;
+}
+
+/* [+-](digits[.digits*] | .digits)[(e|E)[+-]digits] followed by white space; returns the end of the token or NULL */
+static const char *plain_double(const char *p, double *out) {
+  const char *start = p;
+  int neg = 0;
+  if (*p == '+' || *p == '-') neg = (*p++ == '-');
+  uint64_t mant = 0;
+  int ndig = 0, nsig = 0, dec = 0; /* digits seen, significant digits kept in mant, digits after the point */
+  while (*p >= '0' && *p <= '9') {
+    if (nsig < 19 && (mant != 0 || *p != '0')) mant = mant * 10u + (uint64_t)(*p - '0'), ++nsig;
+    else if (mant != 0 || *p != '0') nsig = 100; /* more digits than the shortcut handles */
+    ++p, ++ndig;
+  }
+  if (*p == '.') {
+    ++p;
+    while (*p >= '0' && *p <= '9') {
+      if (nsig < 19 && (mant != 0 || *p != '0')) mant = mant * 10u + (uint64_t)(*p - '0'), ++nsig;
+      else if (mant != 0 || *p != '0') nsig = 100;
+      ++p, ++ndig, ++dec;
+    }
+  }
+  if (ndig == 0) return NULL;
+  int e10 = 0;
+  if (*p == 'e' || *p == 'E') {
+    const char *q = p + 1;
+    int eneg = 0, en = 0, ev = 0;
+    if (*q == '+' || *q == '-') eneg = (*q++ == '-');
+    while (*q >= '0' && *q <= '9' && en < 5) ev = ev * 10 + (*q++ - '0'), ++en;
+    if (en == 0 || en > 4 || (*q >= '0' && *q <= '9')) return NULL; /* "1e", "1e+": scanf's business */
+    e10 = eneg ? -ev : ev;
+    p = q;
+  }
+  if (!is_blank_char(*p)) return NULL;
+  e10 -= dec;
+  if (nsig <= 15 && e10 >= -22 && e10 <= 22) { /* mant < 10^15 < 2^53 and 10^|e10| are exact */
+    const double m = (double)mant;
+    const double v = e10 < 0 ? m / kExact10[-e10] : m * kExact10[e10];
+    *out = neg ? -v : v;
+    return p;
+  }
+  char *endp = NULL;
+  const double v = strtod(start, &endp);
+  if (endp != p) return NULL;
+  *out = v;
+  return p;
+}
+
+/* one record on one line: 12 plain numbers and nothing else.  1 = converted, 0 = not a plain record line */
+static int plain_clim_line(const char *p, int *year, int *day, double v[10]) {
+  while (*p == ' ' || *p == '\t') ++p;
+  if (!(p = plain_int(p, year))) return 0;
+  while (*p == ' ' || *p == '\t') ++p;
+  if (!(p = plain_int(p, day))) return 0;
+  for (int k = 0; k < 10; ++k) {
+    while (*p == ' ' || *p == '\t') ++p;
+    if (!(p = plain_double(p, &v[k]))) return 0;
+  }
+  while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
+  return *p == '\n' || *p == '\0';
+}
+
 int sip_read_clim(const char *path, int gddFlag, int quiet, sip_site_data *s) {
   memset(s, 0, sizeof *s);
   FILE *in = fopen(path, "r");
@@ -266,6 +354,8 @@ int sip_read_clim(const char *path, int gddFlag, int quiet, sip_site_data *s) {
   }
   int64_t cap = 0, n = 0;
   int rc = 0;
+  int plain = !legacy && getenv("SIPNET_HOST_SCANF_CLIM") == NULL; /* (the variable forces the fscanf loop: tests) */
+  long lineStart = plain ? ftell(in) : -1; /* just behind the first line */
   while (status != EOF) {
     if (n == cap) {
       cap = cap ? cap * 2 : 8192;
@@ -298,6 +388,27 @@ int sip_read_clim(const char *path, int gddFlag, int quiet, sip_site_data *s) {
       s->gdd[n] = 0.0;
     }
     ++n;
+    if (plain) { /* the next record, if it is one plain line (see plain_clim_line) */
+      char line[1024];
+      const long at = lineStart; /* file offset of this line: the first line's end plus the lines converted since */
+      double v[10];
+      int got = 0;
+      if (at >= 0 && fgets(line, sizeof line, in) != NULL) {
+        const size_t len = strlen(line); /* (a line with an embedded NUL looks cut short and is left to fscanf) */
+        if (len > 0 && line[len - 1] == '\n' && plain_clim_line(line, &year, &day, v)) {
+          time = v[0], length = v[1], tair = v[2], tsoil = v[3], par = v[4], precip = v[5], vpd = v[6], vpdSoil = v[7],
+          vPress = v[8], wspd = v[9];
+          lineStart += (long)len;
+          got = 1;
+        }
+      }
+      if (got) continue; /* status is still `expected` */
+      plain = 0;         /* anything else, the end of the file included: fscanf from the start of that line on */
+      if (at < 0 || fseek(in, at, SEEK_SET) != 0) {
+        rc = sip_fail(SIPNET_GPU_ERR_INPUT_FILE, "while reading climate file: cannot reposition %s", path);
+        break;
+      }
+    }
     if (legacy)
       status = fscanf(in, "%d %d %d %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf", &loc, &year, &day, &time, &length, &tair,
                       &tsoil, &par, &precip, &vpd, &vpdSoil, &vPress, &wspd, &wet);

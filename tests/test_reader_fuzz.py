@@ -246,3 +246,84 @@ def test_config_parser_agrees_with_reference_on_mutants(smoke_dir, tmp_path):
             rejected += 1
             assert codes["ours"] == codes["ref"], (n, codes, lines, extra)
     assert accepted > 10 and rejected > 3
+
+
+def _read_clim_arrays(lib, path, gdd):
+    from host_util import SiteDataC
+    s = SiteDataC()
+    rc = lib.sip_read_clim(path.encode(), gdd, 1, C.byref(s))
+    out = None
+    if rc == 0:
+        n = s.nsteps
+        out = [np.ctypeslib.as_array(s.year, (n,)).copy(), np.ctypeslib.as_array(s.day, (n,)).copy()]
+        out += [np.ctypeslib.as_array(getattr(s, k), (n,)).copy() for k in A.CLIM_COLS]
+        lib.sip_site_free(C.byref(s))
+    return rc, out, lib.sip_host_error()
+
+
+NUMBER_SPELLINGS = ["0", "-0", "+0", "0.0", "-0.000", "5", "+5", "-5", "5.", ".5", "-.5", "0.5", "12.345", "1e3", "1E3", "1e+3",
+                    "1.5e-3", "-2.5E-07", "123456789012345", "1234567890123456", "0.000000000000001", "9007199254740993",
+                    "1e22", "1e23", "1e-22", "1e-23", "123456789012345e7", "123456789012345e8", "4.9e-324", "1e-400",
+                    "1e400", "1.7976931348623157e308", "0.1", "0.2", "0.3", "2.675", "1.005", "8.41e21", "00012.50",
+                    "3.14159265358979323846264338327950288", "1e0005", "1e00005", "0.30000000000000004", "100000000000000000000000"]
+
+
+def test_clim_fast_path_equals_the_scanf_loop(tmp_path, monkeypatch):
+    """The one-record-per-line fast path of sip_read_clim against its own fscanf loop (SIPNET_HOST_SCANF_CLIM): same
+    exit code, message and bits on files that spell numbers every way the fast path accepts or refuses, with
+    records split over lines, glued lines, blank lines, CR LF, tabs, trailing blanks, a missing final newline, an
+    over-long line, and seeded mutants."""
+    lib = host_lib()
+    rng = random.Random(20260117)
+
+    def record(year, day):
+        return [str(year), str(day)] + [rng.choice(NUMBER_SPELLINGS) if rng.random() < 0.5
+                                        else repr(round(rng.uniform(-50, 3000), rng.randrange(0, 12))) for _ in range(10)]
+
+    def both(text, gdd):
+        path = str(tmp_path / "f.clim")
+        with open(path, "w", newline="") as f:
+            f.write(text)
+        monkeypatch.delenv("SIPNET_HOST_SCANF_CLIM", raising=False)
+        fast = _read_clim_arrays(lib, path, gdd)
+        monkeypatch.setenv("SIPNET_HOST_SCANF_CLIM", "1")
+        slow = _read_clim_arrays(lib, path, gdd)
+        monkeypatch.delenv("SIPNET_HOST_SCANF_CLIM", raising=False)
+        assert fast[0] == slow[0] and fast[2] == slow[2], (fast[0], slow[0], fast[2], slow[2])
+        if fast[0] == 0:
+            for a, b in zip(fast[1], slow[1]):
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        return fast[0]
+
+    accepted = 0
+    for trial in range(120):
+        recs = [record(2016, 1 + i // 2) for i in range(rng.randrange(1, 60))]
+        lines = [" ".join(r) + "\n" for r in recs]
+        style = trial % 12
+        if style == 1:
+            lines = ["\t".join(r) + "  \t\n" for r in recs]                      # tabs, trailing blanks
+        elif style == 2:
+            lines = [" ".join(r) + "\r\n" for r in recs]                         # CR LF
+        elif style == 3 and len(recs) > 2:
+            k = rng.randrange(1, len(recs))
+            lines[k] = " ".join(recs[k][:5]) + "\n" + " ".join(recs[k][5:]) + "\n"  # one record over two lines
+        elif style == 4 and len(recs) > 2:
+            k = rng.randrange(1, len(recs) - 1)
+            lines[k] = lines[k].rstrip("\n") + " " + lines.pop(k + 1)           # two records on one line
+        elif style == 5:
+            lines.insert(rng.randrange(1, len(lines) + 1), rng.choice(["\n", "  \n", "\t\r\n"]))
+        elif style == 6:
+            lines[-1] = lines[-1].rstrip("\n")                                   # no final newline
+        elif style == 7 and len(recs) > 1:
+            k = rng.randrange(1, len(recs))
+            lines[k] = " " * 1100 + lines[k]                                     # longer than the line buffer
+        elif style == 8 and len(recs) > 1:
+            k = rng.randrange(1, len(recs))
+            tok = recs[k][:]
+            tok[rng.randrange(12)] = rng.choice(GARBAGE + ["1e", "1e+", "0x1p3", "1d5", "5.5.5", "--5", "1_000", "2016.5"])
+            lines[k] = " ".join(tok) + "\n"
+        elif style >= 9:
+            for _ in range(rng.randrange(1, 4)):
+                lines = mutate(lines, rng, keep_first=0)
+        accepted += both("".join(lines), trial % 2) == 0
+    assert 40 < accepted < 120          # both outcomes are exercised
