@@ -589,6 +589,46 @@ def section_c2(args, D: Dist, lib, site):
             "note": "4096 members = 128 warps on 592 warp schedulers: latency-bound by construction (round-1 headline)"}
 
 
+def host_writer_rate(T: int, members: int = 64) -> dict:
+    """Rows/s of the drop-in driver's main-output writer (host/sip_output.c: printf-free byte-identical sipnet.out rows,
+    member blocks on all host cores) on this box -- CPU only, beside the reference-with-text-output baseline: it is what
+    a many-member launch with the main output on spends after the run."""
+    lib = C.CDLL(os.path.join(ROOT, "sipnet_b200", "libsipnet_host.so"))
+    lib.sip_write_state_files.restype = C.c_int
+    lib.sip_write_state_files.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_int32)),
+                                          C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_double)), C.c_int64,
+                                          C.POINTER(C.c_double), C.c_int, C.c_int]
+    path_max = 256 + 32                                            # SIP_STATE_PATH_MAX
+    nout = 32
+    rng = np.random.default_rng(5)
+    scale = 10.0 ** np.array([4, 2, 0, 4, 3, 2, 3, 1, 0, 1] + [0] * 10 + [-1, -1, 0, 2, 1, 0, -4, -3, -3, -2, -3, 2], float)
+    buf = np.ascontiguousarray((rng.uniform(0, 1, (T, members, nout)) * scale).transpose(2, 0, 1))   # [col][T][M]
+    year = np.full(T, 2015, np.int32)
+    day = (np.arange(T) // 2 % 365 + 1).astype(np.int32)
+    tm = np.where(np.arange(T) % 2 == 0, 0.0, 12.0)
+    ns = np.full(members, T, np.int64)
+    yp = (C.POINTER(C.c_int32) * members)(*[year.ctypes.data_as(C.POINTER(C.c_int32))] * members)
+    dp = (C.POINTER(C.c_int32) * members)(*[day.ctypes.data_as(C.POINTER(C.c_int32))] * members)
+    tp = (C.POINTER(C.c_double) * members)(*[tm.ctypes.data_as(C.POINTER(C.c_double))] * members)
+    with tempfile.TemporaryDirectory() as td:
+        paths = C.create_string_buffer(members * path_max)
+        for m in range(members):
+            name = os.path.join(td, f"w.out.{m}").encode()
+            paths[m * path_max: m * path_max + len(name)] = name
+        t0 = time.perf_counter()
+        rc = lib.sip_write_state_files(paths, members, ns.ctypes.data_as(C.POINTER(C.c_int64)), yp, dp, tp, T,
+                                       buf.ctypes.data_as(C.POINTER(C.c_double)), 1, 0)
+        dt = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(os.path.join(td, f"w.out.{m}")) for m in range(members))
+    if rc != 0:
+        raise RuntimeError(f"sip_write_state_files returned {rc}")
+    return {"value": members * T / dt, "unit": "rows/s (one row = one member-timestep of sipnet.out text)",
+            "text_gb_s": nbytes / dt / 1e9, "threads": min(os.cpu_count() or 1, 64, (members + 7) // 8),
+            "sample": f"{members} members x {T} steps into {nbytes / 1e6:.0f} MB of text in a temporary directory",
+            "what": "sip_write_state_files (host C, no GPU work): the writer behind the drop-in driver's per-member "
+                    "main output; compare with cpu_baseline_text_output, the reference writing the same rows"}
+
+
 def run_ours(args):
     from sipnet_b200 import _abi as A, api, synth
     D = Dist()
@@ -685,6 +725,10 @@ def run_ours(args):
                     vt, st = cpu.sample(max(1, min(24, M // cores)), text_dir=td)
                 line["cpu_baseline_text_output"] = {"value": vt, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": st}
             cpu.close()
+            try:   # informational, CPU only: never allowed to cost the bench line
+                line["host_writer"] = host_writer_rate(T)
+            except Exception as exc:
+                line["host_writer"] = {"error": str(exc)[:200]}
         print(json.dumps(line), flush=True)
     D.close()
 
