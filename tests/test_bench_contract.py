@@ -71,3 +71,11 @@ def test_both_arms_share_one_config_object():
     assert a == bench.bench_config(args, 7306) and set(a) >= {"workload", "members_per_gpu", "model_steps"}
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert src.count('"config": bench_config(args, T)') == 2      # our arm and the reference arm
+
+
+def test_host_writer_section_runs_without_a_gpu():
+    """bench.py's informational `host_writer` section is host C only (the drop-in driver's main-output writer)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.host_writer_rate(300, members=19)
+    assert r["value"] > 0 and r["text_gb_s"] > 0 and r["threads"] >= 1 and "19 members x 300 steps" in r["sample"]
